@@ -1,0 +1,270 @@
+/*
+ * spk.h — C ABI of libspk.so, the sm_100a implementation of SubPhaser's k-mer hot path.
+ *
+ * The reference (zhangrengang/SubPhaser v1.2.7) is pure Python and has no FFI layer; its boundary for
+ * this path is the module surface `subphaser/__main__.py:11-21` imports.  The Python modules in
+ * `subphaser_b200/` mirror that surface and call the entry points below through ctypes.  Each entry
+ * point cites the reference code (path:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative SPK_E* code on failure; the message of the
+ *     last failure on the calling thread is returned by spk_last_error();
+ *   - pointers named d_* are CALLER-OWNED DEVICE pointers (e.g. torch.Tensor.data_ptr()); pointers
+ *     named h_* are host pointers; sizes are in elements unless the name says bytes;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued
+ *     on it and nothing synchronises unless stated ("syncs");
+ *   - the library allocates no device memory: scratch is passed in (`*_workspace_bytes` tell how much);
+ *   - no global state except the thread-local error string and cached device attributes.
+ */
+#ifndef SPK_H
+#define SPK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_OK 0
+#define SPK_EINVAL (-1)   /* bad argument */
+#define SPK_ECUDA (-2)    /* CUDA runtime error */
+#define SPK_ECAP (-3)     /* caller-supplied buffer too small */
+#define SPK_EOVERFLOW (-4) /* counter overflow / table full */
+
+const char* spk_last_error(void);
+int spk_version(void);
+/* Number of SMs of the current device (persistent grids are sized from it). syncs: no. */
+int spk_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  FASTA bytes -> 2-bit packed bases + validity mask
+ * replaces: the `cat/zcat f | jellyfish count ... /dev/stdin` ingest of Jellyfish.py:697 and the
+ *           SeqIO.parse + str(rc.seq).upper() of Seqs.py:121-139.
+ * Semantics: header lines (from '>' at a line start to the next '\n') and '\n' / '\r' are dropped;
+ * every other byte is one base.  A/C/G/T (either case) -> code 0/1/2/3 with valid=1; any other byte ->
+ * code 0 with valid=0 (it breaks every k-mer window that covers it, as jellyfish does).  Every header
+ * other than one at byte 0 additionally emits ONE invalid separator base so that k-mers never span
+ * records.  Base i lives in bits [2*(i%16), 2*(i%16)+2) of d_packed[i/16]; its validity in bit (i%32)
+ * of d_valid[i/32].  Both arrays must be zero-padded by the caller up to spk_packed_words(cap)/
+ * spk_valid_words(cap) — the kernels write every word of that extent.
+ * d_info (uint64[4], device): [0] = number of bases emitted, [1] = number of valid bases,
+ *                             [2] = number of records (headers seen), [3] = reserved.
+ * ---------------------------------------------------------------------------------------------- */
+size_t spk_packed_words(uint64_t n_bases); /* uint32 words incl. tile padding */
+size_t spk_valid_words(uint64_t n_bases);
+size_t spk_pack_workspace_bytes(size_t nbytes);
+int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d_packed, uint32_t* d_valid,
+                   uint64_t cap_bases, uint64_t* d_info, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  canonical k-mer counting of one chromosome
+ * replaces: `jellyfish count -m K -s 100000000 --canonical` (Jellyfish.py:697; jellyfish 2.2.10).
+ * Every window of k valid bases is counted under min(kmer, revcomp(kmer)) (A<C<G<T, first base most
+ * significant), exactly, into a caller-zeroed open-addressed table:
+ *   layout 0 (packed): one uint64 per slot, (canon << cbits) | count, cbits = 64-2k; used when
+ *                      n_bases < 2^cbits so the count field cannot overflow;
+ *   layout 1 (split):  uint64 key[slots] (empty = ~0) followed by uint32 count[slots].
+ * spk_count_layout picks the layout from an upper bound of the chromosome length (pass the SAME
+ * layout to every call on one table); spk_count_table_bytes the recommended size (load <= 0.7 even
+ * if every k-mer is distinct).  The table must be initialised with spk_count_table_init.
+ * d_stats (uint64[4], device, accumulated — zero it first): [0] valid k-mer occurrences inserted,
+ *   [1] failed inserts (table full; must be 0), [2..3] reserved.
+ * 1 <= k <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+int spk_count_layout(uint64_t n_bases, int k);            /* 0 or 1 for a chromosome of <= n_bases */
+size_t spk_count_table_bytes(uint64_t n_bases, int k);     /* recommended table size */
+uint64_t spk_count_table_slots(size_t table_bytes, int layout);
+int spk_count_table_init(void* d_table, size_t table_bytes, int k, int layout, void* stream);
+int spk_count_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                        void* d_table, size_t table_bytes, int layout, uint64_t* d_stats,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  table scan: `jellyfish dump -c -L lower_count` + the dump parse of Jellyfish.py:90-98
+ * spk_table_stats: one pass over the table.  d_out (uint64[4]): [0] distinct k-mers, [1] k-mers with
+ *   count >= lower_count, [2] sum of those counts (this is `lengths[i]`, Jellyfish.py:97,449),
+ *   [3] sum of all counts.  d_block_counts (uint32[3*spk_table_scan_blocks()+2]) receives the per-block
+ *   number of surviving entries; spk_table_extract turns it into offsets and writes the survivors in
+ *   slot order (deterministic for a given table) as d_keys[i] (canonical k-mer, 2 bits/base, first
+ *   base most significant) and d_counts[i].  d_histo (optional, uint64[histo_len], zeroed by the
+ *   caller) accumulates the count histogram like `jellyfish histo -h` (counts >= histo_len-1 go to
+ *   the last bin).
+ * ---------------------------------------------------------------------------------------------- */
+int spk_table_scan_blocks(void);
+int spk_table_stats(const void* d_table, size_t table_bytes, int k, int layout, uint32_t lower_count,
+                    uint64_t* d_out, uint32_t* d_block_counts, uint64_t* d_histo, uint32_t histo_len,
+                    void* stream);
+int spk_table_extract(const void* d_table, size_t table_bytes, int k, int layout, uint32_t lower_count,
+                      uint32_t* d_block_counts, uint64_t* d_keys, uint32_t* d_counts, uint64_t cap,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3b/K4  union of the per-chromosome dumps -> count matrix -> differential filter
+ * replaces: JellyfishDumps.to_matrix (Jellyfish.py:439-460) and .filter/_filter_kmer
+ *           (Jellyfish.py:462-512, 611-648).
+ * The union table is an open-addressed map canonical k-mer -> row id.  d_ukeys (uint64[uslots]) must
+ * be filled with 0xFF bytes and d_urows (uint32[uslots]) needs no initialisation; *d_nrows (uint32,
+ * zeroed) is the row counter.  spk_union_insert adds keys (rows are numbered in arrival order);
+ * spk_matrix_fill stores counts[i] into d_matrix[row(keys[i]) * ncol + col] (matrix zeroed by caller;
+ * row-major uint32 [nrows x ncol]) and d_row_keys[row] = key.
+ *
+ * spk_filter_differential evaluates _filter_kmer for every row (outfig is always set by
+ * __main__.py:421, so the fold test runs before the frequency gate):
+ *   tot = sum(row); for every homoeologous set with >= 2 groups: f_g = sum(count)/sum(length) over the
+ *   group's columns (IEEE fp64), sort descending, pass if f[0]/(f[baseline]+1e-20) >= min_fold
+ *   (baseline < 0 indexes from the end); include/all < ratio -> reject; then min_freq <= tot <=
+ *   max_freq.  d_flags[row]: bit0 = fold test passed, bit1 = kept (fold && frequency gate).
+ * Config arrays (device int32): set_off[n_sets+1] -> group range, grp_off[n_groups+1] -> member range,
+ * members[] = column indices.  Sets with < 2 groups are skipped as in Jellyfish.py:622-623.
+ * d_counters (uint64[4], zeroed): [0] rows passing the fold test, [1] rows kept.
+ * spk_filter_emit compacts kept rows in row order: d_out_keys[j], d_out_norm[j*ncol + c] =
+ * (double)count / (double)length[c] (Jellyfish.py:648), d_out_tot[j].  d_scan_ws: uint32[nrows+1].
+ * ---------------------------------------------------------------------------------------------- */
+int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_ukeys, uint32_t* d_urows,
+                     uint64_t uslots, uint32_t* d_nrows, uint64_t* d_fail, void* stream);
+int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
+                    const uint64_t* d_ukeys, const uint32_t* d_urows, uint64_t uslots,
+                    uint32_t* d_matrix, uint64_t* d_row_keys, int ncol, int col, void* stream);
+int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
+                            const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
+                            const int32_t* d_grp_off, int n_groups, const int32_t* d_members,
+                            double min_fold, int baseline, double ratio, double min_freq,
+                            double max_freq, uint8_t* d_flags, uint64_t* d_tot,
+                            uint64_t* d_counters, void* stream);
+int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_row_keys, const uint8_t* d_flags,
+                    const uint64_t* d_tot, uint64_t nrows, int ncol, const uint64_t* d_lengths,
+                    uint32_t* d_scan_ws, uint64_t* d_out_keys, double* d_out_norm,
+                    uint64_t* d_out_tot, uint64_t cap, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).
+ * Used to give the matrix a deterministic (sorted) row order and by the BH step.
+ * d_keys_tmp / d_vals_tmp: scratch of n elements each; the result ends in d_keys / d_vals.
+ * key_bits: number of significant low bits (rounded up to a multiple of 4).
+ * ---------------------------------------------------------------------------------------------- */
+size_t spk_sort_workspace_bytes(uint64_t n);
+int spk_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
+                       uint32_t* d_vals_tmp, uint64_t n, int key_bits, void* d_ws, size_t ws_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K9  per-position lookup of subgenome-specific k-mers, counted into bins
+ * replaces: Seqs.map_kmer3 / map_kmer_each4 / _get_kmer (Seqs.py:74-119, 209-244).
+ * The specific-k-mer table maps CANONICAL k-mer -> subgenome index (the reference's dict holds each
+ * k-mer and its reverse complement with the same value, Cluster.py:174-175, which is the same map).
+ * spk_sig_table_build fills an open-addressed table d_skeys (uint64[sslots], pre-filled with 0xFF) /
+ * d_svals (uint8[sslots]).  spk_map_bins then looks up the k-mer starting at every position i of the
+ * packed chromosome and, on a hit with value sg, increments d_line_counts[line(i) * S + sg] where
+ *   line(i) = i / bin_size + (chunk_size ? (i + k - 1) / chunk_size : 0)
+ * i.e. one counter row per (bin, 10-Mb chunk) pair, reproducing the duplicate border lines of
+ * Seqs.py:131-137,229-236 (chunk_size = 0: no chunking, `chunk=False`).  d_line_counts is uint32
+ * [n_lines x S], zeroed by the caller, n_lines = spk_map_num_lines(...).
+ * d_hit_flags (optional, uint8[sslots], zeroed) is set for every table slot that was hit (the
+ * reference's "mapped kmers" set, Seqs.py:109,227); d_nhits (uint64[1], zeroed) counts hits.
+ * ---------------------------------------------------------------------------------------------- */
+int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, uint64_t* d_skeys,
+                        uint8_t* d_svals, uint64_t sslots, uint64_t* d_fail, void* stream);
+uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size, uint64_t chunk_size);
+int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                 const uint64_t* d_skeys, const uint8_t* d_svals, uint64_t sslots, int S,
+                 uint64_t bin_size, uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
+                 uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10  per-window Fisher exact test (right tail) + Benjamini-Hochberg
+ * replaces: Stats.fisher_test (Stats.py:14-31; fisher 0.1.9 `pvalue(...).right_tail`) and
+ *           Stats.correct_pvals (Stats.py:11-12; statsmodels multipletests fdr_bh).
+ * For row r, column i: x11=c[r,i]; x12=sum(row)-x11; x21=tot[i]-x11; x22=sum(tot)-x21-x12 (as coded,
+ * Stats.py:20-23); x21,x22 clamped to 214748364; p = P(X >= x11), X ~ Hypergeom(N=x11+x12+x21+x22,
+ * K=x11+x21, n=x11+x12).  d_counts int64 [W x S] row-major, d_totals int64 [S], d_pvals fp64 [W x S].
+ * spk_enrich_rows applies Pvalues.get_enriched + _enrich (Stats.py:150-192): per row the stable
+ * arg-min, significance, ratios; outputs d_idx int32[W], d_sig uint8[W], d_ratios fp64[W x S].
+ * spk_bh_adjust: q-values of n p-values (needs ws from spk_bh_workspace_bytes).
+ * ---------------------------------------------------------------------------------------------- */
+int spk_fisher_right_tail(const int64_t* d_counts, const int64_t* d_totals, uint64_t W, int S,
+                          double* d_pvals, void* stream);
+int spk_enrich_rows(const int64_t* d_counts, const int64_t* d_totals, const double* d_pvals,
+                    uint64_t W, int S, double max_pval, double cutoff, double min_ratio,
+                    int32_t* d_idx, uint8_t* d_sig, double* d_ratios, void* stream);
+size_t spk_bh_workspace_bytes(uint64_t n);
+int spk_bh_adjust(const double* d_p, double* d_q, uint64_t n, void* d_ws, size_t ws_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K5-K8  statistics over the chromosome x k-mer matrix (all fp64)
+ * Xraw is the M x n row-major matrix of `.kmer.mat` (row = k-mer, column = chromosome).
+ *
+ * spk_zscore_rows: Z[m, c] = (X[m,c] - mean_m) / std_m with population std over the n chromosomes —
+ *   Cluster.normalize_data on data.T, axis=0 (Cluster.py:25-26,76-80).
+ * spk_gram: G[n x n] = sum_m Z[m,:]^T Z[m,:] (optionally only over rows listed in d_idx) — all point-
+ *   to-point geometry K-Means and PCA need for n points in M dimensions.
+ * spk_kmeans_gram: Lloyd K-Means on n points given G (k-means++ seeding from `seed`, n_init restarts,
+ *   max_iter; best inertia wins) -> labels int32[n], inertia.  Replaces sklearn KMeans(n_clusters)
+ *   as called by Cluster.fit (Cluster.py:114-118).
+ * spk_gram_batched + spk_kmeans_gram with R > 1: the bootstrap loop of Cluster.bootstrap
+ *   (Cluster.py:82-112): replicate r clusters the B resampled k-mers d_idx[r*B..] (indices supplied
+ *   by the caller, drawn with replacement).
+ * spk_cluster_scores: adjusted Rand index and V-measure of each replicate vs d_ref_labels
+ *   (Cluster.py:97-100; sklearn.metrics).
+ * spk_centroids: C[s, m] = mean of Z[m, c] over c with label s  (sklearn cluster_centers_).
+ * spk_ttest_groups: Cluster._output_kmers (Cluster.py:178-194) with scipy.stats.ttest_ind: group the
+ *   n values of each raw row by subgenome label, order groups by descending mean (stable), Student
+ *   t-test (pooled variance, two-sided) of the top two; outputs best group, p-value, group means.
+ * spk_pca_gram: eigen-decomposition of G (Jacobi) -> eigenvalues (descending) and scores U*sqrt(l)
+ *   [n x ncomp], explained variance ratio; equals sklearn PCA(svd_solver='full') up to sign
+ *   (Cluster.py:48-51).
+ * ---------------------------------------------------------------------------------------------- */
+int spk_zscore_rows(const double* d_X, uint64_t M, int n, double* d_Z, void* stream);
+size_t spk_gram_workspace_bytes(int n);
+int spk_gram(const double* d_Z, uint64_t M, int n, const uint32_t* d_idx, uint64_t n_idx,
+             double* d_G, void* d_ws, size_t ws_bytes, void* stream);
+/* R Gram matrices, replicate r over the B rows d_idx[r*B .. r*B+B): d_G is fp64 [R x n x n] */
+int spk_gram_batched(const double* d_Z, uint64_t M, int n, const uint32_t* d_idx, int R, int B,
+                     double* d_G, void* stream);
+/* R independent K-Means problems on Gram matrices d_G [R x n x n].  d_order (int32[n], optional):
+ * chromosome indices sorted by name — labels are renumbered by first appearance in that order
+ * (Cluster.sort_subgenomes, Cluster.py:119-126).  d_labels int32 [R x n], d_inertia fp64 [R]. */
+size_t spk_kmeans_workspace_bytes(int R);
+int spk_kmeans_gram(const double* d_G, int R, int n, int S, int n_init, int max_iter, uint64_t seed,
+                    const int32_t* d_order, int32_t* d_labels, double* d_inertia, void* d_ws,
+                    size_t ws_bytes, void* stream);
+int spk_cluster_scores(const int32_t* d_ref_labels, const int32_t* d_labels, int R, int n,
+                       double* d_ari, double* d_vmeasure, void* stream);
+int spk_centroids(const double* d_Z, uint64_t M, int n, const int32_t* d_labels, int S,
+                  double* d_C, void* stream);
+int spk_ttest_groups(const double* d_X, uint64_t M, int n, const int32_t* d_col_group, int S,
+                     int32_t* d_best, double* d_pval, double* d_means, void* stream);
+size_t spk_pca_workspace_bytes(int n);
+int spk_pca_gram(const double* d_G, int n, int ncomp, double* d_eigvals, double* d_scores,
+                 double* d_ratio, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry point (what a file-level caller binds): FASTA bytes in HOST memory -> H2D copy ->
+ * K1 -> K2 -> K3 on `stream`.  d_* are device scratch/outputs as above; d_ascii must hold nbytes.
+ * d_info: uint64[12] device scratch.  d_block_counts as for spk_table_stats.  Sizes derive from
+ * cap_bases (>= nbytes): packed/valid words, workspace, table bytes, layout.
+ * h_out (uint64[8], host): [0] n_bases, [1] n_valid_bases, [2] n_records, [3] valid k-mers,
+ *   [4] distinct, [5] k-mers >= lower_count, [6] sum of their counts (lengths[i]), [7] failed inserts.
+ * syncs: yes (it returns the numbers).  The extracted (key,count) list is left in d_keys/d_counts.
+ * ---------------------------------------------------------------------------------------------- */
+int spk_count_fasta_host(const uint8_t* h_fasta, size_t nbytes, int k, uint32_t lower_count,
+                         uint8_t* d_ascii, uint32_t* d_packed, uint32_t* d_valid, uint64_t cap_bases,
+                         void* d_ws, size_t ws_bytes, void* d_table, size_t table_bytes,
+                         uint32_t* d_block_counts, uint64_t* d_keys, uint32_t* d_counts,
+                         uint64_t cap_out, uint64_t* d_info, uint64_t* h_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic genome generator (TEST/BENCH INFRASTRUCTURE, not part of the product path): writes the
+ * FASTA bytes of one chromosome directly in device memory.  See subphaser_b200/synth.py.
+ * ---------------------------------------------------------------------------------------------- */
+int spk_synth_fasta(uint8_t* d_out, uint64_t nbytes, uint64_t header_len, uint64_t n_bases,
+                    int line_width, const uint64_t* d_seg_start, const int64_t* d_seg_src,
+                    const uint32_t* d_seg_seed, uint64_t n_segs, const uint8_t* d_library,
+                    uint64_t lib_len, const uint64_t* d_nrun_start, const uint64_t* d_nrun_end,
+                    uint64_t n_nruns, double div, double soft_frac, uint64_t seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPK_H */

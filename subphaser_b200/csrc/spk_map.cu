@@ -1,0 +1,192 @@
+// K9: per-position lookup of subgenome-specific k-mers, counted into (bin, chunk) lines.
+//
+// Replaces Seqs.map_kmer3 / map_kmer_each4 / _get_kmer (Seqs.py:74-119, 209-244): for every start
+// position i, `sg = d_kmers[seq[i:i+k]]`; on a hit `d_bin[(i+offset)//bin_size][sg] += 1`.
+// The reference dict holds each specific k-mer and its reverse complement (Cluster.py:174-175), so a
+// forward-strand lookup hits exactly when the CANONICAL k-mer is in the matrix; the table here stores
+// canonical keys only (half the size, stays L2-resident).
+#include "spk_common.cuh"
+#include "spk_tile.cuh"
+
+namespace {
+
+constexpr int MP_BATCH = 8;
+constexpr int MP_SMEM_LINES = 16;
+constexpr int MP_MAX_S = 32;
+
+__global__ void __launch_bounds__(256)
+k_sig_build(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ vals, uint64_t n,
+            uint64_t* __restrict__ skeys, uint8_t* __restrict__ svals, uint64_t sslots,
+            uint64_t* __restrict__ fail) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+        uint64_t slot = spk_slot_of(spk_hash64(key), sslots);
+        bool done = false;
+        for (uint64_t p = 0; p < sslots; p++) {
+            const uint64_t old = atomicCAS((unsigned long long*)(skeys + slot),
+                                           (unsigned long long)SPK_EMPTY_KEY, (unsigned long long)key);
+            if (old == SPK_EMPTY_KEY || old == key) {
+                svals[slot] = vals[i];
+                done = true;
+                break;
+            }
+            slot++;
+            if (slot == sslots) slot = 0;
+        }
+        if (!done) atomicAdd((unsigned long long*)fail, 1ull);
+    }
+}
+
+struct MapArgs {
+    const uint64_t* skeys;
+    const uint8_t* svals;
+    uint64_t sslots;
+    int S;
+    uint64_t bin_size;
+    uint64_t chunk_size;
+    uint32_t* line_counts;
+    uint64_t n_lines;
+    uint8_t* hit_flags;
+    uint64_t* nhits;
+};
+
+__device__ __forceinline__ uint64_t line_of(uint64_t pos, int k, uint64_t bin_size,
+                                            uint64_t chunk_size) {
+    uint64_t l = pos / bin_size;
+    if (chunk_size) l += (pos + (uint64_t)(k - 1)) / chunk_size;
+    return l;
+}
+
+__global__ void __launch_bounds__(SPK_TILE_THREADS, 3)
+k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_bases,
+           int k, MapArgs a) {
+    __shared__ SpkTileSmem sm;
+    __shared__ uint32_t s_cnt[MP_SMEM_LINES * MP_MAX_S];
+    __shared__ uint64_t s_line0;
+    const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
+    const int tid = threadIdx.x;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    spk_tile_init(sm);
+    uint64_t n_hit = 0;
+
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) spk_tile_issue(sm, packed, valid, tile, 0);
+
+    for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
+        const int buf = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) s_cnt[i] = 0;
+        if (tid == 0) s_line0 = line_of(tile * SPK_TILE_BASES, k, a.bin_size, a.chunk_size);
+        __syncthreads();  // buffer buf^1 free, counters cleared, line0 visible
+        if (tid == 0 && tile + gridDim.x < n_tiles)
+            spk_tile_issue(sm, packed, valid, tile + gridDim.x, buf ^ 1);
+        spk_mbar_wait(&sm.bar[buf], parity);
+
+        uint64_t key[SPK_KMERS_PER_THREAD];
+        uint32_t okmask;
+        spk_tile_kmers(sm, buf, kp, key, okmask);
+
+        // line bookkeeping for this thread's 16 consecutive positions
+        const uint64_t pos0 = tile * SPK_TILE_BASES + (uint64_t)tid * SPK_KMERS_PER_THREAD;
+        uint64_t bin = pos0 / a.bin_size;
+        uint64_t brem = pos0 - bin * a.bin_size;
+        uint64_t chk = 0, crem = 0;
+        if (a.chunk_size) {
+            chk = (pos0 + (uint64_t)(k - 1)) / a.chunk_size;
+            crem = (pos0 + (uint64_t)(k - 1)) - chk * a.chunk_size;
+        }
+        const uint64_t line0 = s_line0;
+
+#pragma unroll
+        for (int b0 = 0; b0 < SPK_KMERS_PER_THREAD; b0 += MP_BATCH) {
+            uint64_t slot[MP_BATCH], cur[MP_BATCH];
+#pragma unroll
+            for (int j = 0; j < MP_BATCH; j++) {
+                slot[j] = spk_slot_of(spk_hash64(key[b0 + j]), a.sslots);
+                cur[j] = ((okmask >> (b0 + j)) & 1u) ? __ldg(a.skeys + slot[j]) : SPK_EMPTY_KEY;
+            }
+#pragma unroll
+            for (int j = 0; j < MP_BATCH; j++) {
+                if ((okmask >> (b0 + j)) & 1u) {
+                    uint64_t sl = slot[j], c = cur[j];
+                    const uint64_t kk = key[b0 + j];
+                    while (c != SPK_EMPTY_KEY && c != kk) {
+                        sl++;
+                        if (sl == a.sslots) sl = 0;
+                        c = __ldg(a.skeys + sl);
+                    }
+                    if (c == kk) {
+                        const uint32_t sg = a.svals[sl];
+                        const uint64_t line = bin + chk;
+                        const uint64_t rel = line - line0;
+                        if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
+                        else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
+                        if (a.hit_flags) a.hit_flags[sl] = 1;
+                        n_hit++;
+                    }
+                }
+                // advance the (bin, chunk) cursors to the next position
+                if (++brem == a.bin_size) { brem = 0; bin++; }
+                if (a.chunk_size && ++crem == a.chunk_size) { crem = 0; chk++; }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) {
+            const uint32_t c = s_cnt[i];
+            if (c) {
+                const uint64_t line = line0 + i / MP_MAX_S;
+                const int sg = i % MP_MAX_S;
+                if (line < a.n_lines && sg < a.S) atomicAdd(&a.line_counts[line * a.S + sg], c);
+            }
+        }
+    }
+    n_hit = spk_warp_sum_u64(n_hit);
+    if ((tid & 31) == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
+}
+
+}  // namespace
+
+extern "C" int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n,
+                                   uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,
+                                   uint64_t* d_fail, void* stream) {
+    SPK_CHECK_ARG(d_skeys && d_svals && d_fail, "null pointer");
+    SPK_CHECK_ARG(sslots >= 2, "sslots too small");
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_keys && d_vals, "null keys/vals");
+    const uint64_t blocks = (n + 255) / 256;
+    const unsigned grid = (unsigned)min(blocks, (uint64_t)spk_num_sms() * 16);
+    k_sig_build<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_vals, n, d_skeys, d_svals, sslots,
+                                                        d_fail);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size, uint64_t chunk_size) {
+    if (bin_size == 0 || n_bases == 0) return 0;
+    const uint64_t last = n_bases - 1;
+    uint64_t l = last / bin_size;
+    if (chunk_size) l += (last + (uint64_t)(k - 1)) / chunk_size;
+    return l + 1;
+}
+
+extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                            const uint64_t* d_skeys, const uint8_t* d_svals, uint64_t sslots, int S,
+                            uint64_t bin_size, uint64_t chunk_size, uint32_t* d_line_counts,
+                            uint64_t n_lines, uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
+    SPK_CHECK_ARG(d_packed && d_valid && d_skeys && d_svals && d_line_counts, "null pointer");
+    SPK_CHECK_ARG(k >= 1 && k <= 32, "k must be in [1, 32]");
+    SPK_CHECK_ARG(S >= 1 && S <= MP_MAX_S, "S must be in [1, 32]");
+    SPK_CHECK_ARG(bin_size >= 1, "bin_size must be >= 1");
+    SPK_CHECK_ARG(sslots >= 2, "sslots too small");
+    SPK_CHECK_ARG(n_lines >= spk_map_num_lines(n_bases, k, bin_size, chunk_size), "n_lines too small");
+    if (n_bases < (uint64_t)k) return SPK_OK;
+    const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
+    const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
+    MapArgs a{d_skeys, d_svals, sslots, S, bin_size, chunk_size, d_line_counts, n_lines, d_hit_flags,
+              d_nhits};
+    k_map_bins<<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}

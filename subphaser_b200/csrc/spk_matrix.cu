@@ -1,0 +1,275 @@
+// K3b/K4: union of the per-chromosome (k-mer, count) lists -> count matrix -> differential filter.
+//
+// Replaces JellyfishDumps.to_matrix (Jellyfish.py:439-460: dict kmer -> [count per chromosome], 0
+// where the k-mer was not dumped) and JellyfishDumps.filter / _filter_kmer (Jellyfish.py:462-512,
+// 611-648).  The fp64 arithmetic of _filter_kmer is reproduced operation by operation (this file is
+// compiled with -fmad=false): int sums, one IEEE division per group, `max/(min+1e-20) >= min_fold`.
+#include "spk_common.cuh"
+
+namespace {
+
+constexpr int MX_THREADS = 256;
+constexpr int MX_MAX_GROUPS_PER_SET = 64;
+
+__global__ void __launch_bounds__(MX_THREADS)
+k_union_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ ukeys,
+               uint32_t* __restrict__ urows, uint64_t uslots, uint32_t* __restrict__ nrows,
+               uint64_t* __restrict__ fail) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+        uint64_t slot = spk_slot_of(spk_hash64(key), uslots);
+        bool done = false;
+        for (uint64_t p = 0; p < uslots; p++) {
+            uint64_t cur = __ldcg(ukeys + slot);
+            if (cur == SPK_EMPTY_KEY) {
+                const uint64_t old = atomicCAS((unsigned long long*)(ukeys + slot),
+                                               (unsigned long long)SPK_EMPTY_KEY,
+                                               (unsigned long long)key);
+                if (old == SPK_EMPTY_KEY) {
+                    // winner assigns the row id; readers of urows run in later kernels
+                    urows[slot] = atomicAdd(nrows, 1u);
+                    done = true;
+                    break;
+                }
+                cur = old;
+            }
+            if (cur == key) {
+                done = true;
+                break;
+            }
+            slot++;
+            if (slot == uslots) slot = 0;
+        }
+        if (!done) atomicAdd((unsigned long long*)fail, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(MX_THREADS)
+k_matrix_fill(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n,
+              const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ urows, uint64_t uslots,
+              uint32_t* __restrict__ matrix, uint64_t* __restrict__ row_keys, int ncol, int col) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+        uint64_t slot = spk_slot_of(spk_hash64(key), uslots);
+        for (uint64_t p = 0; p < uslots; p++) {
+            const uint64_t cur = __ldg(ukeys + slot);
+            if (cur == key) {
+                const uint32_t row = urows[slot];
+                matrix[(uint64_t)row * ncol + col] = counts[i];
+                row_keys[row] = key;
+                break;
+            }
+            if (cur == SPK_EMPTY_KEY) break;  // not in the union (cannot happen after union_insert)
+            slot++;
+            if (slot == uslots) slot = 0;
+        }
+    }
+}
+
+struct FilterCfg {
+    const int32_t* set_off;
+    const int32_t* grp_off;
+    const int32_t* members;
+    int n_sets;
+    double min_fold;
+    int baseline;
+    double ratio;
+    double min_freq;
+    double max_freq;
+};
+
+// One thread per matrix row.  Mirrors _filter_kmer (Jellyfish.py:611-648) with outfig set.
+__global__ void __launch_bounds__(MX_THREADS)
+k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
+         const uint64_t* __restrict__ lengths, FilterCfg cfg, uint8_t* __restrict__ flags,
+         uint64_t* __restrict__ tot_out, uint64_t* __restrict__ counters) {
+    uint64_t n_fold = 0, n_keep = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t* row = matrix + r * ncol;
+        uint64_t tot = 0;
+        for (int c = 0; c < ncol; c++) tot += row[c];
+        int include = 0, all = 0;
+        for (int s = 0; s < cfg.n_sets; s++) {
+            const int g0 = cfg.set_off[s], g1 = cfg.set_off[s + 1];
+            const int ng = g1 - g0;
+            if (ng < 2) continue;  // singleton sets are ignored (Jellyfish.py:622-623)
+            all++;
+            double f[MX_MAX_GROUPS_PER_SET];
+            for (int g = g0; g < g1; g++) {
+                uint64_t cs = 0, ls = 0;
+                for (int m = cfg.grp_off[g]; m < cfg.grp_off[g + 1]; m++) {
+                    const int c = cfg.members[m];
+                    cs += row[c];
+                    ls += lengths[c];
+                }
+                f[g - g0] = (double)cs / (double)ls;  // count/lens or sum(count)/sum(lens)
+            }
+            // sorted(freqs, reverse=1): insertion sort, descending
+            for (int i = 1; i < ng; i++) {
+                const double v = f[i];
+                int j = i - 1;
+                while (j >= 0 && f[j] < v) {
+                    f[j + 1] = f[j];
+                    j--;
+                }
+                f[j + 1] = v;
+            }
+            const double fmax = f[0];
+            const double fmin = f[cfg.baseline >= 0 ? cfg.baseline : ng + cfg.baseline];
+            if (1.0 * fmax / (fmin + 1e-20) >= cfg.min_fold) include++;
+        }
+        uint8_t fl = 0;
+        const double rr = 1.0 * (double)include / (double)all;
+        if (!(rr < cfg.ratio)) {
+            fl |= 1;
+            const double t = (double)tot;
+            if (!(t < cfg.min_freq || t > cfg.max_freq)) fl |= 2;
+        }
+        flags[r] = fl;
+        tot_out[r] = tot;
+        n_fold += fl & 1;
+        n_keep += (fl >> 1) & 1;
+    }
+    n_fold = spk_warp_sum_u64(n_fold);
+    n_keep = spk_warp_sum_u64(n_keep);
+    if ((threadIdx.x & 31) == 0) {
+        if (n_fold) atomicAdd((unsigned long long*)&counters[0], (unsigned long long)n_fold);
+        if (n_keep) atomicAdd((unsigned long long*)&counters[1], (unsigned long long)n_keep);
+    }
+}
+
+// exclusive scan of the keep flags -> output positions (single CTA; nrows <= ~1e9 is fine but slow;
+// a chained version can replace it if the union grows that large)
+__global__ void __launch_bounds__(1024) k_scan_flags(const uint8_t* __restrict__ flags, uint64_t n,
+                                                      uint32_t* __restrict__ pos) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    constexpr int PER = 8;
+    for (uint64_t base = 0; base < n; base += 1024 * PER) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * PER;
+        uint32_t loc[PER];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            loc[q] = (i0 + q < n) ? ((flags[i0 + q] >> 1) & 1u) : 0u;
+            sum += loc[q];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t prefix = s_carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix += s_warp[w];
+        uint32_t run = prefix + incl - sum;
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            if (i0 + q < n) pos[i0 + q] = run;
+            run += loc[q];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = prefix + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pos[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(MX_THREADS)
+k_filter_emit(const uint32_t* __restrict__ matrix, const uint64_t* __restrict__ row_keys,
+              const uint8_t* __restrict__ flags, const uint64_t* __restrict__ tot, uint64_t nrows,
+              int ncol, const uint64_t* __restrict__ lengths, const uint32_t* __restrict__ pos,
+              uint64_t* __restrict__ out_keys, double* __restrict__ out_norm,
+              uint64_t* __restrict__ out_tot, uint64_t cap) {
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
+         r += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(flags[r] & 2)) continue;
+        const uint64_t o = pos[r];
+        if (o >= cap) continue;
+        out_keys[o] = row_keys[r];
+        out_tot[o] = tot[r];
+        for (int c = 0; c < ncol; c++)
+            out_norm[o * ncol + c] = (double)matrix[r * ncol + c] / (double)lengths[c];
+    }
+}
+
+unsigned grid_for(uint64_t n) {
+    const uint64_t blocks = (n + MX_THREADS - 1) / MX_THREADS;
+    const uint64_t cap = (uint64_t)spk_num_sms() * 16;
+    return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace
+
+extern "C" int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_ukeys,
+                                uint32_t* d_urows, uint64_t uslots, uint32_t* d_nrows,
+                                uint64_t* d_fail, void* stream) {
+    SPK_CHECK_ARG(d_ukeys && d_urows && d_nrows && d_fail, "null pointer");
+    SPK_CHECK_ARG(uslots >= 2, "uslots too small");
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_keys, "null keys");
+    k_union_insert<<<grid_for(n), MX_THREADS, 0, (cudaStream_t)stream>>>(d_keys, n, d_ukeys, d_urows,
+                                                                         uslots, d_nrows, d_fail);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
+                               const uint64_t* d_ukeys, const uint32_t* d_urows, uint64_t uslots,
+                               uint32_t* d_matrix, uint64_t* d_row_keys, int ncol, int col,
+                               void* stream) {
+    SPK_CHECK_ARG(d_ukeys && d_urows && d_matrix && d_row_keys, "null pointer");
+    SPK_CHECK_ARG(ncol >= 1 && col >= 0 && col < ncol, "bad column");
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_keys && d_counts, "null keys/counts");
+    k_matrix_fill<<<grid_for(n), MX_THREADS, 0, (cudaStream_t)stream>>>(
+        d_keys, d_counts, n, d_ukeys, d_urows, uslots, d_matrix, d_row_keys, ncol, col);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
+                                       const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
+                                       const int32_t* d_grp_off, int n_groups,
+                                       const int32_t* d_members, double min_fold, int baseline,
+                                       double ratio, double min_freq, double max_freq,
+                                       uint8_t* d_flags, uint64_t* d_tot, uint64_t* d_counters,
+                                       void* stream) {
+    SPK_CHECK_ARG(d_lengths && d_set_off && d_grp_off && d_members && d_flags && d_tot && d_counters,
+                  "null pointer");
+    SPK_CHECK_ARG(ncol >= 1 && n_sets >= 1 && n_groups >= 1, "bad shape");
+    SPK_CHECK_ARG(baseline < MX_MAX_GROUPS_PER_SET && baseline >= -MX_MAX_GROUPS_PER_SET,
+                  "baseline out of range");
+    if (nrows == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_matrix, "null matrix");
+    FilterCfg cfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, ratio, min_freq, max_freq};
+    k_filter<<<grid_for(nrows), MX_THREADS, 0, (cudaStream_t)stream>>>(d_matrix, nrows, ncol, d_lengths,
+                                                                       cfg, d_flags, d_tot, d_counters);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_row_keys,
+                               const uint8_t* d_flags, const uint64_t* d_tot, uint64_t nrows, int ncol,
+                               const uint64_t* d_lengths, uint32_t* d_scan_ws, uint64_t* d_out_keys,
+                               double* d_out_norm, uint64_t* d_out_tot, uint64_t cap, void* stream) {
+    SPK_CHECK_ARG(d_flags && d_tot && d_lengths && d_scan_ws, "null pointer");
+    SPK_CHECK_ARG(nrows < 0xffffffffull, "too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_scan_flags<<<1, 1024, 0, st>>>(d_flags, nrows, d_scan_ws);
+    SPK_LAUNCH_CHECK();
+    if (nrows == 0 || cap == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_matrix && d_row_keys && d_out_keys && d_out_norm && d_out_tot, "null pointer");
+    k_filter_emit<<<grid_for(nrows), MX_THREADS, 0, st>>>(d_matrix, d_row_keys, d_flags, d_tot, nrows,
+                                                          ncol, d_lengths, d_scan_ws, d_out_keys,
+                                                          d_out_norm, d_out_tot, cap);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}

@@ -1,0 +1,96 @@
+"""GPU parity: K1 pack + K2 count + K3 dump vs the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+import spk_testutil as util
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_count(fasta_bytes, k, lower):
+    from subphaser_b200 import engine
+    d, n = engine.to_device_bytes(fasta_bytes)
+    seq = engine.pack_fasta(d, n)
+    dump = engine.count_packed(seq, k, lower)
+    keys, counts = dump.to_host()
+    order = np.argsort(keys, kind="stable")
+    return seq, dump, keys[order], counts[order]
+
+
+def _check(fasta_bytes, k, lower):
+    from oracle import kmers
+    okeys, ocounts, st = kmers.count_fasta(fasta_bytes, k, lower)
+    seq, dump, keys, counts = _gpu_count(fasta_bytes, k, lower)
+    assert seq.n_bases == st["n_bases"]
+    assert seq.n_records == st["n_records"]
+    assert dump.n_valid_kmers == st["n_valid_kmers"]
+    assert dump.n_distinct == st["n_distinct"]
+    assert dump.length == st["sum_dumped"]
+    assert len(keys) == st["n_dumped"]
+    np.testing.assert_array_equal(keys, okeys)
+    np.testing.assert_array_equal(counts, ocounts)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 11, 15, 16, 17, 21, 27, 31, 32])
+def test_random_messy(k):
+    rng = np.random.default_rng(100 + k)
+    seq = util.messy_seq(rng, 50000, repeat_unit="AT")
+    _check(util.fasta([("chr1", seq)]), k, 1)
+    _check(util.fasta([("chr1", seq)]), k, 3)
+
+
+def test_known_answer_small():
+    from oracle import kmers
+    fa = b">s\nACGTACGT\n"
+    _, _, keys, counts = _gpu_count(fa, 3, 1)
+    got = {kmers.key_to_str(a, 3): int(b) for a, b in zip(keys, counts)}
+    # ACG,CGT,GTA,TAC,ACG,CGT ; canonical: ACG(=CGT rc) x4, GTA(rc TAC)->GTA x2
+    assert got == {"ACG": 4, "GTA": 2}
+
+
+def test_edge_cases():
+    rng = np.random.default_rng(7)
+    cases = [
+        b"",                                   # empty file
+        b">only_header\n",                     # no sequence
+        b">s\nNNNNNNNNNNNNNNNNNNNNNNNN\n",      # all N
+        b">s\nACG\n",                          # shorter than k
+        b"ACGTACGTACGTAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA\n",  # no header
+        util.fasta([("a", "ACGT" * 50), ("b", "ACGT" * 50), ("c", "")]),  # multi-record + empty record
+        util.fasta([("a", util.random_seq(rng, 5000))], width=7),
+        util.fasta([("a", util.random_seq(rng, 5000))], width=60, crlf=True),
+        util.fasta([("p", "A" * 10000)]),       # homopolymer (run-merge + warp aggregation)
+        util.fasta([("p", "AT" * 5000 + "ACGT" * 2500 + "AACCGGTT" * 1250)]),  # microsatellites
+        util.fasta([("pal", "ACGT" * 3 + "N" + "GAATTC" * 100)]),  # even-k palindromes
+    ]
+    for fa in cases:
+        for k in (4, 6, 15, 17):
+            _check(fa, k, 1)
+            _check(fa, k, 2)
+
+
+def test_n_every_k_minus_1():
+    k = 15
+    unit = "ACGTTGCAAGGCTA" + "N"      # 14 valid bases then N: no k-mer at all
+    _check(util.fasta([("x", unit * 500)]), k, 1)
+    unit2 = "ACGTTGCAAGGCTAC" + "N"    # exactly one k-mer per unit
+    _check(util.fasta([("x", unit2 * 500)]), k, 1)
+
+
+def test_line_wrap_independence():
+    rng = np.random.default_rng(3)
+    seq = util.messy_seq(rng, 30000)
+    ref = None
+    for width in (1, 13, 60, 80, 100000):
+        _, dump, keys, counts = _gpu_count(util.fasta([("c", seq)], width=width), 17, 1)
+        cur = (keys.tobytes(), counts.tobytes())
+        if ref is None:
+            ref = cur
+        assert cur == ref
+
+
+def test_larger_than_tile_and_table_growth():
+    rng = np.random.default_rng(11)
+    seq = util.messy_seq(rng, 1_500_000, repeat_unit="ACGGT")
+    _check(util.fasta([("big", seq)]), 17, 3)
+    _check(util.fasta([("big", seq)]), 21, 1)
