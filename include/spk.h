@@ -117,9 +117,13 @@ int spk_table_extract(const void* d_table, size_t table_bytes, int k, int layout
  *   max_freq.  d_flags[row]: bit0 = fold test passed, bit1 = kept (fold && frequency gate).
  * Config arrays (device int32): set_off[n_sets+1] -> group range, grp_off[n_groups+1] -> member range,
  * members[] = column indices.  Sets with < 2 groups are skipped as in Jellyfish.py:622-623.
+ * by_count != 0 uses the (summed) raw count instead of count/length (Jellyfish.py:632,636).
  * d_counters (uint64[4], zeroed): [0] rows passing the fold test, [1] rows kept.
- * spk_filter_emit compacts kept rows in row order: d_out_keys[j], d_out_norm[j*ncol + c] =
- * (double)count / (double)length[c] (Jellyfish.py:648), d_out_tot[j].  d_scan_ws: uint32[nrows+1].
+ * spk_filter_select compacts the kept rows in row order into (d_out_keys[j], d_out_rows[j]);
+ * d_scan_ws: uint32[nrows+1], d_scan_ws[nrows] ends up holding the number kept.  The caller may then
+ * sort the pairs by key (spk_sort_pairs_u64) for a deterministic row order.  spk_filter_emit writes,
+ * for the m rows listed in d_rows: d_out_norm[j*ncol + c] = (double)count / (double)length[c]
+ * (Jellyfish.py:648) and d_out_tot[j].
  * ---------------------------------------------------------------------------------------------- */
 int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_ukeys, uint32_t* d_urows,
                      uint64_t uslots, uint32_t* d_nrows, uint64_t* d_fail, void* stream);
@@ -129,13 +133,15 @@ int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n
 int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
                             const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
                             const int32_t* d_grp_off, int n_groups, const int32_t* d_members,
-                            double min_fold, int baseline, double ratio, double min_freq,
-                            double max_freq, uint8_t* d_flags, uint64_t* d_tot,
+                            double min_fold, int baseline, int by_count, double ratio,
+                            double min_freq, double max_freq, uint8_t* d_flags, uint64_t* d_tot,
                             uint64_t* d_counters, void* stream);
-int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_row_keys, const uint8_t* d_flags,
-                    const uint64_t* d_tot, uint64_t nrows, int ncol, const uint64_t* d_lengths,
-                    uint32_t* d_scan_ws, uint64_t* d_out_keys, double* d_out_norm,
-                    uint64_t* d_out_tot, uint64_t cap, void* stream);
+int spk_filter_select(const uint64_t* d_row_keys, const uint8_t* d_flags, uint64_t nrows,
+                      uint32_t* d_scan_ws, uint64_t* d_out_keys, uint32_t* d_out_rows, uint64_t cap,
+                      void* stream);
+int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint32_t* d_rows,
+                    uint64_t m, int ncol, const uint64_t* d_lengths, double* d_out_norm,
+                    uint64_t* d_out_tot, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).
@@ -163,6 +169,10 @@ int spk_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
  * d_hit_flags (optional, uint8[sslots], zeroed) is set for every table slot that was hit (the
  * reference's "mapped kmers" set, Seqs.py:109,227); d_nhits (uint64[1], zeroed) counts hits.
  * ---------------------------------------------------------------------------------------------- */
+ /* spk_stack_windows: Circos.stack_matrix / _bed_density(stack=True) (Circos.py:709-742,831-842):
+  * d_out[d_line_window[l] * S + c] += d_line_counts[l * S + c]  (d_out int64 [W x S], zeroed). */
+int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d_line_window, uint64_t n_lines,
+                      int S, int64_t* d_out, void* stream);
 int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, uint64_t* d_skeys,
                         uint8_t* d_svals, uint64_t sslots, uint64_t* d_fail, void* stream);
 uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size, uint64_t chunk_size);
@@ -179,14 +189,17 @@ int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_b
  * Stats.py:20-23); x21,x22 clamped to 214748364; p = P(X >= x11), X ~ Hypergeom(N=x11+x12+x21+x22,
  * K=x11+x21, n=x11+x12).  d_counts int64 [W x S] row-major, d_totals int64 [S], d_pvals fp64 [W x S].
  * spk_enrich_rows applies Pvalues.get_enriched + _enrich (Stats.py:150-192): per row the stable
- * arg-min, significance, ratios; outputs d_idx int32[W], d_sig uint8[W], d_ratios fp64[W x S].
+ * arg-min, significance, ratios; outputs d_idx int32[W], d_sig uint8[W], d_ratios fp64[W x S],
+ * d_pmin fp64[W] (the row's smallest p-value, the one BH corrects).  spk_colsum_i64: the genome-wide
+ * column totals `arr.sum(axis=0)` (Stats.py:145).
  * spk_bh_adjust: q-values of n p-values (needs ws from spk_bh_workspace_bytes).
  * ---------------------------------------------------------------------------------------------- */
 int spk_fisher_right_tail(const int64_t* d_counts, const int64_t* d_totals, uint64_t W, int S,
                           double* d_pvals, void* stream);
+int spk_colsum_i64(const int64_t* d_counts, uint64_t W, int S, int64_t* d_totals, void* stream);
 int spk_enrich_rows(const int64_t* d_counts, const int64_t* d_totals, const double* d_pvals,
                     uint64_t W, int S, double max_pval, double cutoff, double min_ratio,
-                    int32_t* d_idx, uint8_t* d_sig, double* d_ratios, void* stream);
+                    int32_t* d_idx, uint8_t* d_sig, double* d_ratios, double* d_pmin, void* stream);
 size_t spk_bh_workspace_bytes(uint64_t n);
 int spk_bh_adjust(const double* d_p, double* d_q, uint64_t n, void* d_ws, size_t ws_bytes,
                   void* stream);

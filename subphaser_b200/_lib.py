@@ -32,17 +32,20 @@ SIGNATURES = {
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),
     "spk_union_insert": (c_i, [c_p, c_u64, c_p, c_p, c_u64, c_p, c_p, c_p]),
     "spk_matrix_fill": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_p, c_i, c_i, c_p]),
-    "spk_filter_differential": (c_i, [c_p, c_u64, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_d, c_i, c_d,
-                                      c_d, c_d, c_p, c_p, c_p, c_p]),
-    "spk_filter_emit": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_p, c_p, c_p, c_p, c_u64, c_p]),
+    "spk_filter_differential": (c_i, [c_p, c_u64, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_d, c_i, c_i,
+                                      c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
+    "spk_filter_select": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_p, c_u64, c_p]),
+    "spk_filter_emit": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_p, c_p, c_p, c_p]),
     "spk_sort_workspace_bytes": (c_sz, [c_u64]),
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),
+    "spk_stack_windows": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_sig_table_build": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_p]),
     "spk_map_num_lines": (c_u64, [c_u64, c_i, c_u64, c_u64]),
     "spk_map_bins": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p, c_u64, c_i, c_u64, c_u64, c_p, c_u64,
                            c_p, c_p, c_p]),
     "spk_fisher_right_tail": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
-    "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
+    "spk_colsum_i64": (c_i, [c_p, c_u64, c_i, c_p, c_p]),
+    "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
     "spk_bh_workspace_bytes": (c_sz, [c_u64]),
     "spk_bh_adjust": (c_i, [c_p, c_p, c_u64, c_p, c_sz, c_p]),
     "spk_zscore_rows": (c_i, [c_p, c_u64, c_i, c_p, c_p]),

@@ -145,7 +145,32 @@ k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid
     if ((tid & 31) == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
 }
 
+// Circos._bed_density(stack=True) (Circos.py:737-741): window row += bin row
+__global__ void __launch_bounds__(256)
+k_stack_windows(const int64_t* __restrict__ line_counts, const uint32_t* __restrict__ line_window,
+                uint64_t n_lines, int S, int64_t* __restrict__ out) {
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_lines * (uint64_t)S;
+         e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t l = e / S;
+        const int c = (int)(e - l * S);
+        const long long v = line_counts[e];
+        if (v) atomicAdd((unsigned long long*)&out[(uint64_t)line_window[l] * S + c], (unsigned long long)v);
+    }
+}
+
 }  // namespace
+
+extern "C" int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d_line_window,
+                                 uint64_t n_lines, int S, int64_t* d_out, void* stream) {
+    SPK_CHECK_ARG(S >= 1, "S must be >= 1");
+    if (n_lines == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_line_counts && d_line_window && d_out, "null pointer");
+    const uint64_t blocks = (n_lines * (uint64_t)S + 255) / 256;
+    const unsigned grid = (unsigned)min(blocks, (uint64_t)spk_num_sms() * 16);
+    k_stack_windows<<<grid, 256, 0, (cudaStream_t)stream>>>(d_line_counts, d_line_window, n_lines, S, d_out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
 
 extern "C" int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n,
                                    uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,

@@ -9,7 +9,7 @@
 namespace {
 
 constexpr int MX_THREADS = 256;
-constexpr int MX_MAX_GROUPS_PER_SET = 64;
+constexpr int MX_MAX_GROUPS_PER_SET = 32;
 
 __global__ void __launch_bounds__(MX_THREADS)
 k_union_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ ukeys,
@@ -75,6 +75,7 @@ struct FilterCfg {
     int n_sets;
     double min_fold;
     int baseline;
+    int by_count;
     double ratio;
     double min_freq;
     double max_freq;
@@ -105,7 +106,8 @@ k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
                     cs += row[c];
                     ls += lengths[c];
                 }
-                f[g - g0] = (double)cs / (double)ls;  // count/lens or sum(count)/sum(lens)
+                // count/lens or sum(count)/sum(lens); by_count: the raw (summed) count
+                f[g - g0] = cfg.by_count ? (double)cs : (double)cs / (double)ls;
             }
             // sorted(freqs, reverse=1): insertion sort, descending
             for (int i = 1; i < ng; i++) {
@@ -182,21 +184,34 @@ __global__ void __launch_bounds__(1024) k_scan_flags(const uint8_t* __restrict__
     if (threadIdx.x == 0) pos[n] = s_carry;
 }
 
+// compaction of the kept rows in row order: (key, row id) pairs
 __global__ void __launch_bounds__(MX_THREADS)
-k_filter_emit(const uint32_t* __restrict__ matrix, const uint64_t* __restrict__ row_keys,
-              const uint8_t* __restrict__ flags, const uint64_t* __restrict__ tot, uint64_t nrows,
-              int ncol, const uint64_t* __restrict__ lengths, const uint32_t* __restrict__ pos,
-              uint64_t* __restrict__ out_keys, double* __restrict__ out_norm,
-              uint64_t* __restrict__ out_tot, uint64_t cap) {
+k_filter_select(const uint64_t* __restrict__ row_keys, const uint8_t* __restrict__ flags, uint64_t nrows,
+                const uint32_t* __restrict__ pos, uint64_t* __restrict__ out_keys,
+                uint32_t* __restrict__ out_rows, uint64_t cap) {
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
          r += (uint64_t)gridDim.x * blockDim.x) {
         if (!(flags[r] & 2)) continue;
         const uint64_t o = pos[r];
         if (o >= cap) continue;
         out_keys[o] = row_keys[r];
-        out_tot[o] = tot[r];
-        for (int c = 0; c < ncol; c++)
-            out_norm[o * ncol + c] = (double)matrix[r * ncol + c] / (double)lengths[c];
+        out_rows[o] = (uint32_t)r;
+    }
+}
+
+// normalised rows in the order given by `rows`: count / length (Jellyfish.py:648)
+__global__ void __launch_bounds__(MX_THREADS)
+k_filter_emit(const uint32_t* __restrict__ matrix, const uint64_t* __restrict__ tot,
+              const uint32_t* __restrict__ rows, uint64_t m, int ncol,
+              const uint64_t* __restrict__ lengths, double* __restrict__ out_norm,
+              uint64_t* __restrict__ out_tot) {
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < m * (uint64_t)ncol;
+         e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j = e / ncol;
+        const int c = (int)(e - j * ncol);
+        const uint64_t r = rows[j];
+        out_norm[e] = (double)matrix[r * ncol + c] / (double)lengths[c];
+        if (c == 0) out_tot[j] = tot[r];
     }
 }
 
@@ -239,7 +254,7 @@ extern "C" int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows,
                                        const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
                                        const int32_t* d_grp_off, int n_groups,
                                        const int32_t* d_members, double min_fold, int baseline,
-                                       double ratio, double min_freq, double max_freq,
+                                       int by_count, double ratio, double min_freq, double max_freq,
                                        uint8_t* d_flags, uint64_t* d_tot, uint64_t* d_counters,
                                        void* stream) {
     SPK_CHECK_ARG(d_lengths && d_set_off && d_grp_off && d_members && d_flags && d_tot && d_counters,
@@ -249,27 +264,38 @@ extern "C" int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows,
                   "baseline out of range");
     if (nrows == 0) return SPK_OK;
     SPK_CHECK_ARG(d_matrix, "null matrix");
-    FilterCfg cfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, ratio, min_freq, max_freq};
+    FilterCfg cfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio,
+                  min_freq, max_freq};
     k_filter<<<grid_for(nrows), MX_THREADS, 0, (cudaStream_t)stream>>>(d_matrix, nrows, ncol, d_lengths,
                                                                        cfg, d_flags, d_tot, d_counters);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
 
-extern "C" int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_row_keys,
-                               const uint8_t* d_flags, const uint64_t* d_tot, uint64_t nrows, int ncol,
-                               const uint64_t* d_lengths, uint32_t* d_scan_ws, uint64_t* d_out_keys,
-                               double* d_out_norm, uint64_t* d_out_tot, uint64_t cap, void* stream) {
-    SPK_CHECK_ARG(d_flags && d_tot && d_lengths && d_scan_ws, "null pointer");
+extern "C" int spk_filter_select(const uint64_t* d_row_keys, const uint8_t* d_flags, uint64_t nrows,
+                                 uint32_t* d_scan_ws, uint64_t* d_out_keys, uint32_t* d_out_rows,
+                                 uint64_t cap, void* stream) {
+    SPK_CHECK_ARG(d_flags && d_scan_ws, "null pointer");
     SPK_CHECK_ARG(nrows < 0xffffffffull, "too many rows");
     cudaStream_t st = (cudaStream_t)stream;
     k_scan_flags<<<1, 1024, 0, st>>>(d_flags, nrows, d_scan_ws);
     SPK_LAUNCH_CHECK();
     if (nrows == 0 || cap == 0) return SPK_OK;
-    SPK_CHECK_ARG(d_matrix && d_row_keys && d_out_keys && d_out_norm && d_out_tot, "null pointer");
-    k_filter_emit<<<grid_for(nrows), MX_THREADS, 0, st>>>(d_matrix, d_row_keys, d_flags, d_tot, nrows,
-                                                          ncol, d_lengths, d_scan_ws, d_out_keys,
-                                                          d_out_norm, d_out_tot, cap);
+    SPK_CHECK_ARG(d_row_keys && d_out_keys && d_out_rows, "null pointer");
+    k_filter_select<<<grid_for(nrows), MX_THREADS, 0, st>>>(d_row_keys, d_flags, nrows, d_scan_ws,
+                                                            d_out_keys, d_out_rows, cap);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint32_t* d_rows,
+                               uint64_t m, int ncol, const uint64_t* d_lengths, double* d_out_norm,
+                               uint64_t* d_out_tot, void* stream) {
+    SPK_CHECK_ARG(ncol >= 1, "bad shape");
+    if (m == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_matrix && d_tot && d_rows && d_lengths && d_out_norm && d_out_tot, "null pointer");
+    k_filter_emit<<<grid_for(m * (uint64_t)ncol), MX_THREADS, 0, (cudaStream_t)stream>>>(
+        d_matrix, d_tot, d_rows, m, ncol, d_lengths, d_out_norm, d_out_tot);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

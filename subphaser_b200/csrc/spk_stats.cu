@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(128)
 k_enrich_rows(const int64_t* __restrict__ counts, const int64_t* __restrict__ totals,
               const double* __restrict__ pvals, uint64_t W, int S, double max_pval, double cutoff,
               double min_ratio, int32_t* __restrict__ idx_out, uint8_t* __restrict__ sig_out,
-              double* __restrict__ ratios_out) {
+              double* __restrict__ ratios_out, double* __restrict__ pmin_out) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= W) return;
     const double* p = pvals + r * S;
@@ -199,6 +199,23 @@ k_enrich_rows(const int64_t* __restrict__ counts, const int64_t* __restrict__ to
     if (ra[i0] < min_ratio) sig = false;
     idx_out[r] = i0;
     sig_out[r] = sig ? 1 : 0;
+    pmin_out[r] = pmin;
+}
+
+// column sums of the window x subgenome count matrix (Stats.py:145 `arr.sum(axis=0)`), exact integers
+__global__ void __launch_bounds__(256)
+k_colsum_i64(const int64_t* __restrict__ counts, uint64_t W, int S, int64_t* __restrict__ totals) {
+    __shared__ long long s_part[256];
+    const int c = blockIdx.x;
+    long long acc = 0;
+    for (uint64_t r = threadIdx.x; r < W; r += blockDim.x) acc += counts[r * S + c];
+    s_part[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[c] = s_part[0];
 }
 
 // ---- Benjamini-Hochberg (statsmodels fdr_bh): q_(i) = p_(i) / (i/n), reverse running min, clip 1 ----
@@ -266,12 +283,21 @@ extern "C" int spk_fisher_right_tail(const int64_t* d_counts, const int64_t* d_t
 
 extern "C" int spk_enrich_rows(const int64_t* d_counts, const int64_t* d_totals, const double* d_pvals,
                                uint64_t W, int S, double max_pval, double cutoff, double min_ratio,
-                               int32_t* d_idx, uint8_t* d_sig, double* d_ratios, void* stream) {
+                               int32_t* d_idx, uint8_t* d_sig, double* d_ratios, double* d_pmin,
+                               void* stream) {
     SPK_CHECK_ARG(S >= 2 && S <= EN_MAX_S, "S must be in [2, 64] (Stats.py:172 asserts > 1)");
     if (W == 0) return SPK_OK;
-    SPK_CHECK_ARG(d_counts && d_totals && d_pvals && d_idx && d_sig && d_ratios, "null pointer");
+    SPK_CHECK_ARG(d_counts && d_totals && d_pvals && d_idx && d_sig && d_ratios && d_pmin, "null pointer");
     k_enrich_rows<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        d_counts, d_totals, d_pvals, W, S, max_pval, cutoff, min_ratio, d_idx, d_sig, d_ratios);
+        d_counts, d_totals, d_pvals, W, S, max_pval, cutoff, min_ratio, d_idx, d_sig, d_ratios, d_pmin);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_colsum_i64(const int64_t* d_counts, uint64_t W, int S, int64_t* d_totals, void* stream) {
+    SPK_CHECK_ARG(S >= 1 && d_totals, "bad arguments");
+    SPK_CHECK_ARG(W == 0 || d_counts, "null counts");
+    k_colsum_i64<<<S, 256, 0, (cudaStream_t)stream>>>(d_counts, W, S, d_totals);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -166,3 +166,291 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0):
         call("spk_table_extract", _p(table.table), table.table_bytes, k, table.layout, lower_count,
              _p(table.block_counts), _p(keys), _p(counts), n_ge, st)
     return KmerDump(keys, counts, k, sum_ge, n_valid, distinct, seq.name, histo)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K3b/K4: union -> count matrix -> differential filter
+# ----------------------------------------------------------------------------------------------------
+class CountMatrix:
+    """kmer -> [count per chromosome] (the reference's d_mat, Jellyfish.py:439-460), on the device."""
+
+    def __init__(self, matrix, row_keys, lengths, k, labels=None):
+        self.matrix = matrix          # int32 [U, n] (uint32 payload)
+        self.row_keys = row_keys      # int64 [U]   (uint64 payload)
+        self.lengths = list(lengths)
+        self.k = int(k)
+        self.labels = labels
+
+    def __len__(self):
+        return int(self.row_keys.numel())
+
+    @property
+    def ncol(self):
+        return len(self.lengths)
+
+
+def build_matrix(dumps, labels=None):
+    """JellyfishDumps.to_matrix on the device: union of the dumped k-mers, one column per chromosome."""
+    require_cuda()
+    st = _stream()
+    n = len(dumps)
+    total = sum(len(d) for d in dumps)
+    uslots = max(int(total / 0.5) + 1024, 2048)   # >= 2 x #distinct
+    ukeys = torch.full((uslots,), -1, dtype=torch.int64, device=_dev())
+    urows = _empty(uslots, torch.int32)
+    nrows = _zeros(1, torch.int32)
+    fail = _zeros(1, torch.int64)
+    for d in dumps:
+        call("spk_union_insert", _p(d.keys), len(d), _p(ukeys), _p(urows), uslots, _p(nrows), _p(fail), st)
+    U = int(nrows.item())
+    if int(fail.item()):
+        raise OverflowError("union table full")
+    matrix = _zeros(U * n, torch.int32).view(U, n) if U else _zeros(0, torch.int32).view(0, n)
+    row_keys = _empty(U, torch.int64)
+    for i, d in enumerate(dumps):
+        call("spk_matrix_fill", _p(d.keys), _p(d.counts), len(d), _p(ukeys), _p(urows), uslots, _p(matrix),
+             _p(row_keys), n, i, st)
+    k = dumps[0].k if dumps else 0
+    return CountMatrix(matrix, row_keys, [d.length for d in dumps], k, labels)
+
+
+class DiffMatrix:
+    """The differential-k-mer matrix (rows sorted by k-mer): what `.kmer.mat` holds."""
+
+    def __init__(self, keys, norm, tot, k, labels, n_fold_pass, fold_tots=None):
+        self.keys, self.norm, self.tot = keys, norm, tot   # int64 [M], float64 [M, n], int64 [M]
+        self.k, self.labels = int(k), labels
+        self.n_fold_pass = int(n_fold_pass)
+        self.fold_tots = fold_tots                         # totals of all fold-pass k-mers (histogram)
+
+    def __len__(self):
+        return int(self.keys.numel())
+
+
+def flatten_sgs(sgs, labels):
+    """sgs (list of sets -> list of groups -> list of labels) -> CSR int32 arrays of column indices."""
+    col = {lab: i for i, lab in enumerate(labels)}
+    set_off, grp_off, members = [0], [0], []
+    for sg in sgs:
+        for chrs in sg:
+            for c in chrs:
+                if c not in col:
+                    raise KeyError(c)
+                members.append(col[c])
+            grp_off.append(len(members))
+        set_off.append(len(grp_off) - 1)
+    return (np.array(set_off, np.int32), np.array(grp_off, np.int32), np.array(members, np.int32))
+
+
+def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200, max_freq=10000,
+                  by_count=False, want_fold_tots=False):
+    """JellyfishDumps.filter arithmetic (Jellyfish.py:462-512) on the device -> DiffMatrix."""
+    require_cuda()
+    st = _stream()
+    U, n = len(cm), cm.ncol
+    set_off, grp_off, members = flatten_sgs(sgs, labels)
+    d_set, d_grp, d_mem = (torch.from_numpy(a).to(_dev()) for a in (set_off, grp_off, members))
+    d_len = torch.tensor(cm.lengths, dtype=torch.int64, device=_dev())
+    flags = _empty(max(U, 1), torch.uint8)
+    tot = _empty(max(U, 1), torch.int64)
+    counters = _zeros(4, torch.int64)
+    call("spk_filter_differential", _p(cm.matrix), U, n, _p(d_len), _p(d_set), len(set_off) - 1, _p(d_grp),
+         len(grp_off) - 1, _p(d_mem), float(min_fold), int(baseline), int(bool(by_count)), float(ratio),
+         float(min_freq), float(max_freq), _p(flags), _p(tot), _p(counters), st)
+    n_fold, n_keep = (int(x) for x in counters[:2].cpu().tolist())
+    scan = _empty(U + 1, torch.int32)
+    keys = _empty(n_keep, torch.int64)
+    rows = _empty(n_keep, torch.int32)
+    call("spk_filter_select", _p(cm.row_keys), _p(flags), U, _p(scan), _p(keys), _p(rows), n_keep, st)
+    if n_keep > 1:   # deterministic row order: ascending k-mer
+        lib = _lib.load()
+        ws_bytes = lib.spk_sort_workspace_bytes(n_keep)
+        ws = _empty(ws_bytes, torch.uint8)
+        kt, rt = _empty(n_keep, torch.int64), _empty(n_keep, torch.int32)
+        call("spk_sort_pairs_u64", _p(keys), _p(rows), _p(kt), _p(rt), n_keep, 2 * cm.k, _p(ws), ws_bytes, st)
+    norm = _empty(n_keep * n, torch.float64).view(n_keep, n)
+    otot = _empty(n_keep, torch.int64)
+    call("spk_filter_emit", _p(cm.matrix), _p(tot), _p(rows), n_keep, n, _p(d_len), _p(norm), _p(otot), st)
+    fold_tots = None
+    if want_fold_tots and U:
+        fold_tots = tot[:U][(flags[:U] & 1).bool()].cpu().numpy()
+    return DiffMatrix(keys, norm, otot, cm.k, labels, n_fold, fold_tots)
+
+
+# ----------------------------------------------------------------------------------------------------
+# K5-K8: cluster statistics
+# ----------------------------------------------------------------------------------------------------
+def zscore_rows(X):
+    """X float64 [M, n] device -> Z (Cluster.normalize_data on data.T, Cluster.py:76-80)."""
+    require_cuda()
+    M, n = X.shape
+    Z = torch.empty_like(X)
+    call("spk_zscore_rows", _p(X), M, n, _p(Z), _stream())
+    return Z
+
+
+def gram(Z, idx=None):
+    require_cuda()
+    lib = _lib.load()
+    M, n = Z.shape
+    G = _empty(n * n, torch.float64).view(n, n)
+    ws_bytes = lib.spk_gram_workspace_bytes(n)
+    ws = _empty(ws_bytes, torch.uint8)
+    call("spk_gram", _p(Z), M, n, _p(idx), 0 if idx is None else idx.numel(), _p(G), _p(ws), ws_bytes,
+         _stream())
+    return G
+
+
+def kmeans_gram(G, S, order=None, n_init=10, max_iter=300, seed=0):
+    """K-Means of the n points behind Gram matrices G [R, n, n] -> (labels int32 [R, n], inertia [R])."""
+    require_cuda()
+    lib = _lib.load()
+    if G.dim() == 2:
+        G = G.unsqueeze(0)
+    R, n, _ = G.shape
+    G = G.contiguous()
+    labels = _empty(R * n, torch.int32).view(R, n)
+    inertia = _empty(R, torch.float64)
+    ws_bytes = lib.spk_kmeans_workspace_bytes(R)
+    ws = _empty(ws_bytes, torch.uint8)
+    d_order = None if order is None else torch.as_tensor(order, dtype=torch.int32, device=_dev())
+    call("spk_kmeans_gram", _p(G), R, n, S, n_init, max_iter, seed, _p(d_order), _p(labels), _p(inertia),
+         _p(ws), ws_bytes, _stream())
+    return labels, inertia
+
+
+def gram_batched(Z, idx):
+    """idx int32 [R, B] device -> G [R, n, n]."""
+    require_cuda()
+    M, n = Z.shape
+    R, B = idx.shape
+    G = _empty(R * n * n, torch.float64).view(R, n, n)
+    call("spk_gram_batched", _p(Z), M, n, _p(idx.contiguous()), R, B, _p(G), _stream())
+    return G
+
+
+def cluster_scores(ref_labels, labels):
+    require_cuda()
+    R, n = labels.shape
+    ari = _empty(R, torch.float64)
+    vm = _empty(R, torch.float64)
+    ref = torch.as_tensor(ref_labels, dtype=torch.int32, device=_dev()).contiguous()
+    call("spk_cluster_scores", _p(ref), _p(labels.contiguous()), R, n, _p(ari), _p(vm), _stream())
+    return ari, vm
+
+
+def centroids(Z, labels, S):
+    require_cuda()
+    M, n = Z.shape
+    C = _empty(S * M, torch.float64).view(S, M)
+    lab = torch.as_tensor(labels, dtype=torch.int32, device=_dev()).contiguous()
+    call("spk_centroids", _p(Z), M, n, _p(lab), S, _p(C), _stream())
+    return C
+
+
+def ttest_groups(X, col_group, S):
+    """Cluster._output_kmers arithmetic -> (best int32 [M], pval [M], means [M, S])."""
+    require_cuda()
+    M, n = X.shape
+    best = _empty(M, torch.int32)
+    pval = _empty(M, torch.float64)
+    means = _empty(M * S, torch.float64).view(M, S)
+    cg = torch.as_tensor(col_group, dtype=torch.int32, device=_dev()).contiguous()
+    call("spk_ttest_groups", _p(X), M, n, _p(cg), S, _p(best), _p(pval), _p(means), _stream())
+    return best, pval, means
+
+
+def pca_gram(G, ncomp):
+    require_cuda()
+    lib = _lib.load()
+    n = G.shape[0]
+    eig = _empty(n, torch.float64)
+    scores = _empty(n * ncomp, torch.float64).view(n, ncomp)
+    ratio = _empty(ncomp, torch.float64)
+    ws_bytes = lib.spk_pca_workspace_bytes(n)
+    ws = _empty(ws_bytes, torch.uint8)
+    call("spk_pca_gram", _p(G.contiguous()), n, ncomp, _p(eig), _p(scores), _p(ratio), _p(ws), ws_bytes,
+         _stream())
+    return eig, scores, ratio
+
+
+# ----------------------------------------------------------------------------------------------------
+# K9: map specific k-mers to bins
+# ----------------------------------------------------------------------------------------------------
+class SigTable:
+    """canonical specific k-mer -> subgenome index, open-addressed on the device."""
+
+    def __init__(self, keys, vals, k):
+        require_cuda()
+        n = int(keys.numel())
+        self.k = int(k)
+        self.n = n
+        self.slots = max(2 * n + 64, 1024)
+        self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
+        self.svals = _zeros(self.slots, torch.uint8)
+        fail = _zeros(1, torch.int64)
+        call("spk_sig_table_build", _p(keys), _p(vals), n, _p(self.skeys), _p(self.svals), self.slots,
+             _p(fail), _stream())
+        if int(fail.item()):
+            raise OverflowError("specific k-mer table full")
+        self.hit_flags = _zeros(self.slots, torch.uint8)
+
+    def n_mapped(self):
+        return int(self.hit_flags.sum().item())
+
+
+def map_bins(seq, sig, S, bin_size, chunk_size):
+    """-> (line_counts int32 [n_lines, S] device, n_hits)."""
+    require_cuda()
+    lib = _lib.load()
+    n_lines = lib.spk_map_num_lines(seq.n_bases, sig.k, int(bin_size), int(chunk_size))
+    counts = _zeros(max(n_lines, 1) * S, torch.int32).view(max(n_lines, 1), S)
+    nhits = _zeros(1, torch.int64)
+    if seq.n_bases:
+        call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
+             sig.slots, S, int(bin_size), int(chunk_size), _p(counts), max(n_lines, 1), _p(sig.hit_flags),
+             _p(nhits), _stream())
+    return counts[:n_lines], int(nhits.item())
+
+
+def stack_windows(line_counts, line_window, n_windows):
+    """Circos.stack_matrix summation: int64 [L, S] lines -> int64 [W, S] windows (host arrays in/out)."""
+    require_cuda()
+    lc = torch.as_tensor(np.ascontiguousarray(line_counts, dtype=np.int64)).to(_dev())
+    lw = torch.as_tensor(np.ascontiguousarray(line_window, dtype=np.int32)).to(_dev())
+    L, S = lc.shape
+    out = _zeros(max(n_windows, 1) * S, torch.int64).view(max(n_windows, 1), S)
+    call("spk_stack_windows", _p(lc), _p(lw), L, S, _p(out), _stream())
+    return out[:n_windows].cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------------
+# K10: Fisher / enrichment / BH
+# ----------------------------------------------------------------------------------------------------
+def fisher_enrich(counts, max_pval=0.05, cutoff=1.0, min_ratio=0.5):
+    """counts: int64 [W, S] (host or device) -> dict of host numpy arrays
+    (pvals [W,S], idx [W], sig [W], ratios [W,S], qvals [W], totals [S])."""
+    require_cuda()
+    lib = _lib.load()
+    c = torch.as_tensor(np.asarray(counts, dtype=np.int64) if not torch.is_tensor(counts) else counts)
+    c = c.to(device=_dev(), dtype=torch.int64).contiguous()
+    W, S = c.shape
+    st = _stream()
+    totals = _empty(S, torch.int64)
+    call("spk_colsum_i64", _p(c), W, S, _p(totals), st)   # column sums (Stats.py:145)
+    pvals = _empty(W * S, torch.float64).view(W, S)
+    call("spk_fisher_right_tail", _p(c), _p(totals), W, S, _p(pvals), st)
+    idx = _empty(W, torch.int32)
+    sig = _empty(W, torch.uint8)
+    ratios = _empty(W * S, torch.float64).view(W, S)
+    pmin = _empty(W, torch.float64)
+    call("spk_enrich_rows", _p(c), _p(totals), _p(pvals), W, S, float(max_pval), float(cutoff),
+         float(min_ratio), _p(idx), _p(sig), _p(ratios), _p(pmin), st)
+    q = _empty(W, torch.float64)
+    if W:
+        ws_bytes = lib.spk_bh_workspace_bytes(W)
+        ws = _empty(ws_bytes, torch.uint8)
+        call("spk_bh_adjust", _p(pmin), _p(q), W, _p(ws), ws_bytes, st)
+    return dict(pvals=pvals.cpu().numpy(), idx=idx.cpu().numpy(), sig=sig.cpu().numpy().astype(bool),
+                ratios=ratios.cpu().numpy(), pmin=pmin.cpu().numpy(), qvals=q.cpu().numpy(),
+                totals=totals.cpu().numpy())

@@ -1,0 +1,263 @@
+"""GPU: each libspk kernel family against the reference-generated golden vectors (tests/golden/*.json)
+and the CPU oracle (oracle/restate.py), through the C ABI (ctypes) wrappers of subphaser_b200.engine."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    with open(os.path.join(G, name)) as f:
+        return json.load(f)
+
+
+def _dev(a, dtype):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).cuda()
+
+
+# ---- K4 filter ------------------------------------------------------------------------------------------
+def test_filter_matches_reference_vectors():
+    import torch
+    from subphaser_b200 import engine
+    for case in load("filter_kmer.json"):
+        rows = case["rows"]
+        n = len(case["labels"])
+        mat = np.array([r["counts"] for r in rows], dtype=np.int32)
+        cm = engine.CountMatrix(_dev(mat, np.int32), _dev(np.arange(len(rows)), np.int64), case["lengths"], 15,
+                                case["labels"])
+        p = case["params"]
+        dm = engine.filter_matrix(cm, case["sgs"], case["labels"], min_fold=p["min_fold"], baseline=p["baseline"],
+                                  ratio=p["ratio"], min_freq=p["min_freq"], max_freq=p["max_freq"],
+                                  want_fold_tots=True)
+        kept = [i for i, r in enumerate(rows) if r["freqs"]]
+        fold = [i for i, r in enumerate(rows) if r["tot"] is not None]
+        assert dm.n_fold_pass == len(fold)
+        assert engine.u64_numpy(dm.keys).tolist() == kept          # keys are the row ids, sorted ascending
+        norm = dm.norm.cpu().numpy()
+        want = np.array([rows[i]["freqs"] for i in kept], dtype=np.float64).reshape(len(kept), n)
+        assert norm.tobytes() == want.tobytes()                   # bit-exact fp64
+        assert dm.tot.cpu().numpy().tolist() == [rows[i]["tot"] for i in kept]
+        assert sorted(dm.fold_tots.tolist()) == sorted(rows[i]["tot"] for i in fold)
+
+
+def test_union_matrix_matches_oracle():
+    from oracle import kmers, restate
+    from subphaser_b200 import engine
+    import spk_testutil as util
+    records, sgs = util.subgenome_genome(3, n_sg=3, chr_per_sg=2, chr_len=20000)
+    dumps_o, dumps_g = [], []
+    for name, seq in records:
+        fa = util.fasta([(name, seq)])
+        k_, c_, _ = kmers.count_fasta(fa, 13, 2)
+        dumps_o.append((k_, c_))
+        d, n = engine.to_device_bytes(fa)
+        dumps_g.append(engine.count_packed(engine.pack_fasta(d, n), 13, 2))
+    allk, mat, lengths = restate.to_matrix(dumps_o)
+    cm = engine.build_matrix(dumps_g)
+    assert cm.lengths == lengths and len(cm) == len(allk)
+    rk = engine.u64_numpy(cm.row_keys)
+    order = np.argsort(rk)
+    np.testing.assert_array_equal(rk[order], allk)
+    np.testing.assert_array_equal(cm.matrix.cpu().numpy()[order].astype(np.int64), mat)
+
+
+# ---- sort -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,bits", [(1, 8), (2, 64), (1000, 34), (2049, 64), (300000, 42), (1 << 20, 30)])
+def test_radix_sort(n, bits):
+    import torch
+    from subphaser_b200 import engine, _lib
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 2**bits if bits < 64 else 2**63, n, dtype=np.uint64)
+    if bits == 64:
+        keys = keys * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    keys[: n // 3] = keys[n // 3: 2 * (n // 3)][: n // 3]           # duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    dk, dv = _dev(keys.view(np.int64), np.int64), _dev(vals.view(np.int32), np.int32)
+    kt, vt = torch.empty_like(dk), torch.empty_like(dv)
+    lib = _lib.load()
+    wsb = lib.spk_sort_workspace_bytes(n)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    _lib.call("spk_sort_pairs_u64", engine._p(dk), engine._p(dv), engine._p(kt), engine._p(vt), n, bits,
+              engine._p(ws), wsb, engine._stream())
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(engine.u64_numpy(dk), keys[order])
+    np.testing.assert_array_equal(dv.cpu().numpy().view(np.uint32), vals[order])
+
+
+# ---- K9 map + stack -------------------------------------------------------------------------------------
+def test_map_and_stack_match_reference_text(tmp_path):
+    import io
+    from subphaser_b200 import Circos, Seqs, _registry
+    for ci, case in enumerate(load("map_stack.json")):
+        fa = tmp_path / ("c%d.fasta" % ci)
+        seq = case["seq"]
+        fa.write_text(">chrX desc\n" + "\n".join(seq[i:i + 60] for i in range(0, len(seq), 60)) + "\n")
+        out = tmp_path / ("c%d.bin.count" % ci)
+        with open(out, "w") as f:
+            Seqs.map_kmer3([str(fa)], case["d_kmers"], fout=f, k=case["k"], window_size=case["window_size"],
+                           bin_size=case["bin_size"], sg_names=case["sg_names"], ncpu=1, chunk=case["chunk"])
+        assert out.read_text() == case["bin_count_text"]
+        for reg in (True, False):                       # registry shortcut and text re-parse
+            if not reg:
+                _registry.clear()
+            for ws, st in case["stacks"].items():
+                coords, counts = Circos.stack_matrix(str(out), window_size=float(ws) if "." in ws else int(ws))
+                assert [list(c) for c in coords] == st["coords"]
+                assert counts == st["counts"]
+
+
+# ---- K10 Fisher / enrich / BH ------------------------------------------------------------------------------
+def test_fisher_enrich_bh_match_reference_vectors():
+    from subphaser_b200 import engine
+    for case in load("fisher_enrich.json"):
+        mat = np.array([r["row"] for r in case["rows"]], dtype=np.int64)
+        res = engine.fisher_enrich(mat)
+        assert res["totals"].tolist() == case["total"]
+        want_p = np.array([r["pvals"] for r in case["rows"]])
+        # tolerance of the north star: 1e-10 absolute; we also demand 1e-9 relative down to 1e-290
+        np.testing.assert_allclose(res["pvals"], want_p, rtol=1e-9, atol=1e-300)
+        assert res["idx"].tolist() == [r["idx"] for r in case["rows"]]
+        assert res["sig"].tolist() == [r["sig"] for r in case["rows"]]
+        want_r = np.array([r["ratios"] for r in case["rows"]])
+        assert np.array_equal(np.isnan(res["ratios"]), np.isnan(want_r))
+        assert np.nan_to_num(res["ratios"]).tobytes() == np.nan_to_num(want_r).tobytes()   # bit-exact
+        np.testing.assert_allclose(res["qvals"], case["qvals"], rtol=1e-9, atol=1e-300)
+
+
+def test_fisher_against_scipy_wide_range():
+    from scipy.stats import hypergeom
+    from subphaser_b200 import Stats
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        S = int(rng.integers(2, 6))
+        scale = int(10 ** rng.uniform(0.5, 8.2))
+        total = [int(x) for x in rng.integers(scale // 2 + 1, scale + 2, S)]
+        each = [int(rng.integers(0, min(t, max(2, scale // int(rng.integers(1, 50)))) + 1)) for t in total]
+        got = Stats.fisher_test(each, total)
+        se, st = sum(each), sum(total)
+        for i in range(S):
+            x11, x12 = each[i], se - each[i]
+            x21 = total[i] - x11
+            x22 = st - x21 - x12
+            x21, x22 = min(x21, Stats.MAX_INT), min(x22, Stats.MAX_INT)
+            want = float(hypergeom.sf(x11 - 1, x11 + x12 + x21 + x22, x11 + x12, x11 + x21))
+            assert got[i] == pytest.approx(want, abs=1e-10, rel=1e-8)
+
+
+def test_bh_edge_cases():
+    from oracle import restate
+    from subphaser_b200 import Stats
+    for p in ([0.5], [0.0, 0.0, 1.0], [1e-300, 0.04, 0.04, 0.9, 0.2], list(np.linspace(0, 1, 1000)),
+              list(np.random.default_rng(0).random(5000) ** 3)):
+        np.testing.assert_allclose(Stats.correct_pvals(p), restate.bh(p), rtol=1e-15, atol=0)
+    assert len(Stats.correct_pvals([])) == 0
+
+
+# ---- K5-K8 cluster statistics ------------------------------------------------------------------------------
+def test_zscore_bit_exact_vs_numpy():
+    from oracle import restate
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(0)
+    for n in (2, 6, 7, 8, 13, 21, 38, 64, 128):
+        raw = rng.random((3000, n)) * 1e-4
+        Z = engine.zscore_rows(_dev(raw, np.float64)).cpu().numpy()
+        assert Z.tobytes() == np.ascontiguousarray(restate.zscore(raw)).tobytes()
+
+
+def test_ttest_rows_match_reference_vectors():
+    from subphaser_b200 import engine
+    for case in load("ttest_rows.json"):
+        sgs = sorted(case["groups"])
+        n = case["n"]
+        col_group = [0] * n
+        for gi, sg in enumerate(sgs):
+            for c in case["groups"][sg]:
+                col_group[c] = gi
+        X = np.array([r["array"] for r in case["rows"]], dtype=np.float64)
+        best, pval, means = (t.cpu().numpy() for t in engine.ttest_groups(_dev(X, np.float64), col_group, len(sgs)))
+        for i, r in enumerate(case["rows"]):
+            assert sgs[best[i]] == r["max_sg"]
+            assert means[i].tolist() == r["mean_vals"]            # bit-exact group means
+            if math.isnan(r["pvalue"]):
+                assert math.isnan(pval[i])
+            else:
+                assert pval[i] == pytest.approx(r["pvalue"], rel=1e-9, abs=1e-300)
+
+
+def _blobs(rng, n_per, S, M, sep=6.0):
+    centers = rng.normal(0, sep, (S, M))
+    X = np.concatenate([centers[s] + rng.normal(0, 1.0, (n_per, M)) for s in range(S)])
+    perm = rng.permutation(len(X))
+    return X[perm]
+
+
+@pytest.mark.parametrize("n_per,S,M", [(3, 2, 500), (7, 3, 2000), (5, 4, 300), (12, 3, 64)])
+def test_gram_kmeans_centroids_vs_sklearn(n_per, S, M):
+    from oracle import restate
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(n_per * 100 + S)
+    pts = _blobs(rng, n_per, S, M)                     # [n, M]: n chromosomes in M dimensions
+    n = len(pts)
+    raw = np.ascontiguousarray(pts.T)                  # matrix layout [M, n]
+    Z = engine.zscore_rows(_dev(raw, np.float64))
+    Zh = Z.cpu().numpy()
+    Gm = engine.gram(Z).cpu().numpy()
+    np.testing.assert_allclose(Gm, Zh.T @ Zh, rtol=1e-12, atol=1e-9)
+    chrs = ["c%02d" % i for i in range(n)]
+    order = list(range(n))
+    labels, inertia = engine.kmeans_gram(engine.gram(Z), S, order=order, seed=3)
+    want, km = restate.kmeans_labels(Zh, S, chrs, seed=0)
+    assert labels[0].cpu().numpy().tolist() == want
+    assert inertia[0].item() == pytest.approx(km.inertia_, rel=1e-10)
+    C = engine.centroids(Z, labels[0].cpu().numpy(), S).cpu().numpy()
+    mine_to_sk = {}
+    for i in range(n):
+        mine_to_sk[want[i]] = km.labels_[i]
+    for s in range(S):
+        np.testing.assert_allclose(C[s], km.cluster_centers_[mine_to_sk[s]], rtol=0, atol=1e-10)
+
+
+def test_bootstrap_scores_vs_sklearn():
+    from oracle import restate
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(9)
+    pts = _blobs(rng, 7, 3, 1500, sep=1.2)              # modest separation: some replicates disagree
+    n = len(pts)
+    Z = engine.zscore_rows(_dev(np.ascontiguousarray(pts.T), np.float64))
+    Zh = Z.cpu().numpy()
+    chrs = ["c%02d" % i for i in range(n)]
+    ref_labels, _ = restate.kmeans_labels(Zh, 3, chrs)
+    R, B = 64, 200
+    idx = rng.integers(0, Zh.shape[0], (R, B)).astype(np.int32)
+    G = engine.gram_batched(Z, _dev(idx, np.int32))
+    np.testing.assert_allclose(G[5].cpu().numpy(), Zh[idx[5]].T @ Zh[idx[5]], rtol=1e-12, atol=1e-9)
+    labels, _ = engine.kmeans_gram(G, 3, order=list(range(n)), seed=1)
+    want = restate.bootstrap_labels(Zh, 3, chrs, idx)
+    got = labels.cpu().numpy()
+    agree = np.mean([(g == w).all() for g, w in zip(got, want)])
+    assert agree >= 0.95          # both sides are local-search heuristics with different RNG streams
+    ari, vm = engine.cluster_scores(ref_labels, labels)
+    for r in range(R):
+        a, v = restate.cluster_scores(ref_labels, got[r])
+        assert ari[r].item() == pytest.approx(a, abs=1e-12)
+        assert vm[r].item() == pytest.approx(v, abs=1e-12)
+
+
+def test_pca_vs_sklearn_full_svd():
+    from oracle import restate
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(2)
+    pts = _blobs(rng, 7, 3, 4000)
+    Z = engine.zscore_rows(_dev(np.ascontiguousarray(pts.T), np.float64))
+    eig, scores, ratio = (t.cpu().numpy() for t in engine.pca_gram(engine.gram(Z), 3))
+    X, want_ratio = restate.pca_scores(Z.cpu().numpy(), 3)
+    np.testing.assert_allclose(ratio, want_ratio, rtol=0, atol=1e-10)
+    for j in range(3):
+        sgn = 1.0 if np.dot(scores[:, j], X[:, j]) >= 0 else -1.0
+        np.testing.assert_allclose(sgn * scores[:, j], X[:, j], rtol=0, atol=1e-8)
