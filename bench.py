@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — SubPhaser k-mer hot path on B200 (count -> differential matrix -> cluster -> map -> enrich).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                      # our arm, N = 1
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               # CPU arm (oracle port, all cores)
+
+One "step" = one pass of the whole hot path over the wheat-shaped synthetic genome (BASELINE.json
+configs[2]: 21 chromosomes, 14.2 Gb, k=17, 3 subgenomes, 1-Mb windows; it fits one B200).  Prints ONE
+JSON line (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_KMER = 64.375      # 0.375 B streamed + 32-B sector read + 32-B write-back
+METRIC = "kmers_per_s"
+UNIT = "k-mers/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=os.environ.get("SPK_BENCH_CONFIG", "C3"))
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("SPK_BENCH_SCALE", "1.0")))
+    ap.add_argument("--replicates", type=int, default=1000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-bases", type=float, default=3e8)
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = str(index)
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", self.index], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            t = [x.strip() for x in l.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1]))
+                smax.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_count_sample(fasta_bytes, k, lower, threads):
+    """The CPU arm: oracle/kmer_count.c (jellyfish-semantics port) on all host cores."""
+    from oracle import kmers
+    t0 = time.perf_counter()
+    keys, counts, st = kmers.count_fasta(fasta_bytes, k, lower, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return st["n_valid_kmers"], dt
+
+
+def run_reference(args):
+    """--impl reference: the path's CPU implementation timed on the box's host cores.  jellyfish is not
+    installable here, so the counter is the documented port (oracle/kmer_count.c); rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from subphaser_b200 import synth
+    plan, cfg = synth.plan_for(args.config, scale=args.scale)
+    threads = len(os.sched_getaffinity(0))
+    sample_bases = int(min(args.cpu_sample_bases, plan.chroms[0]["length"]))
+    fasta = host_sample(plan, sample_bases)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_count_sample(fasta, cfg["k"], 3, threads)
+    n_k, total = 0, 0.0
+    for _ in range(args.steps):
+        nk, dt = cpu_count_sample(fasta, cfg["k"], 3, threads)
+        n_k += nk
+        total += dt
+    value = n_k / total
+    sample = "count+dump (C port of jellyfish semantics, %d threads) of the first %d bases of chromosome %s of %s" % (
+        threads, sample_bases, plan.chroms[0]["name"], args.config)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args, plan, cfg), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def host_sample(plan, sample_bases):
+    """FASTA bytes of a prefix of chromosome 0, generated on the device and copied back (or with the
+    numpy twin of the generator when no GPU is present, e.g. for the reference arm on a CPU box)."""
+    import numpy as np
+    import torch
+    from subphaser_b200 import synth
+    chrom = dict(plan.chroms[0])
+    chrom["length"] = int(sample_bases)
+    if torch.cuda.is_available():
+        d, nbytes = synth.synth_chromosome(plan, chrom)
+        return d[:nbytes].cpu().numpy()
+    rng = np.random.default_rng(plan.seed)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, chrom["length"])]
+    lines = [b">" + chrom["name"].encode()]
+    lines += [seq[i:i + 60].tobytes() for i in range(0, len(seq), 60)]
+    return np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+
+
+def workload_name(args, plan, cfg):
+    g = sum(c["length"] for c in plan.chroms)
+    return "%s wheat-shaped synthetic: %d chromosomes, %.3g bp, k=%d, %d subgenomes, %d-bp windows%s" % (
+        args.config, len(plan.chroms), g, cfg["k"], len(plan.sg_letters), cfg["window"],
+        "" if args.scale == 1.0 else " (scale %g)" % args.scale)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from subphaser_b200 import _lib, engine, hotpath, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        pg = dist
+    engine.require_cuda()
+    lib = _lib.load()
+
+    plan, cfg = synth.plan_for(args.config, scale=args.scale)
+    k = cfg["k"]
+    labels, sgs = plan.labels, plan.sgs
+    lengths = [c["length"] for c in plan.chroms]
+    owner = hotpath.lpt_assign(lengths, world)
+    mine = [i for i in range(len(lengths)) if owner[i] == rank]
+
+    # ---- synthetic inputs, resident in HBM before any timed region ----
+    d_lib = torch.from_numpy(plan.library).cuda()
+    dev_inputs = [None] * len(lengths)
+    for i in mine:
+        dev_inputs[i] = synth.synth_chromosome(plan, plan.chroms[i], d_library=d_lib)
+    for i in range(len(lengths)):
+        if dev_inputs[i] is None:
+            dev_inputs[i] = (None, plan.fasta_nbytes(plan.chroms[i])[1])
+    torch.cuda.synchronize()
+
+    kw = dict(labels=labels, sgs=sgs, k=k, lower_count=3, min_fold=2, baseline=1, ratio=1, min_freq=200,
+              max_freq=10000, nsg=len(plan.sg_letters), replicates=args.replicates, max_pval=0.05,
+              bin_size=10000, chunk_size=10_000_000, window_size=cfg["window"], seed=0, dist=pg, owner=owner)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, host_inputs, inputs, timer=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        res = None
+        for _ in range(n_steps):
+            res = hotpath.run(inputs, host_inputs=host_inputs, timer=timer, **kw)
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ev = e0.elapsed_time(e1) / 1e3
+        t = torch.tensor([max(wall, ev)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), res
+
+    # ---- device-resident arm: warm-up, then exactly K timed steps ----
+    for _ in range(args.warmup):
+        hotpath.run(dev_inputs, host_inputs=False, **kw)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    timer = hotpath.StageTimer(True)
+    launches0 = lib.spk_launch_count()
+    secs, res = timed(args.steps, False, dev_inputs, timer)
+    launches = lib.spk_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = timer.totals_ms()
+    stage_n = timer.counts()
+    n_kmers = res["n_kmers"]
+    value = n_kmers * args.steps / secs
+    n_windows = res["n_windows"]
+
+    # roofline of the dominant kernel (k_count_canonical), live CUDA-event time on the launching stream
+    count_s = stage_ms.get("count", 0.0) / 1e3
+    cs = torch.tensor([count_s, float(res["n_kmers_local"] * args.steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cs)          # sum of per-rank kernel seconds and units -> mean per-GPU rate
+    peak, peak_src = measured_peak()
+    achieved = (cs[1].item() * BYTES_PER_KMER / cs[0].item()) / 1e9 if cs[0].item() > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "count_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_count_canonical", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_unit": BYTES_PER_KMER, "units_per_launch": res["n_kmers_local"] / max(len(mine), 1),
+                "launches": stage_n.get("count", 0), "avg_launch_ms": stage_ms.get("count", 0.0) / max(stage_n.get("count", 1), 1)}
+
+    # ---- end-to-end arm: host (pinned) FASTA bytes -> H2D inside the timed region -> results D2H ----
+    e2e = None
+    if not args.no_e2e:
+        host_inputs = [None] * len(lengths)
+        for i in range(len(lengths)):
+            if i in mine:
+                d, nb = dev_inputs[i]
+                h = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+                h.copy_(d[:nb])
+                host_inputs[i] = (h, nb)
+            else:
+                host_inputs[i] = (None, dev_inputs[i][1])
+        torch.cuda.synchronize()
+        dev_inputs = None
+        torch.cuda.empty_cache()
+        hotpath.run(host_inputs, host_inputs=True, **kw)          # warm-up
+        esecs, eres = timed(args.steps, True, host_inputs)
+        hb = torch.tensor([float(eres["h2d_bytes"]), float(eres["d2h_bytes"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(hb)
+        e2e = {"value": eres["n_kmers"] * args.steps / esecs, "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()),
+               "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * esecs / args.steps,
+               "windows_per_s": eres["n_windows"] * args.steps / esecs}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        sample_bases = int(min(args.cpu_sample_bases, lengths[0]))
+        fasta = host_sample(plan, sample_bases)
+        nk, dt = cpu_count_sample(fasta, k, 3, threads)
+        cpu = {"value": nk / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "count+dump stage only (C port of jellyfish semantics, oracle/kmer_count.c) on the first "
+                         "%d bases of chromosome %s; %.1f s" % (sample_bases, labels[0], dt)}
+
+    if rank == 0:
+        win_s = (stage_ms.get("map", 0) + stage_ms.get("stack", 0) + stage_ms.get("enrich", 0)) / 1e3
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args, plan, cfg), "kmers_per_step": n_kmers,
+                       "windows_per_step": n_windows, "l2_policy": "inputs larger than L2 (5.3 GB packed sequence, "
+                       "multi-GB hash table per chromosome)", "parallelism": "chromosomes sharded over %d GPU(s), LPT" % world},
+            "windows_per_s": n_windows * args.steps / win_s if win_s > 0 else None,
+            "stage_ms_per_step": {k_: v / args.steps for k_, v in sorted(stage_ms.items())},
+            "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],
+                        "n_windows": n_windows, "labels": res["labels_full"]},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,8 @@ const char* spk_last_error(void);
 int spk_version(void);
 /* Number of SMs of the current device (persistent grids are sized from it). syncs: no. */
 int spk_sm_count(void);
+/* Number of kernels this library has launched since it was loaded (host-side counter). */
+uint64_t spk_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K1  FASTA bytes -> 2-bit packed bases + validity mask
@@ -200,6 +202,9 @@ int spk_colsum_i64(const int64_t* d_counts, uint64_t W, int S, int64_t* d_totals
 int spk_enrich_rows(const int64_t* d_counts, const int64_t* d_totals, const double* d_pvals,
                     uint64_t W, int S, double max_pval, double cutoff, double min_ratio,
                     int32_t* d_idx, uint8_t* d_sig, double* d_ratios, double* d_pmin, void* stream);
+/* Self-check: total mass of Hypergeom(N,K,n) for `count` triples d_NKn[3*i..] summed with the kernel's
+ * own point-mass routine and recurrences (must be 1 within ~1e-13). */
+int spk_debug_hypergeom_mass(const int64_t* d_NKn, uint64_t count, double* d_out, void* stream);
 size_t spk_bh_workspace_bytes(uint64_t n);
 int spk_bh_adjust(const double* d_p, double* d_q, uint64_t n, void* d_ws, size_t ws_bytes,
                   void* stream);

@@ -18,6 +18,7 @@ SIGNATURES = {
     "spk_last_error": (ctypes.c_char_p, []),
     "spk_version": (c_i, []),
     "spk_sm_count": (c_i, []),
+    "spk_launch_count": (c_u64, []),
     "spk_packed_words": (c_sz, [c_u64]),
     "spk_valid_words": (c_sz, [c_u64]),
     "spk_pack_workspace_bytes": (c_sz, [c_sz]),
@@ -46,6 +47,7 @@ SIGNATURES = {
     "spk_fisher_right_tail": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_colsum_i64": (c_i, [c_p, c_u64, c_i, c_p, c_p]),
     "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
+    "spk_debug_hypergeom_mass": (c_i, [c_p, c_u64, c_p, c_p]),
     "spk_bh_workspace_bytes": (c_sz, [c_u64]),
     "spk_bh_adjust": (c_i, [c_p, c_p, c_u64, c_p, c_sz, c_p]),
     "spk_zscore_rows": (c_i, [c_p, c_u64, c_i, c_p, c_p]),

@@ -4,6 +4,7 @@
 #include "spk_common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_spk_launches = 0;
 
 void spk_set_error(const char* fmt, ...) {
     va_list ap;
@@ -30,3 +31,4 @@ int spk_num_sms() {
 extern "C" const char* spk_last_error(void) { return g_err; }
 extern "C" int spk_version(void) { return 100; }
 extern "C" int spk_sm_count(void) { return spk_num_sms(); }
+extern "C" uint64_t spk_launch_count(void) { return g_spk_launches; }

@@ -20,26 +20,26 @@ constexpr int GR_THREADS = 512;
 constexpr int GR_TILE_ROWS = 32;
 constexpr int GR_MAX_ACC = 17;  // ceil(128*129/2 / 512)
 
-// numpy's pairwise summation of a strided run (np.add.reduce along a contiguous axis)
-__device__ double np_pairwise(const double* a, int n) {
+// numpy's pairwise summation of a contiguous run (np.add.reduce along a contiguous axis) for
+// n <= 128 = CL_MAX_N (above 128 numpy recurses on halves; not needed here).  No device recursion:
+// these kernels keep per-thread arrays in local memory and must have a static stack size.
+__device__ __forceinline__ double np_pairwise(const double* a, int n) {
     if (n < 8) {
         double res = 0.0;
         for (int i = 0; i < n; i++) res += a[i];
         return res;
     }
-    if (n <= 128) {
-        double r[8];
-        for (int j = 0; j < 8; j++) r[j] = a[j];
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8)
-            for (int j = 0; j < 8; j++) r[j] += a[i + j];
-        double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; i++) res += a[i];
-        return res;
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
     }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    return np_pairwise(a, n2) + np_pairwise(a + n2, n - n2);
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
 }
 
 // ---- K5 z-score ------------------------------------------------------------------------------------

@@ -26,7 +26,13 @@ int spk_num_sms();
         }                                                                                \
     } while (0)
 
-#define SPK_LAUNCH_CHECK() SPK_CUDA(cudaGetLastError())
+// every kernel launch of the library passes through here: count it (bench.py reports gpu_launches)
+extern unsigned long long g_spk_launches;
+#define SPK_LAUNCH_CHECK()            \
+    do {                              \
+        g_spk_launches++;             \
+        SPK_CUDA(cudaGetLastError()); \
+    } while (0)
 
 // Tile geometry shared by the sequence-streaming kernels (count, map): one CTA tile is TILE_BASES
 // bases = 1 KiB of 2-bit codes + 512 B of validity bits; the halo covers k-1 <= 31 more bases.

@@ -148,6 +148,35 @@ k_fisher(const int64_t* __restrict__ counts, const int64_t* __restrict__ totals,
     pvals[t] = fisher_right_tail(x11, x12, x21, x22);
 }
 
+// Self-check hook: total probability mass of Hypergeom(N, K, n) summed with the same point-mass routine
+// and term recurrences the Fisher kernel uses (from the mode outwards).  Must be 1 to ~1e-13; used by
+// the tests to establish the kernel's absolute accuracy where no exact reference is computable.
+__global__ void k_hypergeom_mass(const int64_t* __restrict__ NKn, uint64_t count, double* __restrict__ out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const double N = (double)NKn[3 * t], K = (double)NKn[3 * t + 1], n = (double)NKn[3 * t + 2];
+    const double B = N - K;
+    const double lo = fmax(0.0, n - B), hi = fmin(n, K);
+    double mode = floor((n + 1.0) * (K + 1.0) / (N + 2.0));
+    mode = fmin(fmax(mode, lo), hi);
+    const double t0 = dhyper(mode, K, B, n);
+    double s = t0, tt = t0;
+    for (double x = mode; x < hi; x += 1.0) {
+        tt *= ((K - x) / (x + 1.0)) * ((n - x) / (B - n + x + 1.0));
+        const double s1 = s + tt;
+        if (s1 == s) break;
+        s = s1;
+    }
+    tt = t0;
+    for (double x = mode; x > lo; x -= 1.0) {
+        tt *= (x / (K - x + 1.0)) * ((B - n + x) / (n - x + 1.0));
+        const double s1 = s + tt;
+        if (s1 == s) break;
+        s = s1;
+    }
+    out[t] = s;
+}
+
 // numpy's pairwise summation for a contiguous run of n < 128 doubles (np.add.reduce)
 __device__ __forceinline__ double np_sum_small(const double* a, int n) {
     if (n < 8) {
@@ -290,6 +319,14 @@ extern "C" int spk_enrich_rows(const int64_t* d_counts, const int64_t* d_totals,
     SPK_CHECK_ARG(d_counts && d_totals && d_pvals && d_idx && d_sig && d_ratios && d_pmin, "null pointer");
     k_enrich_rows<<<(unsigned)((W + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         d_counts, d_totals, d_pvals, W, S, max_pval, cutoff, min_ratio, d_idx, d_sig, d_ratios, d_pmin);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_debug_hypergeom_mass(const int64_t* d_NKn, uint64_t count, double* d_out, void* stream) {
+    if (count == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_NKn && d_out, "null pointer");
+    k_hypergeom_mass<<<(unsigned)((count + 63) / 64), 64, 0, (cudaStream_t)stream>>>(d_NKn, count, d_out);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -144,16 +144,24 @@ class CountTable:
         return _lib.load().spk_count_table_slots(self.table_bytes, self.layout)
 
 
-def count_packed(seq, k, lower_count, table=None, histo_len=0):
-    """K2 + K3 on one packed chromosome -> KmerDump."""
+def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
+    """K2 + K3 on one packed chromosome -> KmerDump.  `timer` (hotpath.StageTimer) brackets the
+    stages with CUDA events on the launching stream."""
     require_cuda()
     if table is None or table.max_bases < seq.n_bases or table.k != k:
         table = CountTable(max(seq.n_bases, 1), k)
     st = _stream()
+    tick = (lambda name: timer.start(name)) if timer is not None else (lambda name: None)
+    tock = (lambda e: timer.stop(e)) if timer is not None else (lambda e: None)
+    e = tick("table_init")
     call("spk_count_table_init", _p(table.table), table.table_bytes, k, table.layout, st)
     table.stats.zero_()
+    tock(e)
+    e = tick("count")
     call("spk_count_canonical", _p(seq.packed), _p(seq.valid), seq.n_bases, k, _p(table.table),
          table.table_bytes, table.layout, _p(table.stats), st)
+    tock(e)
+    e = tick("scan")
     histo = _zeros(histo_len, torch.int64) if histo_len else None
     call("spk_table_stats", _p(table.table), table.table_bytes, k, table.layout, lower_count,
          _p(table.stats[4:]), _p(table.block_counts), _p(histo), histo_len, st)
@@ -165,6 +173,7 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0):
     if n_ge:
         call("spk_table_extract", _p(table.table), table.table_bytes, k, table.layout, lower_count,
              _p(table.block_counts), _p(keys), _p(counts), n_ge, st)
+    tock(e)
     return KmerDump(keys, counts, k, sum_ge, n_valid, distinct, seq.name, histo)
 
 

@@ -1,0 +1,225 @@
+"""Whole hot path on device buffers: count -> matrix -> filter -> cluster/bootstrap -> specific k-mers ->
+map -> windows -> Fisher/BH, without touching the file system.  This is the same sequence the drop-in
+modules run for `__main__.py` (pipeline.py); bench.py and smoke() time it here so that the timed
+region contains only the copies and kernels of the path.
+
+Multi-GPU (one process per GPU, torch.distributed/NCCL): chromosomes are sharded over ranks by
+longest-processing-time assignment; each rank packs, counts and later maps only its chromosomes.  The
+one exchange step is the merge of the per-chromosome dumps into the global k-mer table: dumps are
+broadcast from their owners over NVLink (exact, variable-size) and `lengths` are all-reduced; the
+per-window counts are all-gathered before the genome-wide Fisher step.
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+
+def lpt_assign(lengths, world):
+    """Longest-processing-time assignment of chromosomes to ranks -> owner rank per chromosome."""
+    load = [0] * world
+    owner = [0] * len(lengths)
+    for i in sorted(range(len(lengths)), key=lambda i: -lengths[i]):
+        r = min(range(world), key=lambda r: load[r])
+        owner[i] = r
+        load[r] += lengths[i]
+    return owner
+
+
+class StageTimer:
+    """CUDA-event timers on the launching stream, accumulated per stage name."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.pairs = {}
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.pairs.setdefault(name, []).append((e0, e1))
+        return e1
+
+    @staticmethod
+    def stop(e1):
+        if e1 is not None:
+            e1.record()
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.pairs.items()}
+
+    def counts(self):
+        return {k: len(v) for k, v in self.pairs.items()}
+
+
+def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, ratio=1, min_freq=200,
+        max_freq=10000, nsg=None, replicates=1000, max_pval=0.05, bin_size=10000, chunk_size=10_000_000,
+        window_size=1_000_000, seed=0, host_inputs=False, timer=None, dist=None, owner=None,
+        keep_seqs=None):
+    """chrom_inputs: per chromosome either (device uint8 tensor, nbytes) or, with host_inputs=True,
+    (pinned host uint8 tensor, nbytes) — the H2D copy then happens inside this call.
+    Returns a dict of host-side results (small) and device handles."""
+    engine.require_cuda()
+    t = timer or StageTimer(False)
+    dev = engine._dev()
+    n = len(chrom_inputs)
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist is not None else (0, 1)
+    if owner is None:
+        owner = [0] * n
+    mine = [i for i in range(n) if owner[i] == rank]
+    h2d_bytes = 0
+
+    # ---- K1-K3 per chromosome -----------------------------------------------------------------------
+    max_bytes = max([chrom_inputs[i][1] for i in mine] + [1])
+    table = engine.CountTable(max_bytes, k)
+    seqs, dumps = {}, {}
+    n_kmers = 0
+    for i in mine:
+        buf, nbytes = chrom_inputs[i]
+        if host_inputs:
+            e = t.start("h2d")
+            d = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
+            d[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+            t.stop(e)
+            h2d_bytes += nbytes
+        else:
+            d = buf
+        e = t.start("pack")
+        seq = engine.pack_fasta(d, nbytes, name=labels[i], trim=True)
+        t.stop(e)
+        if host_inputs:
+            del d
+        dump = engine.count_packed(seq, k, lower_count, table=table, timer=t)
+        seqs[i], dumps[i] = seq, dump
+        n_kmers += dump.n_valid_kmers
+    del table
+
+    # ---- exchange: every rank needs every dump (exact merge of the global k-mer table) -------------
+    if world > 1:
+        e = t.start("exchange")
+        meta = torch.zeros(n, 2, dtype=torch.int64, device=dev)
+        for i in mine:
+            meta[i, 0], meta[i, 1] = len(dumps[i]), dumps[i].length
+        dist.all_reduce(meta)
+        meta_h = meta.cpu().tolist()
+        for i in range(n):
+            cnt, length = int(meta_h[i][0]), int(meta_h[i][1])
+            if owner[i] != rank:
+                dumps[i] = engine.KmerDump(torch.empty(cnt, dtype=torch.int64, device=dev),
+                                           torch.empty(cnt, dtype=torch.int32, device=dev), k, length, 0, 0, labels[i])
+            if cnt:
+                dist.broadcast(dumps[i].keys, src=owner[i])
+                dist.broadcast(dumps[i].counts, src=owner[i])
+        kk = torch.tensor([n_kmers], dtype=torch.int64, device=dev)
+        dist.all_reduce(kk)
+        n_kmers_total = int(kk.item())
+        t.stop(e)
+    else:
+        n_kmers_total = n_kmers
+    dump_list = [dumps[i] for i in range(n)]
+
+    # ---- K3b/K4 matrix + filter -----------------------------------------------------------------------
+    e = t.start("matrix")
+    cm = engine.build_matrix(dump_list, labels)
+    t.stop(e)
+    e = t.start("filter")
+    dm = engine.filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
+                              min_freq=min_freq, max_freq=max_freq)
+    t.stop(e)
+    n_union, M = len(cm), len(dm)
+    del cm
+    if M == 0:
+        raise ValueError("0 kmer remained after filtering. Please reset the filter options.")
+
+    # ---- K5-K8 cluster ---------------------------------------------------------------------------------
+    if nsg is None:
+        nsg = max(len(sg) for sg in sgs)
+    e = t.start("cluster")
+    Z = engine.zscore_rows(dm.norm)
+    G = engine.gram(Z)
+    order = [i for _, i in sorted(zip(labels, range(n)))]
+    lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
+    lab_full_h = lab_full[0].cpu().numpy()
+    R = int(replicates)
+    d_bs = None
+    if R > 0:
+        idx = np.random.RandomState(seed).randint(0, M, size=(R, R)).astype(np.int32)
+        d_idx = torch.from_numpy(idx).to(dev)
+        Gb = engine.gram_batched(Z, d_idx)
+        lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
+        ari, vm = engine.cluster_scores(lab_full_h, lab_b)
+        lab_b_h = lab_b.cpu().numpy()
+        d_bs = [int(100 * int(np.sum(lab_b_h[:, i] == lab_full_h[i])) / R) for i in range(n)]
+    eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
+    t.stop(e)
+    e = t.start("ttest")
+    best, pval, means = engine.ttest_groups(dm.norm, lab_full_h.tolist(), nsg)
+    keep = ~(pval > max_pval)
+    sig_keys = dm.keys[keep].contiguous()
+    sig_vals = best[keep].to(torch.uint8).contiguous()
+    t.stop(e)
+
+    # ---- K9 map ----------------------------------------------------------------------------------------
+    e = t.start("sigtable")
+    sig = engine.SigTable(sig_keys, sig_vals, k)
+    t.stop(e)
+    win_counts = {}
+    for i in mine:
+        e = t.start("map")
+        lines, nh = engine.map_bins(seqs[i], sig, nsg, bin_size, chunk_size)
+        t.stop(e)
+        # ---- stack lines into windows (Circos.stack_matrix) ----
+        e = t.start("stack")
+        L = seqs[i].n_bases
+        nl = lines.shape[0]
+        # window of each line: its first position // window_size (host glue on ~L/bin_size integers)
+        lid = np.arange(nl, dtype=np.int64)
+        if chunk_size:
+            brk = np.unique(np.concatenate([np.arange(0, max(L, 1), bin_size, dtype=np.int64),
+                                            np.maximum(np.arange(0, L + k, chunk_size, dtype=np.int64) - (k - 1), 0)]))
+            brk = brk[brk < max(L, 1)]
+            first_line = brk // bin_size + (brk + k - 1) // chunk_size
+            pos = np.zeros(nl, dtype=np.int64)
+            pos[first_line] = brk
+        else:
+            pos = lid * bin_size
+        win = (pos // window_size).astype(np.int32)
+        nwin = int(win.max()) + 1 if nl else 0
+        out = torch.zeros(max(nwin, 1), nsg, dtype=torch.int64, device=dev)
+        lc = lines.to(torch.int64)
+        _lib.call("spk_stack_windows", engine._p(lc), engine._p(torch.from_numpy(win).to(dev)), nl, nsg,
+                  engine._p(out), engine._stream())
+        win_counts[i] = out[:nwin]
+        t.stop(e)
+    if keep_seqs is not None:
+        keep_seqs.update(seqs)
+
+    # ---- gather windows, K10 ---------------------------------------------------------------------------
+    if world > 1:
+        e = t.start("exchange")
+        nw = torch.zeros(n, dtype=torch.int64, device=dev)
+        for i in mine:
+            nw[i] = win_counts[i].shape[0]
+        dist.all_reduce(nw)
+        for i in range(n):
+            if owner[i] != rank:
+                win_counts[i] = torch.empty(int(nw[i].item()), nsg, dtype=torch.int64, device=dev)
+            if win_counts[i].numel():
+                dist.broadcast(win_counts[i], src=owner[i])
+        t.stop(e)
+    e = t.start("enrich")
+    allw = torch.cat([win_counts[i] for i in range(n)], dim=0)
+    nz = allw.any(dim=1)                      # zero-hit windows are absent in the reference (Circos.py:737)
+    allw = allw[nz].contiguous()
+    enr = engine.fisher_enrich(allw, max_pval=max_pval)
+    t.stop(e)
+    d2h_bytes = int(dm.norm.numel() * 8 + dm.keys.numel() * 8 + allw.numel() * 8 * 4)
+    return dict(n_kmers=n_kmers_total, n_kmers_local=n_kmers, n_union=n_union, n_diff=M, n_sig=int(sig_keys.numel()),
+                n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
+                lengths=[d.length for d in dump_list], enrich=enr, dm=dm, pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
+                h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, matrix_host=(engine.u64_numpy(dm.keys), dm.norm.cpu().numpy()))

