@@ -217,7 +217,7 @@ def main():
         e0.record()
         res = None
         for _ in range(n_steps):
-            res = hotpath.run(inputs, host_inputs=host_inputs, timer=timer, **kw)
+            res = hotpath.run(inputs, host_inputs=host_inputs, timer=timer, return_host=host_inputs, **kw)
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -278,7 +278,7 @@ def main():
         torch.cuda.synchronize()
         dev_inputs = None
         torch.cuda.empty_cache()
-        hotpath.run(host_inputs, host_inputs=True, **kw)          # warm-up
+        hotpath.run(host_inputs, host_inputs=True, return_host=True, **kw)          # warm-up
         esecs, eres = timed(args.steps, True, host_inputs)
         hb = torch.tensor([float(eres["h2d_bytes"]), float(eres["d2h_bytes"])], dtype=torch.float64, device="cuda")
         if world > 1:

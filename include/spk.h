@@ -83,6 +83,22 @@ int spk_count_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint6
                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K2+K3 (v2)  partitioned counting: same semantics and outputs as spk_count_canonical +
+ * spk_table_stats + spk_table_extract in ONE asynchronous call, but the chromosome is first split
+ * into hash partitions whose tables stay resident in L2 (see subphaser_b200/csrc/spk_pcount.cu).
+ * Requires n_bases < 2^32 - 1.  d_ws: spk_pcount_workspace_bytes(n_bases, k) bytes, 256-B aligned.
+ * d_keys/d_counts receive every k-mer with count >= lower_count in arbitrary order (like a
+ * jellyfish dump); entries beyond `cap` are dropped — compare d_stats[5] with cap.
+ * d_stats (uint64[8], overwritten): [0] valid k-mer occurrences, [1] failed inserts (must be 0),
+ *   [4] distinct, [5] k-mers >= lower_count, [6] sum of their counts (lengths[i]), [7] sum of all counts.
+ * ---------------------------------------------------------------------------------------------- */
+size_t spk_pcount_workspace_bytes(uint64_t n_bases, int k);
+int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                         uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
+                         uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
+                         uint32_t histo_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K3  table scan: `jellyfish dump -c -L lower_count` + the dump parse of Jellyfish.py:90-98
  * spk_table_stats: one pass over the table.  d_out (uint64[4]): [0] distinct k-mers, [1] k-mers with
  *   count >= lower_count, [2] sum of those counts (this is `lengths[i]`, Jellyfish.py:97,449),
@@ -122,7 +138,7 @@ int spk_table_extract(const void* d_table, size_t table_bytes, int k, int layout
  * by_count != 0 uses the (summed) raw count instead of count/length (Jellyfish.py:632,636).
  * d_counters (uint64[4], zeroed): [0] rows passing the fold test, [1] rows kept.
  * spk_filter_select compacts the kept rows in row order into (d_out_keys[j], d_out_rows[j]);
- * d_scan_ws: uint32[nrows+1], d_scan_ws[nrows] ends up holding the number kept.  The caller may then
+ * d_scan_ws: uint32[nrows + 2 + nrows/8192], d_scan_ws[nrows] ends up holding the number kept.  The caller may then
  * sort the pairs by key (spk_sort_pairs_u64) for a deterministic row order.  spk_filter_emit writes,
  * for the m rows listed in d_rows: d_out_norm[j*ncol + c] = (double)count / (double)length[c]
  * (Jellyfish.py:648) and d_out_tot[j].
@@ -175,6 +191,11 @@ int spk_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
   * d_out[d_line_window[l] * S + c] += d_line_counts[l * S + c]  (d_out int64 [W x S], zeroed). */
 int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d_line_window, uint64_t n_lines,
                       int S, int64_t* d_out, void* stream);
+/* spk_stack_lines: the same stacking for the line-count array of ONE chromosome straight from
+ * spk_map_bins (no text round trip): line l is assigned to window (its bin start) / window_size. */
+int spk_stack_lines(const uint32_t* d_line_counts, uint64_t n_lines, int S, int k, uint64_t bin_size,
+                    uint64_t chunk_size, uint64_t window_size, uint64_t n_bases, int64_t* d_out,
+                    uint64_t n_windows, void* stream);
 int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, uint64_t* d_skeys,
                         uint8_t* d_svals, uint64_t sslots, uint64_t* d_fail, void* stream);
 uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size, uint64_t chunk_size);

@@ -28,6 +28,8 @@ SIGNATURES = {
     "spk_count_table_slots": (c_u64, [c_sz, c_i]),
     "spk_count_table_init": (c_i, [c_p, c_sz, c_i, c_i, c_p]),
     "spk_count_canonical": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_sz, c_i, c_p, c_p]),
+    "spk_pcount_workspace_bytes": (c_sz, [c_u64, c_i]),
+    "spk_pcount_canonical": (c_i, [c_p, c_p, c_u64, c_i, c_u32, c_p, c_sz, c_p, c_p, c_u64, c_p, c_p, c_u32, c_p]),
     "spk_table_scan_blocks": (c_i, []),
     "spk_table_stats": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u32, c_p]),
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "spk_sort_workspace_bytes": (c_sz, [c_u64]),
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),
     "spk_stack_windows": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
+    "spk_stack_lines": (c_i, [c_p, c_u64, c_i, c_i, c_u64, c_u64, c_u64, c_u64, c_p, c_u64, c_p]),
     "spk_sig_table_build": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_p]),
     "spk_map_num_lines": (c_u64, [c_u64, c_i, c_u64, c_u64]),
     "spk_map_bins": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p, c_u64, c_i, c_u64, c_u64, c_p, c_u64,

@@ -158,7 +158,45 @@ k_stack_windows(const int64_t* __restrict__ line_counts, const uint32_t* __restr
     }
 }
 
+// Device-side stack of the (bin, chunk) lines of one chromosome: line l covers positions starting at
+// p_l = min{p : line_of(p) >= l}; its printed start is (p_l / bin_size) * bin_size and the reference
+// assigns it to window start // window_size (Circos.py:732).
+__global__ void __launch_bounds__(256)
+k_stack_lines(const uint32_t* __restrict__ line_counts, uint64_t n_lines, int S, int k, uint64_t bin_size,
+              uint64_t chunk_size, uint64_t window_size, uint64_t n_bases, int64_t* __restrict__ out,
+              uint64_t n_windows) {
+    const uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    bool any = false;
+    for (int c = 0; c < S; c++) any |= line_counts[l * S + c] != 0;
+    if (!any) return;
+    uint64_t lo = 0, hi = n_bases;  // first p with line_of(p) >= l
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (line_of(mid, k, bin_size, chunk_size) >= l) hi = mid;
+        else lo = mid + 1;
+    }
+    const uint64_t w = ((lo / bin_size) * bin_size) / window_size;
+    if (w >= n_windows) return;
+    for (int c = 0; c < S; c++) {
+        const uint32_t v = line_counts[l * S + c];
+        if (v) atomicAdd((unsigned long long*)&out[w * S + c], (unsigned long long)v);
+    }
+}
+
 }  // namespace
+
+extern "C" int spk_stack_lines(const uint32_t* d_line_counts, uint64_t n_lines, int S, int k,
+                               uint64_t bin_size, uint64_t chunk_size, uint64_t window_size,
+                               uint64_t n_bases, int64_t* d_out, uint64_t n_windows, void* stream) {
+    SPK_CHECK_ARG(S >= 1 && bin_size >= 1 && window_size >= 1, "bad arguments");
+    if (n_lines == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_line_counts && d_out, "null pointer");
+    k_stack_lines<<<(unsigned)((n_lines + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        d_line_counts, n_lines, S, k, bin_size, chunk_size, window_size, n_bases, d_out, n_windows);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
 
 extern "C" int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d_line_window,
                                  uint64_t n_lines, int S, int64_t* d_out, void* stream) {

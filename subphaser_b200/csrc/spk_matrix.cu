@@ -143,45 +143,79 @@ k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
     }
 }
 
-// exclusive scan of the keep flags -> output positions (single CTA; nrows <= ~1e9 is fine but slow;
-// a chained version can replace it if the union grows that large)
-__global__ void __launch_bounds__(1024) k_scan_flags(const uint8_t* __restrict__ flags, uint64_t n,
-                                                      uint32_t* __restrict__ pos) {
+// Exclusive scan of the keep flags -> output positions, three passes: per-CTA totals over 8192-row
+// segments, a single-CTA scan of those totals, then the in-segment scan.
+constexpr int SF_PER = 8;
+constexpr int SF_SEG = 1024 * SF_PER;
+
+__device__ __forceinline__ uint32_t sf_block_scan(uint32_t sum, uint32_t* s_warp, uint32_t* total) {
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t prefix = 0, tot = 0;
+    for (int w = 0; w < 32; w++) {
+        if (w < (int)(threadIdx.x >> 5)) prefix += s_warp[w];
+        tot += s_warp[w];
+    }
+    __syncthreads();
+    *total = tot;
+    return prefix + incl - sum;
+}
+
+__global__ void __launch_bounds__(1024) k_flags_seg_totals(const uint8_t* __restrict__ flags, uint64_t n,
+                                                            uint32_t* __restrict__ seg_tot) {
+    __shared__ uint32_t s_warp[32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * SF_SEG + (uint64_t)threadIdx.x * SF_PER;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < SF_PER; q++) sum += (i0 + q < n) ? ((flags[i0 + q] >> 1) & 1u) : 0u;
+    uint32_t tot;
+    sf_block_scan(sum, s_warp, &tot);
+    if (threadIdx.x == 0) seg_tot[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_flags_scan_totals(uint32_t* seg_tot, uint64_t nseg,
+                                                             uint32_t* __restrict__ grand) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    constexpr int PER = 8;
-    for (uint64_t base = 0; base < n; base += 1024 * PER) {
-        const uint64_t i0 = base + (uint64_t)threadIdx.x * PER;
-        uint32_t loc[PER];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            loc[q] = (i0 + q < n) ? ((flags[i0 + q] >> 1) & 1u) : 0u;
-            sum += loc[q];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((threadIdx.x & 31) >= o) incl += t;
-        }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    for (uint64_t base = 0; base < nseg; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint32_t v = (i < nseg) ? seg_tot[i] : 0;
+        uint32_t tot;
+        const uint32_t excl = sf_block_scan(v, s_warp, &tot);
+        if (i < nseg) seg_tot[i] = s_carry + excl;
         __syncthreads();
-        uint32_t prefix = s_carry;
-        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix += s_warp[w];
-        uint32_t run = prefix + incl - sum;
-#pragma unroll
-        for (int q = 0; q < PER; q++) {
-            if (i0 + q < n) pos[i0 + q] = run;
-            run += loc[q];
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = prefix + incl;
+        if (threadIdx.x == 0) s_carry += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) pos[n] = s_carry;
+    if (threadIdx.x == 0) *grand = s_carry;
+}
+
+__global__ void __launch_bounds__(1024) k_flags_seg_scan(const uint8_t* __restrict__ flags, uint64_t n,
+                                                          const uint32_t* __restrict__ seg_off,
+                                                          uint32_t* __restrict__ pos) {
+    __shared__ uint32_t s_warp[32];
+    const uint64_t i0 = (uint64_t)blockIdx.x * SF_SEG + (uint64_t)threadIdx.x * SF_PER;
+    uint32_t loc[SF_PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < SF_PER; q++) {
+        loc[q] = (i0 + q < n) ? ((flags[i0 + q] >> 1) & 1u) : 0u;
+        sum += loc[q];
+    }
+    uint32_t tot;
+    uint32_t run = seg_off[blockIdx.x] + sf_block_scan(sum, s_warp, &tot);
+#pragma unroll
+    for (int q = 0; q < SF_PER; q++) {
+        if (i0 + q < n) pos[i0 + q] = run;
+        run += loc[q];
+    }
 }
 
 // compaction of the kept rows in row order: (key, row id) pairs
@@ -278,8 +312,19 @@ extern "C" int spk_filter_select(const uint64_t* d_row_keys, const uint8_t* d_fl
     SPK_CHECK_ARG(d_flags && d_scan_ws, "null pointer");
     SPK_CHECK_ARG(nrows < 0xffffffffull, "too many rows");
     cudaStream_t st = (cudaStream_t)stream;
-    k_scan_flags<<<1, 1024, 0, st>>>(d_flags, nrows, d_scan_ws);
+    // d_scan_ws: [0, nrows] positions (+ grand total at [nrows]), then the per-segment totals
+    const uint64_t nseg = (nrows + SF_SEG - 1) / SF_SEG;
+    uint32_t* seg = d_scan_ws + nrows + 1;
+    if (nseg) {
+        k_flags_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(d_flags, nrows, seg);
+        SPK_LAUNCH_CHECK();
+    }
+    k_flags_scan_totals<<<1, 1024, 0, st>>>(seg, nseg, d_scan_ws + nrows);
     SPK_LAUNCH_CHECK();
+    if (nseg) {
+        k_flags_seg_scan<<<(unsigned)nseg, 1024, 0, st>>>(d_flags, nrows, seg, d_scan_ws);
+        SPK_LAUNCH_CHECK();
+    }
     if (nrows == 0 || cap == 0) return SPK_OK;
     SPK_CHECK_ARG(d_row_keys && d_out_keys && d_out_rows, "null pointer");
     k_filter_select<<<grid_for(nrows), MX_THREADS, 0, st>>>(d_row_keys, d_flags, nrows, d_scan_ws,

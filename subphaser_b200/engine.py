@@ -126,19 +126,36 @@ class KmerDump:
 
 
 class CountTable:
-    """Reusable device scratch for counting chromosomes of up to `max_bases` bases."""
+    """Reusable device scratch for counting chromosomes of up to `max_bases` bases.
 
-    def __init__(self, max_bases, k):
+    mode "partitioned" (default): spk_pcount_canonical, tables stay in L2 (spk_pcount.cu).
+    mode "global": the v1 single open-addressed table in HBM (spk_count.cu); used for chromosomes of
+    2^32 bases or more, or when SPK_COUNT_MODE=global."""
+
+    def __init__(self, max_bases, k, lower_count=1, mode=None):
         require_cuda()
         lib = _lib.load()
         self.k = int(k)
         self.max_bases = int(max_bases)
-        self.layout = lib.spk_count_layout(self.max_bases, self.k)
-        self.table_bytes = lib.spk_count_table_bytes(self.max_bases, self.k)
-        self.table = _empty(self.table_bytes, torch.uint8)
-        nb = lib.spk_table_scan_blocks()
-        self.block_counts = _empty(3 * nb + 2, torch.int32)
+        self.lower_count = max(int(lower_count), 1)
+        if mode is None:
+            mode = os.environ.get("SPK_COUNT_MODE", "partitioned")
+        if self.max_bases >= 2**32 - 1:
+            mode = "global"
+        self.mode = mode
         self.stats = _zeros(8, torch.int64)
+        if mode == "partitioned":
+            self.ws_bytes = lib.spk_pcount_workspace_bytes(self.max_bases, self.k)
+            self.ws = _empty(self.ws_bytes, torch.uint8)
+            self.cap = self.max_bases // self.lower_count + 1024
+            self.out_keys = _empty(self.cap, torch.int64)
+            self.out_counts = _empty(self.cap, torch.int32)
+        else:
+            self.layout = lib.spk_count_layout(self.max_bases, self.k)
+            self.table_bytes = lib.spk_count_table_bytes(self.max_bases, self.k)
+            self.table = _empty(self.table_bytes, torch.uint8)
+            nb = lib.spk_table_scan_blocks()
+            self.block_counts = _empty(3 * nb + 2, torch.int32)
 
     def slots(self):
         return _lib.load().spk_count_table_slots(self.table_bytes, self.layout)
@@ -148,11 +165,29 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
     """K2 + K3 on one packed chromosome -> KmerDump.  `timer` (hotpath.StageTimer) brackets the
     stages with CUDA events on the launching stream."""
     require_cuda()
-    if table is None or table.max_bases < seq.n_bases or table.k != k:
-        table = CountTable(max(seq.n_bases, 1), k)
+    if (table is None or table.max_bases < seq.n_bases or table.k != k
+            or (table.mode == "partitioned" and table.lower_count > max(int(lower_count), 1))):
+        table = CountTable(max(seq.n_bases, 1), k, lower_count)
     st = _stream()
     tick = (lambda name: timer.start(name)) if timer is not None else (lambda name: None)
     tock = (lambda e: timer.stop(e)) if timer is not None else (lambda e: None)
+    histo = _zeros(histo_len, torch.int64) if histo_len else None
+    if table.mode == "partitioned":
+        e = tick("count")
+        call("spk_pcount_canonical", _p(seq.packed), _p(seq.valid), seq.n_bases, k, lower_count, _p(table.ws),
+             table.ws_bytes, _p(table.out_keys), _p(table.out_counts), table.cap, _p(table.stats), _p(histo),
+             histo_len, st)
+        tock(e)
+        n_valid, n_fail, _, _, distinct, n_ge, sum_ge, _ = (int(x) for x in table.stats.cpu().tolist())
+        if n_fail:
+            raise OverflowError("k-mer table full: %d inserts failed" % n_fail)
+        if n_ge > table.cap:
+            raise OverflowError("dump capacity exceeded: %d > %d" % (n_ge, table.cap))
+        e = tick("scan")
+        keys = table.out_keys[:n_ge].clone()
+        counts = table.out_counts[:n_ge].clone()
+        tock(e)
+        return KmerDump(keys, counts, k, sum_ge, n_valid, distinct, seq.name, histo)
     e = tick("table_init")
     call("spk_count_table_init", _p(table.table), table.table_bytes, k, table.layout, st)
     table.stats.zero_()
@@ -162,7 +197,6 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
          table.table_bytes, table.layout, _p(table.stats), st)
     tock(e)
     e = tick("scan")
-    histo = _zeros(histo_len, torch.int64) if histo_len else None
     call("spk_table_stats", _p(table.table), table.table_bytes, k, table.layout, lower_count,
          _p(table.stats[4:]), _p(table.block_counts), _p(histo), histo_len, st)
     n_valid, n_fail, _, _, distinct, n_ge, sum_ge, _ = (int(x) for x in table.stats.cpu().tolist())
@@ -267,7 +301,7 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
          len(grp_off) - 1, _p(d_mem), float(min_fold), int(baseline), int(bool(by_count)), float(ratio),
          float(min_freq), float(max_freq), _p(flags), _p(tot), _p(counters), st)
     n_fold, n_keep = (int(x) for x in counters[:2].cpu().tolist())
-    scan = _empty(U + 1, torch.int32)
+    scan = _empty(U + 2 + U // 8192 + 1, torch.int32)
     keys = _empty(n_keep, torch.int64)
     rows = _empty(n_keep, torch.int32)
     call("spk_filter_select", _p(cm.row_keys), _p(flags), U, _p(scan), _p(keys), _p(rows), n_keep, st)

@@ -60,7 +60,7 @@ class StageTimer:
 def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, ratio=1, min_freq=200,
         max_freq=10000, nsg=None, replicates=1000, max_pval=0.05, bin_size=10000, chunk_size=10_000_000,
         window_size=1_000_000, seed=0, host_inputs=False, timer=None, dist=None, owner=None,
-        keep_seqs=None):
+        keep_seqs=None, return_host=False):
     """chrom_inputs: per chromosome either (device uint8 tensor, nbytes) or, with host_inputs=True,
     (pinned host uint8 tensor, nbytes) — the H2D copy then happens inside this call.
     Returns a dict of host-side results (small) and device handles."""
@@ -76,7 +76,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
 
     # ---- K1-K3 per chromosome -----------------------------------------------------------------------
     max_bytes = max([chrom_inputs[i][1] for i in mine] + [1])
-    table = engine.CountTable(max_bytes, k)
+    table = engine.CountTable(max_bytes, k, lower_count)
     seqs, dumps = {}, {}
     n_kmers = 0
     for i in mine:
@@ -173,27 +173,15 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         e = t.start("map")
         lines, nh = engine.map_bins(seqs[i], sig, nsg, bin_size, chunk_size)
         t.stop(e)
-        # ---- stack lines into windows (Circos.stack_matrix) ----
+        # ---- stack lines into windows (Circos.stack_matrix) on the device ----
         e = t.start("stack")
         L = seqs[i].n_bases
         nl = lines.shape[0]
-        # window of each line: its first position // window_size (host glue on ~L/bin_size integers)
-        lid = np.arange(nl, dtype=np.int64)
-        if chunk_size:
-            brk = np.unique(np.concatenate([np.arange(0, max(L, 1), bin_size, dtype=np.int64),
-                                            np.maximum(np.arange(0, L + k, chunk_size, dtype=np.int64) - (k - 1), 0)]))
-            brk = brk[brk < max(L, 1)]
-            first_line = brk // bin_size + (brk + k - 1) // chunk_size
-            pos = np.zeros(nl, dtype=np.int64)
-            pos[first_line] = brk
-        else:
-            pos = lid * bin_size
-        win = (pos // window_size).astype(np.int32)
-        nwin = int(win.max()) + 1 if nl else 0
+        nwin = int(((max(L - 1, 0) // bin_size) * bin_size) // window_size) + 1 if L else 0
         out = torch.zeros(max(nwin, 1), nsg, dtype=torch.int64, device=dev)
-        lc = lines.to(torch.int64)
-        _lib.call("spk_stack_windows", engine._p(lc), engine._p(torch.from_numpy(win).to(dev)), nl, nsg,
-                  engine._p(out), engine._stream())
+        if nl:
+            _lib.call("spk_stack_lines", engine._p(lines), nl, nsg, k, int(bin_size), int(chunk_size),
+                      int(window_size), L, engine._p(out), nwin, engine._stream())
         win_counts[i] = out[:nwin]
         t.stop(e)
     if keep_seqs is not None:
@@ -222,4 +210,5 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     return dict(n_kmers=n_kmers_total, n_kmers_local=n_kmers, n_union=n_union, n_diff=M, n_sig=int(sig_keys.numel()),
                 n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
                 lengths=[d.length for d in dump_list], enrich=enr, dm=dm, pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
-                h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, matrix_host=(engine.u64_numpy(dm.keys), dm.norm.cpu().numpy()))
+                h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes if return_host else int(allw.numel() * 8 * 4),
+                matrix_host=(engine.u64_numpy(dm.keys), dm.norm.cpu().numpy()) if return_host else None)

@@ -7,11 +7,22 @@ import spk_testutil as util
 pytestmark = pytest.mark.gpu
 
 
+MODE = ["partitioned"]
+
+
+@pytest.fixture(params=["partitioned", "global"], autouse=True)
+def count_mode(request):
+    """every test runs against both counters: v2 (L2-resident partitions) and v1 (global table)"""
+    MODE[0] = request.param
+    yield
+
+
 def _gpu_count(fasta_bytes, k, lower):
     from subphaser_b200 import engine
     d, n = engine.to_device_bytes(fasta_bytes)
     seq = engine.pack_fasta(d, n)
-    dump = engine.count_packed(seq, k, lower)
+    table = engine.CountTable(max(seq.n_bases, 1), k, lower, mode=MODE[0])
+    dump = engine.count_packed(seq, k, lower, table=table)
     keys, counts = dump.to_host()
     order = np.argsort(keys, kind="stable")
     return seq, dump, keys[order], counts[order]

@@ -335,3 +335,29 @@ def test_pca_vs_sklearn_full_svd():
     for j in range(3):
         sgn = 1.0 if np.dot(scores[:, j], X[:, j]) >= 0 else -1.0
         np.testing.assert_allclose(sgn * scores[:, j], X[:, j], rtol=0, atol=1e-8)
+
+
+def test_stack_lines_kernel_matches_reference_stack(tmp_path):
+    """hotpath's device-side stacking (spk_stack_lines) == Circos.stack_matrix of the reference text."""
+    import torch
+    from subphaser_b200 import Seqs, _lib, engine
+    for ci, case in enumerate(load("map_stack.json")):
+        seq = case["seq"]
+        fa = (">chrX\n" + seq + "\n").encode()
+        d, n = engine.to_device_bytes(fa)
+        ps = engine.pack_fasta(d, n)
+        sig, k = Seqs._sig_table(case["d_kmers"], case["k"], case["sg_names"])
+        S = len(case["sg_names"])
+        chunk = int(case["window_size"]) if case["chunk"] else 0
+        lines, nh = engine.map_bins(ps, sig, S, case["bin_size"], chunk)
+        for ws, st in case["stacks"].items():
+            ws_i = int(float(ws))
+            L = ps.n_bases
+            nwin = ((max(L - 1, 0) // case["bin_size"]) * case["bin_size"]) // ws_i + 1
+            out = torch.zeros(nwin, S, dtype=torch.int64, device="cuda")
+            _lib.call("spk_stack_lines", engine._p(lines), lines.shape[0], S, k, case["bin_size"], chunk, ws_i, L,
+                      engine._p(out), nwin, engine._stream())
+            got = out.cpu().numpy()
+            nz = got.any(axis=1)
+            assert [[int(x) for x in r] for r in got[nz]] == st["counts"]
+            assert [int(w) * ws_i for w in np.nonzero(nz)[0]] == [c[1] for c in st["coords"]]
