@@ -1,29 +1,32 @@
-// K2 (v2): partitioned canonical k-mer counting — the table never leaves L2.
+// K2+K3 (partitioned): canonical k-mer counting with every random access on-chip.
 //
-// The v1 kernel (spk_count.cu) inserts straight into a multi-GB table: every k-mer is a random DRAM
-// read-modify-write and the chip saturates at ~1e10 inserts/s (GUPS-bound; ncu: 111 B DRAM read per
-// k-mer, 27 % L2 hit, 29 % DRAM throughput).  Here the chromosome is first split into P hash
-// partitions, streamed to HBM as 4-byte remainders, and each partition is then counted in an
-// open-addressed table small enough (<= ~16 MB) to stay resident in the 126 MB L2:
+// Measured on B200 (tools/atomics_bench.cu): a dependent "load slot, then atomic on it" sustains only
+// ~1.5e10/s when the table lives in HBM (the v1 kernel, spk_count.cu, sits exactly there) and ~6e10/s
+// even when the table is L2-resident, while shared-memory atomics run > 3e11/s.  So the chromosome is
+// split into P = 2^pbits hash partitions small enough that one partition's table fits in the shared
+// memory of a CTA; HBM only sees streaming traffic:
 //
-//   phase 0  k_part_hist     per 64-tile chunk: histogram of partition ids (smem atomics)
-//            k_part_offsets  column scans -> exact write offset of every (chunk, partition) run
-//   phase 1  k_part_scatter  recompute the k-mers, append remainder r to its partition (smem cursors)
-//   phase 2  k_part_count    G partitions at a time: coalesced read of r, probe + CAS/RED in L2
-//            k_part_extract  scan the G tables (L2 hits): stats, dump count >= L, clear for reuse
+//   phase 0  k_part_pass<hist>     recompute k-mers tile by tile (TMA-staged), RED partition sizes
+//            k_scan_*              exclusive scan of the P sizes -> partition extents, cursors
+//   phase 1  k_part_pass<scatter>  same traversal, append the 32-bit remainder r to its partition
+//   phase 2  k_part_count          one CTA per partition: stream r, insert into an smem table
+//                                  (CAS on new keys, 32-bit add on hits), then scan the table:
+//                                  stats, histogram, dump of count >= L
 //
-// DRAM traffic per k-mer: 0.375 B (sequence, twice) + 4 B write + 4 B read, all streaming.
-// Partitioning uses a bijective mixer f on the 2k-bit canonical word: partition = top bits of f(u),
-// remainder r = low bits; the dump inverts f, so keys are exact.  Semantics identical to v1 / jellyfish.
+// DRAM traffic per k-mer: 2 x 0.375 B (sequence, read twice) + 4 B write + 4 B read.
+// Partitioning uses a bijective mixer f on the 2k-bit canonical word: partition = top pbits of f(u),
+// remainder r = the rest; the dump applies f^-1, so keys are exact and the result is bit-identical to
+// the v1 kernel / the jellyfish semantics (only the dump ORDER differs, which is arbitrary anyway).
 #include <stdlib.h>
 #include "spk_common.cuh"
 #include "spk_tile.cuh"
 
 namespace {
 
-constexpr int PC_CHUNK_TILES = 64;
-constexpr int PC_MAX_P = 1024;
-constexpr int PC_BATCH = 8;
+constexpr int PC_SLOTS = 8192;          // smem table slots per CTA (64 KB as u64, 96 KB for wide keys)
+constexpr int PC_TARGET = 3072;         // planned mean entries per partition (all distinct -> load 0.375)
+constexpr int PC_MAX_PBITS = 22;
+constexpr int PC_THREADS = 256;
 constexpr uint64_t PC_C1 = 0xff51afd7ed558ccdULL;
 constexpr uint64_t PC_C2 = 0xc4ceb9fe1a85ec53ULL;
 
@@ -38,7 +41,7 @@ static_assert(PC_C1 * PC_C1_INV == 1ull && PC_C2 * PC_C2_INV == 1ull, "inverse c
 
 struct Mixer {
     uint64_t mask;  // 2k low bits
-    int s;          // xorshift distance >= ceil(2k/2): x ^= x >> s is an involution on 2k-bit words
+    int s;          // xorshift distance k = (2k)/2: x ^= x >> s is an involution on 2k-bit words
     int rbits;      // remainder bits = 2k - pbits
     __host__ __device__ uint64_t fwd(uint64_t u) const {
         uint64_t x = u;
@@ -60,146 +63,99 @@ struct Mixer {
 };
 
 struct PcPlan {
-    int k, pbits, P, ent64;       // ent64: remainders do not fit 32 bits
+    int k, pbits, ent64;
+    uint64_t P;
     Mixer mx;
-    uint64_t n_tiles, n_chunks;
-    uint64_t T;                   // table slots per partition
-    int G;                        // partitions counted concurrently
-    // workspace offsets (bytes)
-    size_t off_buf, off_hist, off_psize, off_pstart, off_tables, off_cursor, total;
+    uint64_t n_tiles;
+    size_t off_buf, off_psize, off_pstart, off_cursor, off_segs, off_out, total;
 };
 
 inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
-
-int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return (e && *e) ? atoi(e) : dflt;
-}
 
 int make_plan(uint64_t n_bases, int k, PcPlan* pl) {
     if (k < 1 || k > 32) return SPK_EINVAL;
     if (n_bases >= 0xffffffffull) return SPK_EINVAL;  // 32-bit partition offsets
     pl->k = k;
-    const double table_mb = (double)env_int("SPK_PCOUNT_TABLE_MB", 16);
-    // smallest power of two P with (n/P)/0.7 * 8 B <= table_mb
-    int pbits = 4;
-    while (pbits < 10 && ((double)n_bases / (double)(1u << pbits)) / 0.7 * 8.0 > table_mb * 1e6) pbits++;
-    if (2 * k - pbits > 32 && 2 * k - 10 <= 32) pbits = 2 * k - 32;  // keep remainders in 32 bits if possible
-    if (pbits > 2 * k) pbits = 2 * k;                                 // tiny k: at most 4^k partitions
+    int pbits = 2;
+    while (pbits < PC_MAX_PBITS && (n_bases >> pbits) > (uint64_t)PC_TARGET) pbits++;
+    if (pbits > 2 * k) pbits = 2 * k;  // tiny k: at most 4^k distinct words
     pl->pbits = pbits;
-    pl->P = 1 << pbits;
+    pl->P = 1ull << pbits;
     pl->ent64 = (2 * k - pbits > 32) ? 1 : 0;
     pl->mx.mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-    pl->mx.s = k;  // = 2k/2
+    pl->mx.s = k;
     pl->mx.rbits = 2 * k - pbits;
     pl->n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
-    pl->n_chunks = (pl->n_tiles + PC_CHUNK_TILES - 1) / PC_CHUNK_TILES;
-    // distinct keys spread uniformly over partitions whatever their multiplicities
-    uint64_t per_part = n_bases / pl->P + 1;
-    if (pl->mx.rbits < 40 && (1ull << pl->mx.rbits) < per_part) per_part = 1ull << pl->mx.rbits;
-    pl->T = (uint64_t)((double)per_part / 0.7) + 4096;
-    pl->G = env_int("SPK_PCOUNT_G", 4);
-    if (pl->G > pl->P) pl->G = pl->P;
-    if (pl->G < 1) pl->G = 1;
     size_t off = 0;
     pl->off_buf = off;
     off += al256((size_t)(n_bases + 64) * (pl->ent64 ? 8 : 4));
-    pl->off_hist = off;
-    off += al256((size_t)(pl->n_chunks + 1) * pl->P * 4);
     pl->off_psize = off;
-    off += al256((size_t)pl->P * 4);
+    off += al256((size_t)(pl->P + 1) * 4);
     pl->off_pstart = off;
     off += al256((size_t)(pl->P + 1) * 4);
-    pl->off_tables = off;
-    off += al256((size_t)pl->G * pl->T * (pl->ent64 ? 12 : 8));
     pl->off_cursor = off;
+    off += al256((size_t)(pl->P + 1) * 4);
+    pl->off_segs = off;
+    off += al256((size_t)(pl->P / 1024 + 2) * 4);
+    pl->off_out = off;
     off += 256;
     pl->total = off;
     return SPK_OK;
 }
 
-// ---- phases 0 and 1 share the traversal ---------------------------------------------------------------
+// ---- phases 0 and 1: one traversal of the packed sequence -----------------------------------------------
 template <bool SCATTER, bool ENT64>
 __global__ void __launch_bounds__(SPK_TILE_THREADS, 4)
-k_part_pass(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles,
-            int k, Mixer mx, int P, uint32_t* __restrict__ chunk_hist, const uint32_t* __restrict__ pstart,
-            void* __restrict__ buf, uint64_t* __restrict__ stats) {
+k_part_pass(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k,
+            Mixer mx, uint32_t* __restrict__ psize, uint32_t* __restrict__ cursor, void* __restrict__ buf,
+            uint64_t* __restrict__ stats) {
     __shared__ SpkTileSmem sm;
-    __shared__ uint32_t s_bins[PC_MAX_P];
     const int tid = threadIdx.x;
     const SpkKmerParams kp = spk_kmer_params(k);
-    const uint64_t chunk = blockIdx.x;
-    const uint64_t t0 = chunk * PC_CHUNK_TILES;
-    const uint64_t t1 = min(t0 + PC_CHUNK_TILES, n_tiles);
     spk_tile_init(sm);
-    for (int p = tid; p < P; p += SPK_TILE_THREADS)
-        s_bins[p] = SCATTER ? (pstart[p] + chunk_hist[chunk * P + p]) : 0u;
     uint64_t n_valid = 0;
-    if (tid == 0 && t0 < t1) spk_tile_issue(sm, packed, valid, t0, 0);
-    uint32_t it = 0;
-    for (uint64_t tile = t0; tile < t1; tile++, it++) {
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) spk_tile_issue(sm, packed, valid, tile, 0);
+    const uint64_t rmask = (mx.rbits >= 64) ? ~0ull : ((1ull << mx.rbits) - 1);
+    for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
         const int b = it & 1;
-        __syncthreads();  // buffer b^1 free; s_bins initialised (first iteration)
-        if (tid == 0 && tile + 1 < t1) spk_tile_issue(sm, packed, valid, tile + 1, b ^ 1);
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < n_tiles) spk_tile_issue(sm, packed, valid, tile + gridDim.x, b ^ 1);
         spk_mbar_wait(&sm.bar[b], (it >> 1) & 1);
         uint64_t key[SPK_KMERS_PER_THREAD];
         uint32_t okmask;
         spk_tile_kmers(sm, b, kp, key, okmask);
         n_valid += __popc(okmask);
+        if (!SCATTER) {
 #pragma unroll
-        for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
-            if ((okmask >> j) & 1u) {
-                const uint64_t h = mx.fwd(key[j]);
-                const uint32_t p = (uint32_t)(h >> mx.rbits);
-                const uint32_t pos = atomicAdd(&s_bins[p], 1u);
-                if (SCATTER) {
-                    const uint64_t r = h & ((1ull << mx.rbits) - 1);
-                    if (ENT64) ((uint64_t*)buf)[pos] = r;
-                    else ((uint32_t*)buf)[pos] = (uint32_t)r;
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+                if ((okmask >> j) & 1u) atomicAdd(&psize[mx.fwd(key[j]) >> mx.rbits], 1u);
+        } else {
+            // issue all 16 cursor atomics first, then the 16 stores
+            uint32_t pos[SPK_KMERS_PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                key[j] = mx.fwd(key[j]);
+                pos[j] = ((okmask >> j) & 1u) ? atomicAdd(&cursor[key[j] >> mx.rbits], 1u) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                if ((okmask >> j) & 1u) {
+                    const uint64_t r = key[j] & rmask;
+                    if (ENT64) ((uint64_t*)buf)[pos[j]] = r;
+                    else ((uint32_t*)buf)[pos[j]] = (uint32_t)r;
                 }
             }
         }
     }
-    __syncthreads();
     if (!SCATTER) {
-        for (int p = tid; p < P; p += SPK_TILE_THREADS) chunk_hist[chunk * P + p] = s_bins[p];
         n_valid = spk_warp_sum_u64(n_valid);
         if ((tid & 31) == 0 && n_valid) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_valid);
     }
 }
 
-// Column scans of chunk_hist [n_chunks x P]: block = 32 partitions x 32 segments of chunks.
-// chunk_hist[c][p] becomes the exclusive prefix over chunks; psize[p] the column total.
-__global__ void __launch_bounds__(1024)
-k_part_colscan(uint32_t* __restrict__ chunk_hist, uint64_t n_chunks, int P, uint32_t* __restrict__ psize) {
-    __shared__ uint32_t s_seg[32][33];
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
-    const int p = blockIdx.x * 32 + lane;
-    const uint64_t per = (n_chunks + 31) / 32;
-    const uint64_t c0 = min((uint64_t)seg * per, n_chunks), c1 = min(c0 + per, n_chunks);
-    uint32_t sum = 0;
-    if (p < P)
-        for (uint64_t c = c0; c < c1; c++) sum += chunk_hist[c * P + p];
-    s_seg[seg][lane] = sum;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int s2 = 0; s2 < seg; s2++) base += s_seg[s2][lane];
-    if (p < P) {
-        uint32_t run = base;
-        for (uint64_t c = c0; c < c1; c++) {
-            const uint32_t v = chunk_hist[c * P + p];
-            chunk_hist[c * P + p] = run;
-            run += v;
-        }
-        if (seg == 31) psize[p] = run;
-    }
-}
-
-// exclusive scan of the P partition sizes (P <= 1024) -> pstart[0..P]
-__global__ void __launch_bounds__(1024) k_part_starts(const uint32_t* __restrict__ psize, int P,
-                                                       uint32_t* __restrict__ pstart) {
-    __shared__ uint32_t s_warp[32];
-    const uint32_t v = ((int)threadIdx.x < P) ? psize[threadIdx.x] : 0u;
+// ---- exclusive scan of the P partition sizes (three passes over 1024-element segments) --------------------
+__device__ __forceinline__ uint32_t block_scan_1024(uint32_t v, uint32_t* s_warp, uint32_t* total) {
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -208,13 +164,58 @@ __global__ void __launch_bounds__(1024) k_part_starts(const uint32_t* __restrict
     }
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
     __syncthreads();
-    uint32_t prefix = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix += s_warp[w];
-    if ((int)threadIdx.x < P) pstart[threadIdx.x] = prefix + incl - v;
-    if ((int)threadIdx.x == P - 1) pstart[P] = prefix + incl;
+    uint32_t prefix = 0, tot = 0;
+    for (int w = 0; w < 32; w++) {
+        if (w < (int)(threadIdx.x >> 5)) prefix += s_warp[w];
+        tot += s_warp[w];
+    }
+    __syncthreads();
+    *total = tot;
+    return prefix + incl - v;
 }
 
-// ---- phase 2 ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_seg_totals(const uint32_t* __restrict__ v, uint64_t n,
+                                                           uint32_t* __restrict__ seg) {
+    __shared__ uint32_t s_warp[32];
+    const uint64_t i = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+    uint32_t tot;
+    block_scan_1024(i < n ? v[i] : 0u, s_warp, &tot);
+    if (threadIdx.x == 0) seg[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_segs(uint32_t* seg, uint64_t nseg) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nseg; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        uint32_t tot;
+        const uint32_t excl = block_scan_1024(i < nseg ? seg[i] : 0u, s_warp, &tot);
+        if (i < nseg) seg[i] = s_carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t* __restrict__ v, uint64_t n,
+                                                      const uint32_t* __restrict__ seg,
+                                                      uint32_t* __restrict__ pstart,
+                                                      uint32_t* __restrict__ cursor) {
+    __shared__ uint32_t s_warp[32];
+    const uint64_t i = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t x = i < n ? v[i] : 0u;
+    uint32_t tot;
+    const uint32_t e = seg[blockIdx.x] + block_scan_1024(x, s_warp, &tot);
+    if (i < n) {
+        pstart[i] = e;
+        cursor[i] = e;
+        if (i == n - 1) pstart[n] = e + x;
+    }
+}
+
+// ---- phase 2: one partition per CTA iteration, table in shared memory ---------------------------------------
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
     h *= 0x85ebca6bu;
@@ -224,181 +225,143 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     return h;
 }
 
-template <bool ENT64>
-__device__ __forceinline__ uint64_t slot_of_r(uint64_t r, uint64_t T) {
-    if (ENT64) return __umul64hi(spk_hash64(r), T);
-    return (uint64_t)__umulhi(fmix32((uint32_t)r), (uint32_t)T);
-}
+struct CountOut {
+    uint64_t* keys;
+    uint32_t* counts;
+    uint64_t cap;
+    uint64_t* cursor;
+    uint64_t* stats;
+    uint64_t* histo;
+    uint32_t histo_len;
+    uint32_t lower;
+};
 
-// ENT32 slot: (r << 32) | count, empty = 0.  ENT64: keys[T] (empty = ~0) then counts[T].
+// ENT32: slot u64 = (r << 32) | count, empty = 0 (count >= 1 once occupied).
+// ENT64: key u64 (empty = ~0) and count u32 in separate arrays.
 template <bool ENT64>
-__global__ void __launch_bounds__(256)
-k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, int g0, int G, int P,
-             int ctas_per_part, uint8_t* __restrict__ tables, uint64_t T, uint64_t* __restrict__ stats) {
-    const int gslot = blockIdx.x / ctas_per_part;
-    const int p = g0 + gslot;
-    if (gslot >= G || p >= P) return;
-    const int cta = blockIdx.x - gslot * ctas_per_part;
-    const uint64_t beg = pstart[p], end = pstart[p + 1];
-    uint64_t* tkeys = (uint64_t*)(tables + (size_t)gslot * T * (ENT64 ? 12 : 8));
-    uint32_t* tcnt = ENT64 ? (uint32_t*)(tkeys + T) : nullptr;
-    const uint64_t stride = (uint64_t)ctas_per_part * 256;
-    uint64_t n_fail = 0;
-    for (uint64_t base = beg + (uint64_t)cta * 256 + threadIdx.x; base < end; base += stride * PC_BATCH) {
-        uint64_t r[PC_BATCH], slot[PC_BATCH], cur[PC_BATCH];
-        bool ok[PC_BATCH];
-#pragma unroll
-        for (int j = 0; j < PC_BATCH; j++) {
-            const uint64_t i = base + (uint64_t)j * stride;
-            ok[j] = i < end;
-            r[j] = 0;
-            if (ok[j]) r[j] = ENT64 ? __ldcs((const uint64_t*)buf + i) : (uint64_t)__ldcs((const uint32_t*)buf + i);
+__global__ void __launch_bounds__(PC_THREADS, 3)
+k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
+             CountOut o) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint64_t* s_key = (uint64_t*)s_raw;
+    uint32_t* s_cnt = (uint32_t*)(s_raw + (size_t)PC_SLOTS * 8);  // ENT64 only
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint64_t s_red[4][PC_THREADS / 32];
+    const int tid = threadIdx.x;
+    uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0, n_fail = 0;
+    uint32_t h1 = 0, h2 = 0;
+    if (o.histo) s_hist[tid] = 0;
+    const uint64_t EMPTY = ENT64 ? SPK_EMPTY_KEY : 0ull;
+
+    for (uint64_t p = blockIdx.x; p < P; p += gridDim.x) {
+        const uint32_t beg = pstart[p], end = pstart[p + 1];
+        const uint32_t n_p = end - beg;
+        if (n_p == 0) continue;
+        // table size: power of two >= 2 * entries, at most PC_SLOTS
+        uint32_t tsz = 64;
+        while (tsz < PC_SLOTS && tsz < 2 * n_p) tsz <<= 1;
+        const uint32_t tmask = tsz - 1;
+        __syncthreads();  // previous partition's scan is finished
+        for (uint32_t i = tid; i < tsz; i += PC_THREADS) {
+            s_key[i] = EMPTY;
+            if (ENT64) s_cnt[i] = 0;
         }
-#pragma unroll
-        for (int j = 0; j < PC_BATCH; j++) {
-            slot[j] = slot_of_r<ENT64>(r[j], T);
-            cur[j] = ok[j] ? __ldcg(tkeys + slot[j]) : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < PC_BATCH; j++) {
-            if (!ok[j]) continue;
-            uint64_t s = slot[j], c = cur[j];
+        __syncthreads();
+        // ---- insert ----
+        for (uint32_t i = beg + tid; i < end; i += PC_THREADS) {
+            const uint64_t r = ENT64 ? __ldcs((const uint64_t*)buf + i) : (uint64_t)__ldcs((const uint32_t*)buf + i);
+            uint32_t s = (ENT64 ? (uint32_t)spk_hash64(r) : fmix32((uint32_t)r)) & tmask;
             bool done = false;
-            for (uint64_t probes = 0; probes < T; probes++) {
-                if (!ENT64) {
-                    if (c == 0) {
-                        const uint64_t old = atomicCAS((unsigned long long*)(tkeys + s), 0ull,
-                                                       (unsigned long long)((r[j] << 32) | 1ull));
-                        if (old == 0) { done = true; break; }
-                        c = old;
-                    }
-                    if ((c >> 32) == r[j]) {
-                        atomicAdd((unsigned long long*)(tkeys + s), 1ull);
+            for (uint32_t probes = 0; probes < tsz; probes++) {
+                uint64_t c = s_key[s];
+                if (c == EMPTY) {
+                    const uint64_t fresh = ENT64 ? r : ((r << 32) | 1ull);
+                    const uint64_t old = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)EMPTY,
+                                                   (unsigned long long)fresh);
+                    if (old == EMPTY) {
+                        if (ENT64) atomicAdd(&s_cnt[s], 1u);
                         done = true;
                         break;
                     }
-                } else {
-                    if (c == SPK_EMPTY_KEY) {
-                        const uint64_t old = atomicCAS((unsigned long long*)(tkeys + s),
-                                                       (unsigned long long)SPK_EMPTY_KEY, (unsigned long long)r[j]);
-                        c = (old == SPK_EMPTY_KEY) ? r[j] : old;
-                    }
-                    if (c == r[j]) {
-                        atomicAdd(tcnt + s, 1u);
-                        done = true;
-                        break;
-                    }
+                    c = old;
                 }
-                s++;
-                if (s == T) s = 0;
-                c = __ldcg(tkeys + s);
+                if (ENT64 ? (c == r) : ((c >> 32) == r)) {
+                    if (ENT64) atomicAdd(&s_cnt[s], 1u);
+                    else atomicAdd((unsigned int*)&s_key[s], 1u);   // low word = count (little endian)
+                    done = true;
+                    break;
+                }
+                s = (s + 1) & tmask;
             }
             if (!done) n_fail++;
         }
-    }
-    if (n_fail) atomicAdd((unsigned long long*)&stats[1], (unsigned long long)n_fail);
-}
-
-template <bool ENT64>
-__global__ void __launch_bounds__(256)
-k_part_extract(int g0, int G, int P, int ctas_per_part, uint8_t* __restrict__ tables, uint64_t T, Mixer mx,
-               uint32_t lower, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts, uint64_t cap,
-               uint64_t* __restrict__ cursor, uint64_t* __restrict__ stats, uint64_t* __restrict__ histo,
-               uint32_t histo_len) {
-    __shared__ uint64_t s_red[4][8];
-    __shared__ uint32_t s_hist[256];
-    const int gslot = blockIdx.x / ctas_per_part;
-    const int p = g0 + gslot;
-    const bool active = gslot < G && p < P;
-    const int cta = blockIdx.x - gslot * ctas_per_part;
-    uint64_t* tkeys = (uint64_t*)(tables + (size_t)gslot * T * (ENT64 ? 12 : 8));
-    uint32_t* tcnt = ENT64 ? (uint32_t*)(tkeys + T) : nullptr;
-    uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0;
-    uint32_t h1 = 0, h2 = 0;
-    if (histo) {
-        s_hist[threadIdx.x] = 0;
         __syncthreads();
-    }
-    const uint64_t per = (T + ctas_per_part - 1) / ctas_per_part;
-    const uint64_t beg = min((uint64_t)cta * per, T), end = active ? min(beg + per, T) : beg;
-    for (uint64_t base = beg; base < end; base += 256) {
-        const uint64_t i = base + threadIdx.x;
-        uint64_t r = 0, cnt = 0;
-        bool occ = false;
-        if (i < end) {
-            if (!ENT64) {
-                const uint64_t v = tkeys[i];
-                if (v != 0) {
-                    occ = true;
-                    r = v >> 32;
-                    cnt = v & 0xffffffffull;
-                    tkeys[i] = 0;
-                }
-            } else {
-                const uint64_t v = tkeys[i];
-                if (v != SPK_EMPTY_KEY) {
-                    occ = true;
-                    r = v;
-                    cnt = tcnt[i];
-                    tkeys[i] = SPK_EMPTY_KEY;
-                    tcnt[i] = 0;
+        // ---- scan: stats, histogram, dump ----
+        for (uint32_t base = 0; base < tsz; base += PC_THREADS) {
+            const uint32_t i = base + tid;
+            const uint64_t v = (i < tsz) ? s_key[i] : EMPTY;   // tables smaller than the CTA exist
+            const bool occ = v != EMPTY;
+            uint64_t r = 0, cnt = 0;
+            if (occ) {
+                r = ENT64 ? v : (v >> 32);
+                cnt = ENT64 ? (uint64_t)s_cnt[i] : (v & 0xffffffffull);
+                distinct++;
+                sumall += cnt;
+                if (o.histo) {
+                    const uint64_t b = cnt < (uint64_t)(o.histo_len - 1) ? cnt : (uint64_t)(o.histo_len - 1);
+                    if (b == 1) h1++;
+                    else if (b == 2) h2++;
+                    else if (b < 256) atomicAdd(&s_hist[b], 1u);
+                    else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
                 }
             }
-        }
-        const bool keep = occ && cnt >= lower;
-        if (occ) {
-            distinct++;
-            sumall += cnt;
+            const bool keep = occ && cnt >= o.lower;
             if (keep) {
                 nge++;
                 sumge += cnt;
             }
-            if (histo) {
-                const uint64_t b = cnt < (uint64_t)(histo_len - 1) ? cnt : (uint64_t)(histo_len - 1);
-                if (b == 1) h1++;
-                else if (b == 2) h2++;
-                else if (b < 256) atomicAdd(&s_hist[b], 1u);
-                else atomicAdd((unsigned long long*)&histo[b], 1ull);
-            }
-        }
-        // warp-aggregated append
-        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-        if (ballot) {
-            const int lane = threadIdx.x & 31;
-            uint64_t wbase = 0;
-            if (lane == 0) wbase = atomicAdd((unsigned long long*)cursor, (unsigned long long)__popc(ballot));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (keep) {
-                const uint64_t o = wbase + __popc(ballot & ((1u << lane) - 1));
-                if (o < cap) {
-                    out_keys[o] = mx.inv(((uint64_t)p << mx.rbits) | r);
-                    out_counts[o] = (uint32_t)cnt;
+            const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+            if (ballot) {
+                const int lane = tid & 31;
+                uint64_t wbase = 0;
+                if (lane == 0) wbase = atomicAdd((unsigned long long*)o.cursor, (unsigned long long)__popc(ballot));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (keep) {
+                    const uint64_t at = wbase + __popc(ballot & ((1u << lane) - 1));
+                    if (at < o.cap) {
+                        o.keys[at] = mx.inv((p << mx.rbits) | r);
+                        o.counts[at] = (uint32_t)cnt;
+                    }
                 }
             }
         }
     }
-    if (histo) {
+    // ---- per-CTA totals ----
+    __syncthreads();
+    if (o.histo) {
         h1 = spk_warp_sum_u32(h1);
         h2 = spk_warp_sum_u32(h2);
-        if ((threadIdx.x & 31) == 0) {
+        if ((tid & 31) == 0) {
             if (h1) atomicAdd(&s_hist[1], h1);
             if (h2) atomicAdd(&s_hist[2], h2);
         }
         __syncthreads();
-        if (threadIdx.x < histo_len && s_hist[threadIdx.x])
-            atomicAdd((unsigned long long*)&histo[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+        if ((uint32_t)tid < o.histo_len && s_hist[tid])
+            atomicAdd((unsigned long long*)&o.histo[tid], (unsigned long long)s_hist[tid]);
     }
     uint64_t v[4] = {distinct, nge, sumge, sumall};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         v[q] = spk_warp_sum_u64(v[q]);
-        if ((threadIdx.x & 31) == 0) s_red[q][threadIdx.x >> 5] = v[q];
+        if ((tid & 31) == 0) s_red[q][tid >> 5] = v[q];
     }
+    n_fail = spk_warp_sum_u64(n_fail);
+    if ((tid & 31) == 0 && n_fail) atomicAdd((unsigned long long*)&o.stats[1], (unsigned long long)n_fail);
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (tid < 4) {
         uint64_t s = 0;
-        for (int w = 0; w < 8; w++) s += s_red[threadIdx.x][w];
-        if (s) atomicAdd((unsigned long long*)&stats[4 + threadIdx.x], (unsigned long long)s);
+        for (int w = 0; w < PC_THREADS / 32; w++) s += s_red[tid][w];
+        if (s) atomicAdd((unsigned long long*)&o.stats[4 + tid], (unsigned long long)s);
     }
 }
 
@@ -407,43 +370,39 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
              uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo, uint32_t histo_len,
              cudaStream_t st) {
     void* buf = ws + pl.off_buf;
-    uint32_t* hist = (uint32_t*)(ws + pl.off_hist);
     uint32_t* psize = (uint32_t*)(ws + pl.off_psize);
     uint32_t* pstart = (uint32_t*)(ws + pl.off_pstart);
-    uint8_t* tables = (uint8_t*)(ws + pl.off_tables);
-    uint64_t* cursor = (uint64_t*)(ws + pl.off_cursor);
-    SPK_CUDA(cudaMemsetAsync(cursor, 0, 256, st));
-    // tables: ENT32 empty = 0; ENT64 keys empty = 0xFF.., counts 0 (k_part_extract restores this state)
-    if (!ENT64) {
-        SPK_CUDA(cudaMemsetAsync(tables, 0, (size_t)pl.G * pl.T * 8, st));
-    } else {
-        for (int g = 0; g < pl.G; g++) {
-            SPK_CUDA(cudaMemsetAsync(tables + (size_t)g * pl.T * 12, 0xFF, pl.T * 8, st));
-            SPK_CUDA(cudaMemsetAsync(tables + (size_t)g * pl.T * 12 + pl.T * 8, 0, pl.T * 4, st));
-        }
-    }
-    if (pl.n_chunks == 0) return SPK_OK;
-    k_part_pass<false, ENT64><<<(unsigned)pl.n_chunks, SPK_TILE_THREADS, 0, st>>>(
-        pk, vl, pl.n_tiles, pl.k, pl.mx, pl.P, hist, nullptr, nullptr, d_stats);
-    SPK_LAUNCH_CHECK();
-    k_part_colscan<<<(pl.P + 31) / 32, 1024, 0, st>>>(hist, pl.n_chunks, pl.P, psize);
-    SPK_LAUNCH_CHECK();
-    k_part_starts<<<1, 1024, 0, st>>>(psize, pl.P, pstart);
-    SPK_LAUNCH_CHECK();
-    k_part_pass<true, ENT64><<<(unsigned)pl.n_chunks, SPK_TILE_THREADS, 0, st>>>(
-        pk, vl, pl.n_tiles, pl.k, pl.mx, pl.P, hist, pstart, buf, d_stats);
-    SPK_LAUNCH_CHECK();
+    uint32_t* cursor = (uint32_t*)(ws + pl.off_cursor);
+    uint32_t* segs = (uint32_t*)(ws + pl.off_segs);
+    uint64_t* out_cursor = (uint64_t*)(ws + pl.off_out);
+    SPK_CUDA(cudaMemsetAsync(psize, 0, (pl.P + 1) * 4, st));
+    SPK_CUDA(cudaMemsetAsync(out_cursor, 0, 256, st));
+    if (pl.n_tiles == 0) return SPK_OK;
     const int sms = spk_num_sms();
-    int cpp = (sms * 6 + pl.G - 1) / pl.G;      // CTAs per partition in the count kernel
-    if (cpp < 1) cpp = 1;
-    int cpe = (sms * 4 + pl.G - 1) / pl.G;
-    for (int g0 = 0; g0 < pl.P; g0 += pl.G) {
-        k_part_count<ENT64><<<cpp * pl.G, 256, 0, st>>>(buf, pstart, g0, pl.G, pl.P, cpp, tables, pl.T, d_stats);
-        SPK_LAUNCH_CHECK();
-        k_part_extract<ENT64><<<cpe * pl.G, 256, 0, st>>>(g0, pl.G, pl.P, cpe, tables, pl.T, pl.mx, lower, d_keys,
-                                                          d_counts, cap, cursor, d_stats, d_histo, histo_len);
-        SPK_LAUNCH_CHECK();
+    const unsigned pass_grid = (unsigned)min((uint64_t)sms * 4, pl.n_tiles);
+    k_part_pass<false, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
+                                                                      nullptr, nullptr, d_stats);
+    SPK_LAUNCH_CHECK();
+    const uint64_t nseg = (pl.P + 1023) / 1024;
+    k_scan_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs);
+    SPK_LAUNCH_CHECK();
+    k_scan_segs<<<1, 1024, 0, st>>>(segs, nseg);
+    SPK_LAUNCH_CHECK();
+    k_scan_apply<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs, pstart, cursor);
+    SPK_LAUNCH_CHECK();
+    k_part_pass<true, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
+                                                                     cursor, buf, d_stats);
+    SPK_LAUNCH_CHECK();
+    const size_t smem = (size_t)PC_SLOTS * (ENT64 ? 12 : 8);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[ENT64 ? 1 : 0]) {
+        SPK_CUDA(cudaFuncSetAttribute(k_part_count<ENT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ENT64 ? 1 : 0] = true;
     }
+    CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower};
+    const unsigned cgrid = (unsigned)min((uint64_t)sms * (ENT64 ? 2 : 3), pl.P);
+    k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
+    SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
 
