@@ -17,11 +17,16 @@ constexpr int MP_MAX_S = 32;
 __global__ void __launch_bounds__(256)
 k_sig_build(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ vals, uint64_t n,
             uint64_t* __restrict__ skeys, uint8_t* __restrict__ svals, uint64_t sslots,
-            uint64_t* __restrict__ fail) {
+            uint32_t* __restrict__ filter, uint64_t fmask, uint64_t* __restrict__ fail) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
-        uint64_t slot = spk_slot_of(spk_hash64(key), sslots);
+        const uint64_t h = spk_hash64(key);
+        if (filter) {
+            const uint64_t fb = h & fmask;
+            atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+        }
+        uint64_t slot = spk_slot_of(h, sslots);
         bool done = false;
         for (uint64_t p = 0; p < sslots; p++) {
             const uint64_t old = atomicCAS((unsigned long long*)(skeys + slot),
@@ -42,6 +47,8 @@ struct MapArgs {
     const uint64_t* skeys;
     const uint8_t* svals;
     uint64_t sslots;
+    const uint32_t* filter;   // one-hash Bloom bitmap over the keys (nullptr: none)
+    uint64_t fmask;
     int S;
     uint64_t bin_size;
     uint64_t chunk_size;
@@ -98,38 +105,49 @@ k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid
         }
         const uint64_t line0 = s_line0;
 
+        // stage 1: one-bit membership filter for all 16 positions (a miss costs a single 4-byte load;
+        // ~97 % of the positions of a real chromosome are misses)
+        uint64_t hsh[SPK_KMERS_PER_THREAD];
+        uint32_t cand = okmask;
+        if (a.filter) {
+            uint32_t fw[SPK_KMERS_PER_THREAD];
 #pragma unroll
-        for (int b0 = 0; b0 < SPK_KMERS_PER_THREAD; b0 += MP_BATCH) {
-            uint64_t slot[MP_BATCH], cur[MP_BATCH];
-#pragma unroll
-            for (int j = 0; j < MP_BATCH; j++) {
-                slot[j] = spk_slot_of(spk_hash64(key[b0 + j]), a.sslots);
-                cur[j] = ((okmask >> (b0 + j)) & 1u) ? __ldg(a.skeys + slot[j]) : SPK_EMPTY_KEY;
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                hsh[j] = spk_hash64(key[j]);
+                fw[j] = ((okmask >> j) & 1u) ? __ldg(a.filter + ((hsh[j] & a.fmask) >> 5)) : 0u;
             }
 #pragma unroll
-            for (int j = 0; j < MP_BATCH; j++) {
-                if ((okmask >> (b0 + j)) & 1u) {
-                    uint64_t sl = slot[j], c = cur[j];
-                    const uint64_t kk = key[b0 + j];
-                    while (c != SPK_EMPTY_KEY && c != kk) {
-                        sl++;
-                        if (sl == a.sslots) sl = 0;
-                        c = __ldg(a.skeys + sl);
-                    }
-                    if (c == kk) {
-                        const uint32_t sg = a.svals[sl];
-                        const uint64_t line = bin + chk;
-                        const uint64_t rel = line - line0;
-                        if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
-                        else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
-                        if (a.hit_flags) a.hit_flags[sl] = 1;
-                        n_hit++;
-                    }
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+                if (!((fw[j] >> (hsh[j] & 31)) & 1u)) cand &= ~(1u << j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) hsh[j] = spk_hash64(key[j]);
+        }
+        // stage 2: table probes for the candidates
+#pragma unroll
+        for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+            if ((cand >> j) & 1u) {
+                uint64_t sl = spk_slot_of(hsh[j], a.sslots);
+                uint64_t c = __ldg(a.skeys + sl);
+                const uint64_t kk = key[j];
+                while (c != SPK_EMPTY_KEY && c != kk) {
+                    sl++;
+                    if (sl == a.sslots) sl = 0;
+                    c = __ldg(a.skeys + sl);
                 }
-                // advance the (bin, chunk) cursors to the next position
-                if (++brem == a.bin_size) { brem = 0; bin++; }
-                if (a.chunk_size && ++crem == a.chunk_size) { crem = 0; chk++; }
+                if (c == kk) {
+                    const uint32_t sg = a.svals[sl];
+                    const uint64_t line = bin + chk;
+                    const uint64_t rel = line - line0;
+                    if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
+                    else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
+                    if (a.hit_flags) a.hit_flags[sl] = 1;
+                    n_hit++;
+                }
             }
+            // advance the (bin, chunk) cursors to the next position
+            if (++brem == a.bin_size) { brem = 0; bin++; }
+            if (a.chunk_size && ++crem == a.chunk_size) { crem = 0; chk++; }
         }
         __syncthreads();
         for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) {
@@ -212,15 +230,18 @@ extern "C" int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d
 
 extern "C" int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n,
                                    uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,
-                                   uint64_t* d_fail, void* stream) {
+                                   uint32_t* d_filter, uint64_t filter_bits, uint64_t* d_fail,
+                                   void* stream) {
     SPK_CHECK_ARG(d_skeys && d_svals && d_fail, "null pointer");
     SPK_CHECK_ARG(sslots >= 2, "sslots too small");
+    SPK_CHECK_ARG(!d_filter || (filter_bits >= 32 && (filter_bits & (filter_bits - 1)) == 0),
+                  "filter_bits must be a power of two >= 32");
     if (n == 0) return SPK_OK;
     SPK_CHECK_ARG(d_keys && d_vals, "null keys/vals");
     const uint64_t blocks = (n + 255) / 256;
     const unsigned grid = (unsigned)min(blocks, (uint64_t)spk_num_sms() * 16);
     k_sig_build<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_vals, n, d_skeys, d_svals, sslots,
-                                                        d_fail);
+                                                        d_filter, d_filter ? filter_bits - 1 : 0, d_fail);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -235,8 +256,11 @@ extern "C" uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size
 
 extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
                             const uint64_t* d_skeys, const uint8_t* d_svals, uint64_t sslots, int S,
-                            uint64_t bin_size, uint64_t chunk_size, uint32_t* d_line_counts,
-                            uint64_t n_lines, uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
+                            const uint32_t* d_filter, uint64_t filter_bits, uint64_t bin_size,
+                            uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
+                            uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
+    SPK_CHECK_ARG(!d_filter || (filter_bits >= 32 && (filter_bits & (filter_bits - 1)) == 0),
+                  "filter_bits must be a power of two >= 32");
     SPK_CHECK_ARG(d_packed && d_valid && d_skeys && d_svals && d_line_counts, "null pointer");
     SPK_CHECK_ARG(k >= 1 && k <= 32, "k must be in [1, 32]");
     SPK_CHECK_ARG(S >= 1 && S <= MP_MAX_S, "S must be in [1, 32]");
@@ -246,8 +270,8 @@ extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, u
     if (n_bases < (uint64_t)k) return SPK_OK;
     const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
-    MapArgs a{d_skeys, d_svals, sslots, S, bin_size, chunk_size, d_line_counts, n_lines, d_hit_flags,
-              d_nhits};
+    MapArgs a{d_skeys, d_svals, sslots, d_filter, d_filter ? filter_bits - 1 : 0, S, bin_size, chunk_size,
+              d_line_counts, n_lines, d_hit_flags, d_nhits};
     k_map_bins<<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a);
     SPK_LAUNCH_CHECK();

@@ -431,9 +431,13 @@ class SigTable:
         self.slots = max(2 * n + 64, 1024)
         self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
         self.svals = _zeros(self.slots, torch.uint8)
+        self.filter_bits = 1024
+        while self.filter_bits < 16 * n:
+            self.filter_bits *= 2
+        self.filter = _zeros(self.filter_bits // 32, torch.int32)
         fail = _zeros(1, torch.int64)
         call("spk_sig_table_build", _p(keys), _p(vals), n, _p(self.skeys), _p(self.svals), self.slots,
-             _p(fail), _stream())
+             _p(self.filter), self.filter_bits, _p(fail), _stream())
         if int(fail.item()):
             raise OverflowError("specific k-mer table full")
         self.hit_flags = _zeros(self.slots, torch.uint8)
@@ -451,8 +455,8 @@ def map_bins(seq, sig, S, bin_size, chunk_size):
     nhits = _zeros(1, torch.int64)
     if seq.n_bases:
         call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
-             sig.slots, S, int(bin_size), int(chunk_size), _p(counts), max(n_lines, 1), _p(sig.hit_flags),
-             _p(nhits), _stream())
+             sig.slots, S, _p(sig.filter), sig.filter_bits, int(bin_size), int(chunk_size), _p(counts),
+             max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())
     return counts[:n_lines], int(nhits.item())
 
 

@@ -79,12 +79,28 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     table = engine.CountTable(max_bytes, k, lower_count)
     seqs, dumps = {}, {}
     n_kmers = 0
-    for i in mine:
+    # host inputs: the H2D copy of chromosome j+1 runs on a side stream while chromosome j is counted
+    copy_stream = torch.cuda.Stream() if host_inputs else None
+    main_stream = torch.cuda.current_stream()
+
+    def start_copy(i):
+        buf, nbytes = chrom_inputs[i]
+        d = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
+        copy_stream.wait_stream(main_stream)       # the block may have been used by earlier main-stream work
+        with torch.cuda.stream(copy_stream):
+            d[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return d, ev
+
+    pending = start_copy(mine[0]) if (host_inputs and mine) else None
+    for pos, i in enumerate(mine):
         buf, nbytes = chrom_inputs[i]
         if host_inputs:
-            e = t.start("h2d")
-            d = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
-            d[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+            d, ev = pending
+            pending = start_copy(mine[pos + 1]) if pos + 1 < len(mine) else None
+            e = t.start("h2d_wait")
+            main_stream.wait_event(ev)
             t.stop(e)
             h2d_bytes += nbytes
         else:
