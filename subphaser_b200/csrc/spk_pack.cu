@@ -3,11 +3,11 @@
 // Replaces the text ingest the reference delegates to `cat f | jellyfish count ... /dev/stdin`
 // (Jellyfish.py:697) and to SeqIO.parse + upper() (Seqs.py:121-139).
 //
-// Four streaming passes over 4-KiB byte tiles (256 threads x 16 B, one coalesced uint4 each):
+// Three streaming passes over 4-KiB byte tiles (256 threads x 16 B, one coalesced uint4 each):
 //   A  last '\n' of every tile                      -> exclusive max-scan  (which line does a tile start in)
 //   B  kept bases / valid bases / headers per tile  -> exclusive sum-scan  (where does a tile write)
-//   C  emit one code byte per kept base (0..3 = ACGT, 4 = invalid) at its final index
-//   D  codes -> 2-bit words + validity bits (zero padded to the tile-aligned extent)
+//   C  classify again and OR the 2-bit codes / validity bits of each thread's <= 16 kept bases straight
+//      into the zero-initialised output words (<= 4 RED.OR per thread; no byte stores, no code array)
 // A byte is in a header iff the first byte of its line is '>'.
 #include "spk_common.cuh"
 
@@ -21,7 +21,6 @@ struct PackWs {
     int64_t* tile_last_nl;   // [ntiles]  global position of last '\n' in tile (or -1); scanned in place
     uint64_t* tile_off;      // [ntiles+1] kept bases before tile (after scan)
     uint32_t* tile_kept;     // [ntiles]
-    uint8_t* codes;          // [nbytes]
     uint64_t* totals;        // [4] scratch: valid count, records
 };
 
@@ -41,15 +40,13 @@ __host__ PackWs carve_ws(void* ws, size_t nbytes, size_t* total) {
     off += align_up(ntiles * 4, 256);
     w.totals = (uint64_t*)(p + off);
     off += 256;
-    w.codes = (uint8_t*)(p + off);
-    off += align_up(nbytes + 64, 256);
     if (total) *total = off;
     return w;
 }
 
 __device__ __forceinline__ uint4 load_tile_bytes(const uint8_t* __restrict__ in, size_t nbytes,
                                                  size_t pos) {
-    // 16 bytes starting at pos (pos is 16-aligned relative to the buffer start, which is >=16-aligned)
+    // 16 bytes starting at pos (16-aligned); bytes past the end read as '\n'
     uint4 v;
     if (pos + 16 <= nbytes) {
         v = *reinterpret_cast<const uint4*>(in + pos);
@@ -62,9 +59,25 @@ __device__ __forceinline__ uint4 load_tile_bytes(const uint8_t* __restrict__ in,
     return v;
 }
 
-__device__ __forceinline__ uint8_t byte_of(const uint4& v, int i) {
-    const uint32_t w = (i < 4) ? v.x : (i < 8) ? v.y : (i < 12) ? v.z : v.w;
-    return (uint8_t)(w >> (8 * (i & 3)));
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int w) {
+    return w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+}
+
+// index (0..15) of the last '\n' among the 16 bytes, or -1
+__device__ __forceinline__ int last_newline16(const uint4& v) {
+    int last = -1;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t x = word_of(v, w) ^ 0x0a0a0a0au;                       // zero byte where '\n'
+        const uint32_t z = (x - 0x01010101u) & ~x & 0x80808080u;              // exact for the first zero byte
+        if (z) {
+            // scan the four bytes explicitly (borrow propagation makes higher flags unreliable)
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (((word_of(v, w) >> (8 * b)) & 0xffu) == 0x0au) last = w * 4 + b;
+        }
+    }
+    return last;
 }
 
 // ---- pass A -------------------------------------------------------------------------------------
@@ -77,9 +90,14 @@ __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t*
         int last = -1;
         if (pos < nbytes) {
             const uint4 v = load_tile_bytes(in, nbytes, pos);
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (byte_of(v, i) == '\n' && pos + i < nbytes) last = threadIdx.x * 16 + i;
+            const int l = last_newline16(v);
+            if (l >= 0) {
+                // bytes past the end were padded with '\n': clamp to real bytes
+                int ll = l;
+                while (ll >= 0 && pos + ll >= nbytes) ll--;
+                while (ll >= 0 && ((word_of(v, ll >> 2) >> (8 * (ll & 3))) & 0xffu) != 0x0au) ll--;
+                if (ll >= 0) last = threadIdx.x * 16 + ll;
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
@@ -149,60 +167,57 @@ __global__ void __launch_bounds__(1024) k_scan_sum_excl(const uint32_t* in, uint
     if (threadIdx.x == 0) out[n] = s_carry;
 }
 
-// Classify the 16 bytes of one thread.  codes[i]: 0..3 base, 4 invalid-but-kept, 255 dropped.
-// `ls` = global position of the last '\n' before this thread's first byte (-1: none).
-__device__ __forceinline__ void classify16(const uint8_t* __restrict__ in, size_t nbytes, size_t pos,
-                                           const uint4& v, int64_t ls, uint8_t* codes, int& kept,
-                                           int& valid, int& headers) {
+// Classify the 16 bytes of one thread.  Kept bases are appended, in order, to `bits` (2 bits each, first
+// kept base lowest) and `vbits` (1 bit each).  `bol`: the first byte is at the beginning of a line;
+// `hdr`: the line the first byte belongs to is a header (only meaningful when !bol).
+__device__ __forceinline__ void classify16(const uint4& v, size_t pos, size_t nbytes, bool bol, bool hdr,
+                                           uint32_t& bits, uint32_t& vbits, int& kept, int& valid,
+                                           int& headers) {
+    bits = vbits = 0;
     kept = valid = headers = 0;
-    bool hdr = false;
-    {
-        const size_t line_start = (size_t)(ls + 1);
-        hdr = (line_start < pos) ? (in[line_start] == '>') : false;  // line_start == pos handled below
-    }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const size_t p = pos + i;
-        const uint8_t c = byte_of(v, i);
-        uint8_t code = 255;
-        if (p < nbytes) {
-            const bool at_line_start = ((int64_t)p == ls + 1);
-            if (c == '\n') {
-                ls = (int64_t)p;
-                hdr = false;
-            } else if (at_line_start && c == '>') {
-                hdr = true;
-                headers++;
-                if (p != 0) code = 4;  // record separator
-            } else if (!hdr && c != '\r') {
-                switch (c) {
-                    case 'A': case 'a': code = 0; break;
-                    case 'C': case 'c': code = 1; break;
-                    case 'G': case 'g': code = 2; break;
-                    case 'T': case 't': code = 3; break;
-                    default: code = 4;
-                }
-            }
+        const uint32_t c = (word_of(v, i >> 2) >> (8 * (i & 3))) & 0xffu;
+        if (pos + i >= nbytes) break;
+        if (c == '\n') {
+            bol = true;
+            hdr = false;
+            continue;
         }
-        codes[i] = code;
-        kept += (code != 255);
-        valid += (code < 4);
+        if (bol && c == '>') {
+            hdr = true;
+            headers++;
+            bol = false;
+            if (pos + i != 0) kept++;  // record separator: one invalid base (bits stay 0)
+            continue;
+        }
+        bol = false;
+        if (hdr || c == '\r') continue;
+        const uint32_t u = (c & 0xdfu) - 'A';                                // upper-case letter index
+        const bool ok = u < 26u && ((0x00080045u >> u) & 1u);                // A, C, G, T
+        if (ok) {
+            const uint32_t x = (c >> 1) & 3u;                                // A0 C1 G3 T2
+            bits |= (x ^ (x >> 1)) << (2 * kept);                            // A0 C1 G2 T3
+            vbits |= 1u << kept;
+            valid++;
+        }
+        kept++;
     }
 }
 
-// exclusive max-scan of per-thread last-newline positions inside a CTA, seeded with the tile carry
-__device__ __forceinline__ int64_t block_excl_max(int64_t v, int64_t carry, int64_t* s_warp) {
-    int64_t incl = v;
+// exclusive max-scan of per-thread last-newline offsets (int, tile-local; -1 none) inside a CTA
+__device__ __forceinline__ int block_excl_max(int v, int* s_warp) {
+    int incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
         if ((threadIdx.x & 31) >= o) incl = max(incl, t);
     }
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
     __syncthreads();
-    int64_t prefix = carry;
+    int prefix = -1;
     for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix = max(prefix, s_warp[w]);
-    int64_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if ((threadIdx.x & 31) == 0) excl = -1;
     __syncthreads();
     return max(excl, prefix);
@@ -234,39 +249,73 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
                                                           const int64_t* __restrict__ tile_carry_nl,
                                                           uint32_t* __restrict__ tile_kept,
                                                           const uint64_t* __restrict__ tile_off,
-                                                          uint8_t* __restrict__ codes_out,
+                                                          uint32_t* __restrict__ packed,
+                                                          uint32_t* __restrict__ valid_out,
                                                           uint64_t* __restrict__ totals) {
-    __shared__ int64_t s_w64[PK_THREADS / 32];
+    __shared__ int s_wi[PK_THREADS / 32];
     __shared__ uint32_t s_w32[PK_THREADS / 32];
+    __shared__ int s_carry_hdr;
     uint64_t my_valid = 0, my_hdr = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const size_t pos = tile * PK_TILE + (size_t)threadIdx.x * PK_BYTES_PER_THREAD;
-        uint4 v = make_uint4(0x0a0a0a0a, 0x0a0a0a0a, 0x0a0a0a0a, 0x0a0a0a0a);
-        int64_t my_last = -1;
+        const size_t tbase = tile * PK_TILE;
+        const size_t pos = tbase + (size_t)threadIdx.x * PK_BYTES_PER_THREAD;
+        const int64_t carry = tile_carry_nl[tile];       // last '\n' before this tile (-1: none)
+        if (threadIdx.x == 0) {
+            // is the line that straddles into this tile a header?  (one byte read per tile)
+            const size_t ls = (size_t)(carry + 1);
+            s_carry_hdr = (ls < tbase) ? (in[ls] == '>') : 0;
+        }
+        uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        int my_last = -1;
         if (pos < nbytes) {
             v = load_tile_bytes(in, nbytes, pos);
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (byte_of(v, i) == '\n' && pos + i < nbytes) my_last = (int64_t)(pos + i);
+            const int l = last_newline16(v);
+            if (l >= 0) my_last = threadIdx.x * 16 + l;   // padded '\n' past the end are harmless here
         }
-        const int64_t ls = block_excl_max(my_last, tile_carry_nl[tile], s_w64);
-        uint8_t codes[16];
-        int kept, valid, headers;
-        classify16(in, nbytes, pos, v, ls, codes, kept, valid, headers);
+        const int prev_nl = block_excl_max(my_last, s_wi);   // tile-local offset of the last '\n' before my bytes
+        // state at my first byte
+        bool bol = false, hdr = false;
+        const int my_off = threadIdx.x * 16;
+        if (pos >= nbytes) {
+            // nothing to classify (keeps every global read inside the buffer)
+        } else if (prev_nl >= 0) {
+            bol = (prev_nl + 1 == my_off);
+            // first byte of my line lives in this tile at offset prev_nl+1 (< my_off when !bol)
+            hdr = bol ? false : (in[tbase + prev_nl + 1] == '>');
+        } else {
+            bol = ((int64_t)tbase + my_off == carry + 1);
+            hdr = bol ? false : (((size_t)(carry + 1) >= tbase) ? (in[carry + 1] == '>') : (s_carry_hdr != 0));
+        }
+        uint32_t bits, vbits;
+        int kept, nvalid, headers;
+        classify16(v, pos, nbytes, bol, hdr, bits, vbits, kept, nvalid, headers);
         if (!EMIT) {
             uint32_t tot;
             block_excl_sum((uint32_t)kept, s_w32, &tot);
             if (threadIdx.x == 0) tile_kept[tile] = tot;
-            my_valid += valid;
+            my_valid += nvalid;
             my_hdr += headers;
         } else {
             const uint32_t off = block_excl_sum((uint32_t)kept, s_w32, nullptr);
-            uint8_t* dst = codes_out + tile_off[tile] + off;
-            int j = 0;
-#pragma unroll
-            for (int i = 0; i < 16; i++)
-                if (codes[i] != 255) dst[j++] = codes[i];
+            if (kept) {
+                const uint64_t o = tile_off[tile] + off;
+                // 2-bit codes: up to 32 payload bits starting at bit 2*(o%16) of word o/16
+                const uint64_t w = o >> 4;
+                const int sh = 2 * (int)(o & 15);
+                if (bits) {
+                    if (bits << sh) atomicOr(&packed[w], bits << sh);
+                    if (sh && (bits >> (32 - sh))) atomicOr(&packed[w + 1], bits >> (32 - sh));
+                }
+                // validity: up to 16 bits starting at bit o%32 of word o/32
+                if (vbits) {
+                    const uint64_t vw = o >> 5;
+                    const int vs = (int)(o & 31);
+                    atomicOr(&valid_out[vw], vbits << vs);
+                    if (vs > 16 && (vbits >> (32 - vs))) atomicOr(&valid_out[vw + 1], vbits >> (32 - vs));
+                }
+            }
         }
+        __syncthreads();   // s_carry_hdr is rewritten by the next iteration
     }
     if (!EMIT) {
         my_valid = spk_warp_sum_u64(my_valid);
@@ -284,52 +333,6 @@ __global__ void k_write_info(const uint64_t* tile_off, size_t ntiles, const uint
     info[1] = totals[0];
     info[2] = totals[1];
     info[3] = 0;
-}
-
-// ---- pass D --------------------------------------------------------------------------------------
-// one thread = 32 bases -> 2 packed words + 1 validity word
-__global__ void __launch_bounds__(256) k_pack_codes(const uint8_t* __restrict__ codes,
-                                                     const uint64_t* __restrict__ info,
-                                                     uint32_t* __restrict__ packed,
-                                                     uint32_t* __restrict__ valid, size_t n_groups) {
-    const uint64_t n = info[0];
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_groups;
-         g += (size_t)gridDim.x * blockDim.x) {
-        const uint64_t base = (uint64_t)g * 32;
-        uint32_t w0 = 0, w1 = 0, vm = 0;
-        if (base < n) {
-            uint4 a, b;
-            if (base + 32 <= n) {
-                a = *reinterpret_cast<const uint4*>(codes + base);
-                b = *reinterpret_cast<const uint4*>(codes + base + 16);
-            } else {
-                uint8_t tmp[32];
-#pragma unroll
-                for (int i = 0; i < 32; i++) tmp[i] = (base + i < n) ? codes[base + i] : (uint8_t)4;
-                a = *reinterpret_cast<uint4*>(tmp);
-                b = *reinterpret_cast<uint4*>(tmp + 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t c = byte_of(a, i);
-                if (c < 4) {
-                    w0 |= c << (2 * i);
-                    vm |= 1u << i;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t c = byte_of(b, i);
-                if (c < 4) {
-                    w1 |= c << (2 * i);
-                    vm |= 1u << (16 + i);
-                }
-            }
-        }
-        packed[2 * g] = w0;
-        packed[2 * g + 1] = w1;
-        valid[g] = vm;
-    }
 }
 
 }  // namespace
@@ -365,33 +368,28 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
     const size_t ntiles = (nbytes + PK_TILE - 1) / PK_TILE;
     const int sms = spk_num_sms();
     SPK_CUDA(cudaMemsetAsync(w.totals, 0, 32, st));
+    // outputs are OR-accumulated: zero the whole tile-aligned extent (this is also the padding)
+    SPK_CUDA(cudaMemsetAsync(d_packed, 0, spk_packed_words(cap_bases) * 4, st));
+    SPK_CUDA(cudaMemsetAsync(d_valid, 0, spk_valid_words(cap_bases) * 4, st));
     if (ntiles > 0) {
         const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
         k_tile_last_newline<<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl);
         SPK_LAUNCH_CHECK();
         k_scan_max_excl<<<1, 1024, 0, st>>>(w.tile_last_nl, ntiles);
         SPK_LAUNCH_CHECK();
-        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl,
-                                                       w.tile_kept, nullptr, nullptr, w.totals);
+        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_kept,
+                                                       nullptr, nullptr, nullptr, w.totals);
         SPK_LAUNCH_CHECK();
     }
     k_scan_sum_excl<<<1, 1024, 0, st>>>(w.tile_kept, w.tile_off, ntiles);
     SPK_LAUNCH_CHECK();
     if (ntiles > 0) {
         const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
-        k_classify<true><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl,
-                                                      nullptr, w.tile_off, w.codes, nullptr);
+        k_classify<true><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, nullptr,
+                                                      w.tile_off, d_packed, d_valid, nullptr);
         SPK_LAUNCH_CHECK();
     }
     k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, d_info);
     SPK_LAUNCH_CHECK();
-    // pack the whole tile-aligned extent of cap_bases so padding is zero
-    const size_t n_groups = spk_valid_words(cap_bases);  // 32 bases per group; packed has 2x words
-    {
-        const size_t blocks = (n_groups + 255) / 256;
-        const unsigned grid = (unsigned)min((size_t)sms * 16, max(blocks, (size_t)1));
-        k_pack_codes<<<grid, 256, 0, st>>>(w.codes, d_info, d_packed, d_valid, n_groups);
-        SPK_LAUNCH_CHECK();
-    }
     return SPK_OK;
 }
