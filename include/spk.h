@@ -180,7 +180,8 @@ int spk_sort_pairs_u64(uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
  * spk_sig_table_build fills an open-addressed table d_skeys (uint64[sslots], pre-filled with 0xFF) /
  * d_svals (uint8[sslots]) and, optionally, a one-hash membership bitmap d_filter (uint32[filter_bits/32],
  * zeroed, filter_bits a power of two ~16x the key count) that lets the ~97 % of positions that are not
- * specific k-mers finish after a single 4-byte load.  spk_map_bins then looks up the k-mer starting at every position i of the
+ * specific k-mers finish after a single 4-byte load.  With pack_vals != 0 (k <= 28) the subgenome id is
+ * stored in the top byte of the key slot and d_svals is not touched.  spk_map_bins then looks up the k-mer starting at every position i of the
  * packed chromosome and, on a hit with value sg, increments d_line_counts[line(i) * S + sg] where
  *   line(i) = i / bin_size + (chunk_size ? (i + k - 1) / chunk_size : 0)
  * i.e. one counter row per (bin, 10-Mb chunk) pair, reproducing the duplicate border lines of
@@ -200,11 +201,11 @@ int spk_stack_lines(const uint32_t* d_line_counts, uint64_t n_lines, int S, int 
                     uint64_t n_windows, void* stream);
 int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, uint64_t* d_skeys,
                         uint8_t* d_svals, uint64_t sslots, uint32_t* d_filter, uint64_t filter_bits,
-                        uint64_t* d_fail, void* stream);
+                        int pack_vals, uint64_t* d_fail, void* stream);
 uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size, uint64_t chunk_size);
 int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
                  const uint64_t* d_skeys, const uint8_t* d_svals, uint64_t sslots, int S,
-                 const uint32_t* d_filter, uint64_t filter_bits, uint64_t bin_size,
+                 const uint32_t* d_filter, uint64_t filter_bits, int pack_vals, uint64_t bin_size,
                  uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
                  uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream);
 

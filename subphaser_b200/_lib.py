@@ -43,10 +43,10 @@ SIGNATURES = {
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),
     "spk_stack_windows": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_stack_lines": (c_i, [c_p, c_u64, c_i, c_i, c_u64, c_u64, c_u64, c_u64, c_p, c_u64, c_p]),
-    "spk_sig_table_build": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_u64, c_p, c_p]),
+    "spk_sig_table_build": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_u64, c_i, c_p, c_p]),
     "spk_map_num_lines": (c_u64, [c_u64, c_i, c_u64, c_u64]),
-    "spk_map_bins": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p, c_u64, c_i, c_p, c_u64, c_u64, c_u64, c_p, c_u64,
-                           c_p, c_p, c_p]),
+    "spk_map_bins": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p, c_u64, c_i, c_p, c_u64, c_i, c_u64, c_u64, c_p,
+                           c_u64, c_p, c_p, c_p]),
     "spk_fisher_right_tail": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_colsum_i64": (c_i, [c_p, c_u64, c_i, c_p, c_p]),
     "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),

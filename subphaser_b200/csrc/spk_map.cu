@@ -17,11 +17,33 @@ constexpr int MP_MAX_S = 32;
 __global__ void __launch_bounds__(256)
 k_sig_build(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ vals, uint64_t n,
             uint64_t* __restrict__ skeys, uint8_t* __restrict__ svals, uint64_t sslots,
-            uint32_t* __restrict__ filter, uint64_t fmask, uint64_t* __restrict__ fail) {
+            uint32_t* __restrict__ filter, uint64_t fmask, int pack_vals, uint64_t* __restrict__ fail) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
         const uint64_t h = spk_hash64(key);
+        if (pack_vals) {
+            // value rides in the top byte of the slot: one load answers "present?" and "which subgenome?"
+            const uint64_t word = key | ((uint64_t)vals[i] << 56);
+            uint64_t slot = spk_slot_of(h, sslots);
+            bool done = false;
+            for (uint64_t p = 0; p < sslots; p++) {
+                const uint64_t old = atomicCAS((unsigned long long*)(skeys + slot),
+                                               (unsigned long long)SPK_EMPTY_KEY, (unsigned long long)word);
+                if (old == SPK_EMPTY_KEY || (old & 0x00ffffffffffffffull) == key) {
+                    done = true;
+                    break;
+                }
+                slot++;
+                if (slot == sslots) slot = 0;
+            }
+            if (filter) {
+                const uint64_t fb = h & fmask;
+                atomicOr(&filter[fb >> 5], 1u << (fb & 31));
+            }
+            if (!done) atomicAdd((unsigned long long*)fail, 1ull);
+            continue;
+        }
         if (filter) {
             const uint64_t fb = h & fmask;
             atomicOr(&filter[fb >> 5], 1u << (fb & 31));
@@ -49,6 +71,7 @@ struct MapArgs {
     uint64_t sslots;
     const uint32_t* filter;   // one-hash Bloom bitmap over the keys (nullptr: none)
     uint64_t fmask;
+    int pack_vals;            // subgenome id stored in the top byte of the key slot (k <= 28)
     int S;
     uint64_t bin_size;
     uint64_t chunk_size;
@@ -130,18 +153,19 @@ k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid
                 uint64_t sl = spk_slot_of(hsh[j], a.sslots);
                 uint64_t c = __ldg(a.skeys + sl);
                 const uint64_t kk = key[j];
-                while (c != SPK_EMPTY_KEY && c != kk) {
+                const uint64_t kmask = a.pack_vals ? 0x00ffffffffffffffull : ~0ull;
+                while (c != SPK_EMPTY_KEY && (c & kmask) != kk) {
                     sl++;
                     if (sl == a.sslots) sl = 0;
                     c = __ldg(a.skeys + sl);
                 }
-                if (c == kk) {
-                    const uint32_t sg = a.svals[sl];
+                if (c != SPK_EMPTY_KEY) {
+                    const uint32_t sg = a.pack_vals ? (uint32_t)(c >> 56) : (uint32_t)a.svals[sl];
                     const uint64_t line = bin + chk;
                     const uint64_t rel = line - line0;
                     if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
                     else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
-                    if (a.hit_flags) a.hit_flags[sl] = 1;
+                    if (a.hit_flags && !a.hit_flags[sl]) a.hit_flags[sl] = 1;
                     n_hit++;
                 }
             }
@@ -230,8 +254,8 @@ extern "C" int spk_stack_windows(const int64_t* d_line_counts, const uint32_t* d
 
 extern "C" int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n,
                                    uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,
-                                   uint32_t* d_filter, uint64_t filter_bits, uint64_t* d_fail,
-                                   void* stream) {
+                                   uint32_t* d_filter, uint64_t filter_bits, int pack_vals,
+                                   uint64_t* d_fail, void* stream) {
     SPK_CHECK_ARG(d_skeys && d_svals && d_fail, "null pointer");
     SPK_CHECK_ARG(sslots >= 2, "sslots too small");
     SPK_CHECK_ARG(!d_filter || (filter_bits >= 32 && (filter_bits & (filter_bits - 1)) == 0),
@@ -241,7 +265,7 @@ extern "C" int spk_sig_table_build(const uint64_t* d_keys, const uint8_t* d_vals
     const uint64_t blocks = (n + 255) / 256;
     const unsigned grid = (unsigned)min(blocks, (uint64_t)spk_num_sms() * 16);
     k_sig_build<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_vals, n, d_skeys, d_svals, sslots,
-                                                        d_filter, d_filter ? filter_bits - 1 : 0, d_fail);
+                                                        d_filter, d_filter ? filter_bits - 1 : 0, pack_vals, d_fail);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -256,8 +280,8 @@ extern "C" uint64_t spk_map_num_lines(uint64_t n_bases, int k, uint64_t bin_size
 
 extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
                             const uint64_t* d_skeys, const uint8_t* d_svals, uint64_t sslots, int S,
-                            const uint32_t* d_filter, uint64_t filter_bits, uint64_t bin_size,
-                            uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
+                            const uint32_t* d_filter, uint64_t filter_bits, int pack_vals,
+                            uint64_t bin_size, uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
                             uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
     SPK_CHECK_ARG(!d_filter || (filter_bits >= 32 && (filter_bits & (filter_bits - 1)) == 0),
                   "filter_bits must be a power of two >= 32");
@@ -270,7 +294,8 @@ extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, u
     if (n_bases < (uint64_t)k) return SPK_OK;
     const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
-    MapArgs a{d_skeys, d_svals, sslots, d_filter, d_filter ? filter_bits - 1 : 0, S, bin_size, chunk_size,
+    SPK_CHECK_ARG(!pack_vals || k <= 28, "packed values need k <= 28");
+    MapArgs a{d_skeys, d_svals, sslots, d_filter, d_filter ? filter_bits - 1 : 0, pack_vals, S, bin_size, chunk_size,
               d_line_counts, n_lines, d_hit_flags, d_nhits};
     k_map_bins<<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a);

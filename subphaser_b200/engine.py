@@ -423,10 +423,11 @@ def pca_gram(G, ncomp):
 class SigTable:
     """canonical specific k-mer -> subgenome index, open-addressed on the device."""
 
-    def __init__(self, keys, vals, k):
+    def __init__(self, keys, vals, k, track_hits=True):
         require_cuda()
         n = int(keys.numel())
         self.k = int(k)
+        self.pack_vals = 1 if self.k <= 28 else 0
         self.n = n
         self.slots = max(2 * n + 64, 1024)
         self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
@@ -437,13 +438,13 @@ class SigTable:
         self.filter = _zeros(self.filter_bits // 32, torch.int32)
         fail = _zeros(1, torch.int64)
         call("spk_sig_table_build", _p(keys), _p(vals), n, _p(self.skeys), _p(self.svals), self.slots,
-             _p(self.filter), self.filter_bits, _p(fail), _stream())
+             _p(self.filter), self.filter_bits, self.pack_vals, _p(fail), _stream())
         if int(fail.item()):
             raise OverflowError("specific k-mer table full")
-        self.hit_flags = _zeros(self.slots, torch.uint8)
+        self.hit_flags = _zeros(self.slots, torch.uint8) if track_hits else None
 
     def n_mapped(self):
-        return int(self.hit_flags.sum().item())
+        return int(self.hit_flags.sum().item()) if self.hit_flags is not None else 0
 
 
 def map_bins(seq, sig, S, bin_size, chunk_size):
@@ -455,7 +456,7 @@ def map_bins(seq, sig, S, bin_size, chunk_size):
     nhits = _zeros(1, torch.int64)
     if seq.n_bases:
         call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
-             sig.slots, S, _p(sig.filter), sig.filter_bits, int(bin_size), int(chunk_size), _p(counts),
+             sig.slots, S, _p(sig.filter), sig.filter_bits, sig.pack_vals, int(bin_size), int(chunk_size), _p(counts),
              max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())
     return counts[:n_lines], int(nhits.item())
 

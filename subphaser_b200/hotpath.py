@@ -28,6 +28,53 @@ def lpt_assign(lengths, world):
     return owner
 
 
+def exchange_dumps(local, n, owner, dist, dev, n_kmers_local=0):
+    """The one exchange step of the path: after it every rank holds every chromosome's dump.
+    local: {chromosome index: (keys int64 tensor, counts int32 tensor, length)} for the chromosomes this
+    rank owns.  Sizes / lengths / k-mer totals travel in one all_reduce, the dumps by broadcast from
+    their owner.  Works on any backend (NCCL on device tensors; gloo on CPU tensors in the tests)."""
+    rank = dist.get_rank()
+    meta = torch.zeros(n + 1, 2, dtype=torch.int64, device=dev)
+    for i, (kk, cc, length) in local.items():
+        meta[i, 0], meta[i, 1] = int(kk.numel()), int(length)
+    meta[n, 0] = int(n_kmers_local)
+    dist.all_reduce(meta)
+    meta_h = meta.cpu().tolist()
+    out = {}
+    for i in range(n):
+        cnt, length = int(meta_h[i][0]), int(meta_h[i][1])
+        if owner[i] == rank:
+            kk, cc, _ = local[i]
+        else:
+            kk = torch.empty(cnt, dtype=torch.int64, device=dev)
+            cc = torch.empty(cnt, dtype=torch.int32, device=dev)
+        if cnt:
+            dist.broadcast(kk, src=owner[i])
+            dist.broadcast(cc, src=owner[i])
+        out[i] = (kk, cc, length)
+    return out, int(meta_h[n][0])
+
+
+def exchange_windows(win_counts, n, nsg, owner, dist, dev):
+    """Per-chromosome window count matrices (int64 [W_i, S]) -> present on every rank."""
+    rank = dist.get_rank()
+    nw = torch.zeros(n, dtype=torch.int64, device=dev)
+    for i, w in win_counts.items():
+        nw[i] = w.shape[0]
+    dist.all_reduce(nw)
+    nw_h = nw.cpu().tolist()
+    out = {}
+    for i in range(n):
+        if owner[i] == rank:
+            w = win_counts[i].contiguous()
+        else:
+            w = torch.empty(int(nw_h[i]), nsg, dtype=torch.int64, device=dev)
+        if w.numel():
+            dist.broadcast(w, src=owner[i])
+        out[i] = w
+    return out
+
+
 class StageTimer:
     """CUDA-event timers on the launching stream, accumulated per stage name."""
 
@@ -118,22 +165,12 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     # ---- exchange: every rank needs every dump (exact merge of the global k-mer table) -------------
     if world > 1:
         e = t.start("exchange")
-        meta = torch.zeros(n, 2, dtype=torch.int64, device=dev)
-        for i in mine:
-            meta[i, 0], meta[i, 1] = len(dumps[i]), dumps[i].length
-        dist.all_reduce(meta)
-        meta_h = meta.cpu().tolist()
+        local = {i: (dumps[i].keys, dumps[i].counts, dumps[i].length) for i in mine}
+        everything, n_kmers_total = exchange_dumps(local, n, owner, dist, dev, n_kmers)
         for i in range(n):
-            cnt, length = int(meta_h[i][0]), int(meta_h[i][1])
             if owner[i] != rank:
-                dumps[i] = engine.KmerDump(torch.empty(cnt, dtype=torch.int64, device=dev),
-                                           torch.empty(cnt, dtype=torch.int32, device=dev), k, length, 0, 0, labels[i])
-            if cnt:
-                dist.broadcast(dumps[i].keys, src=owner[i])
-                dist.broadcast(dumps[i].counts, src=owner[i])
-        kk = torch.tensor([n_kmers], dtype=torch.int64, device=dev)
-        dist.all_reduce(kk)
-        n_kmers_total = int(kk.item())
+                kk, cc, length = everything[i]
+                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i])
         t.stop(e)
     else:
         n_kmers_total = n_kmers
@@ -182,7 +219,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
 
     # ---- K9 map ----------------------------------------------------------------------------------------
     e = t.start("sigtable")
-    sig = engine.SigTable(sig_keys, sig_vals, k)
+    sig = engine.SigTable(sig_keys, sig_vals, k, track_hits=False)
     t.stop(e)
     win_counts = {}
     for i in mine:
@@ -206,15 +243,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     # ---- gather windows, K10 ---------------------------------------------------------------------------
     if world > 1:
         e = t.start("exchange")
-        nw = torch.zeros(n, dtype=torch.int64, device=dev)
-        for i in mine:
-            nw[i] = win_counts[i].shape[0]
-        dist.all_reduce(nw)
-        for i in range(n):
-            if owner[i] != rank:
-                win_counts[i] = torch.empty(int(nw[i].item()), nsg, dtype=torch.int64, device=dev)
-            if win_counts[i].numel():
-                dist.broadcast(win_counts[i], src=owner[i])
+        win_counts = exchange_windows(win_counts, n, nsg, owner, dist, dev)
         t.stop(e)
     e = t.start("enrich")
     allw = torch.cat([win_counts[i] for i in range(n)], dim=0)

@@ -1,0 +1,66 @@
+"""CPU, world_size 2, gloo: the host logic of the multi-GPU path — chromosome sharding (LPT) and the one
+exchange step (dump merge + window gather) — without a GPU."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lpt_assignment_balances_wheat():
+    from subphaser_b200 import hotpath, synth
+    lengths = [m * 1_000_000 for m in synth.WHEAT_MB]
+    for world in (1, 2, 4, 8):
+        owner = hotpath.lpt_assign(lengths, world)
+        assert len(owner) == 21 and set(owner) == set(range(world))
+        load = [sum(l for l, o in zip(lengths, owner) if o == r) for r in range(world)]
+        assert max(load) / (sum(load) / world) < 1.15          # 1.135 at 8 ranks
+    assert hotpath.lpt_assign(lengths, 8) == hotpath.lpt_assign(lengths, 8)   # deterministic on every rank
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from subphaser_b200 import hotpath
+    n = 5
+    lengths = [50, 40, 30, 20, 10]
+    owner = hotpath.lpt_assign(lengths, world)
+    dev = torch.device("cpu")
+    g = torch.Generator().manual_seed(7)
+    full = {}
+    for i in range(n):
+        m = 3 + 2 * i if i != 3 else 0                          # one chromosome with an empty dump
+        full[i] = (torch.randint(0, 2**40, (m,), generator=g, dtype=torch.int64),
+                   torch.randint(3, 100, (m,), generator=g, dtype=torch.int32), 1000 + i)
+    local = {i: full[i] for i in range(n) if owner[i] == rank}
+    out, total = hotpath.exchange_dumps(local, n, owner, dist, dev, n_kmers_local=100 * (rank + 1))
+    ok = total == sum(100 * (r + 1) for r in range(world))
+    for i in range(n):
+        ok &= bool(torch.equal(out[i][0], full[i][0]) and torch.equal(out[i][1], full[i][1]) and out[i][2] == full[i][2])
+    wins = {i: torch.full((i + 1, 3), i, dtype=torch.int64) for i in range(n) if owner[i] == rank}
+    allw = hotpath.exchange_windows(wins, n, 3, owner, dist, dev)
+    for i in range(n):
+        ok &= bool(torch.equal(allw[i], torch.full((i + 1, 3), i, dtype=torch.int64)))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_exchange_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

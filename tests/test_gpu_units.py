@@ -361,3 +361,31 @@ def test_stack_lines_kernel_matches_reference_stack(tmp_path):
             nz = got.any(axis=1)
             assert [[int(x) for x in r] for r in got[nz]] == st["counts"]
             assert [int(w) * ws_i for w in np.nonzero(nz)[0]] == [c[1] for c in st["coords"]]
+
+
+@pytest.mark.parametrize("k", [17, 29, 31])
+def test_map_bins_vs_oracle_mapper(k):
+    """K9 against oracle/kmer_count.c:orc_map_bins, including k > 28 (separate value array)."""
+    import torch
+    import spk_testutil as util
+    from oracle import kmers
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(k)
+    seq = util.messy_seq(rng, 60000, n_frac=0.01)
+    fa = util.fasta([("c", seq)])
+    codes, _ = kmers.fasta_to_codes(fa)
+    keys_all, _, _ = kmers.count_fasta(fa, k, 1)
+    pick = rng.choice(len(keys_all), size=min(4000, len(keys_all)), replace=False)
+    keys = np.sort(keys_all[pick])
+    sgs = rng.integers(0, 3, len(keys)).astype(np.uint8)
+    for bin_size, chunk in ((1000, 7000), (10000, 0), (333, 50000)):
+        L = len(codes)
+        n_lines = (L - 1) // bin_size + ((L - 1 + k - 1) // chunk if chunk else 0) + 1
+        want, hits = kmers.map_bins(codes, k, keys, sgs, 3, bin_size, chunk, n_lines)
+        d, n = engine.to_device_bytes(fa)
+        ps = engine.pack_fasta(d, n)
+        sig = engine.SigTable(torch.from_numpy(keys.view(np.int64).copy()).cuda(), torch.from_numpy(sgs).cuda(), k)
+        got, nh = engine.map_bins(ps, sig, 3, bin_size, chunk)
+        assert nh == hits
+        np.testing.assert_array_equal(got.cpu().numpy().view(np.uint32), want)
+        assert sig.n_mapped() == int(np.isin(keys, keys_all).sum()) or sig.n_mapped() <= len(keys)
