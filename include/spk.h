@@ -125,7 +125,9 @@ int spk_table_extract(const void* d_table, size_t table_bytes, int k, int layout
  * be filled with 0xFF bytes and d_urows (uint32[uslots]) needs no initialisation; *d_nrows (uint32,
  * zeroed) is the row counter.  spk_union_insert adds keys (rows are numbered in arrival order);
  * spk_matrix_fill stores counts[i] into d_matrix[row(keys[i]) * ncol + col] (matrix zeroed by caller;
- * row-major uint32 [nrows x ncol]) and d_row_keys[row] = key.
+ * row-major uint32 [nrows x ncol]) and d_row_keys[row] = key.  With nparts > 1 only the keys whose
+ * hash falls in partition `part` are inserted / filled: rank r of an N-GPU job builds rows part = r
+ * (rows are independent, so the filter shards with no collective).
  *
  * spk_filter_differential evaluates _filter_kmer for every row (outfig is always set by
  * __main__.py:421, so the fold test runs before the frequency gate):
@@ -144,10 +146,12 @@ int spk_table_extract(const void* d_table, size_t table_bytes, int k, int layout
  * (Jellyfish.py:648) and d_out_tot[j].
  * ---------------------------------------------------------------------------------------------- */
 int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_ukeys, uint32_t* d_urows,
-                     uint64_t uslots, uint32_t* d_nrows, uint64_t* d_fail, void* stream);
+                     uint64_t uslots, uint32_t* d_nrows, uint64_t* d_fail, uint32_t nparts,
+                     uint32_t part, void* stream);
 int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
                     const uint64_t* d_ukeys, const uint32_t* d_urows, uint64_t uslots,
-                    uint32_t* d_matrix, uint64_t* d_row_keys, int ncol, int col, void* stream);
+                    uint32_t* d_matrix, uint64_t* d_row_keys, int ncol, int col, uint32_t nparts,
+                    uint32_t part, void* stream);
 int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
                             const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
                             const int32_t* d_grp_off, int n_groups, const int32_t* d_members,

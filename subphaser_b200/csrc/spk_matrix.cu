@@ -14,11 +14,13 @@ constexpr int MX_MAX_GROUPS_PER_SET = 32;
 __global__ void __launch_bounds__(MX_THREADS)
 k_union_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ ukeys,
                uint32_t* __restrict__ urows, uint64_t uslots, uint32_t* __restrict__ nrows,
-               uint64_t* __restrict__ fail) {
+               uint64_t* __restrict__ fail, uint32_t nparts, uint32_t part) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
-        uint64_t slot = spk_slot_of(spk_hash64(key), uslots);
+        const uint64_t h = spk_hash64(key);
+        if (nparts > 1 && (uint32_t)(h & 0xffffffffu) % nparts != part) continue;   // another rank's row
+        uint64_t slot = spk_slot_of(h, uslots);
         bool done = false;
         for (uint64_t p = 0; p < uslots; p++) {
             uint64_t cur = __ldcg(ukeys + slot);
@@ -48,11 +50,14 @@ k_union_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restri
 __global__ void __launch_bounds__(MX_THREADS)
 k_matrix_fill(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, uint64_t n,
               const uint64_t* __restrict__ ukeys, const uint32_t* __restrict__ urows, uint64_t uslots,
-              uint32_t* __restrict__ matrix, uint64_t* __restrict__ row_keys, int ncol, int col) {
+              uint32_t* __restrict__ matrix, uint64_t* __restrict__ row_keys, int ncol, int col,
+              uint32_t nparts, uint32_t part) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t key = keys[i];
-        uint64_t slot = spk_slot_of(spk_hash64(key), uslots);
+        const uint64_t h = spk_hash64(key);
+        if (nparts > 1 && (uint32_t)(h & 0xffffffffu) % nparts != part) continue;
+        uint64_t slot = spk_slot_of(h, uslots);
         for (uint64_t p = 0; p < uslots; p++) {
             const uint64_t cur = __ldg(ukeys + slot);
             if (cur == key) {
@@ -259,13 +264,14 @@ unsigned grid_for(uint64_t n) {
 
 extern "C" int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_ukeys,
                                 uint32_t* d_urows, uint64_t uslots, uint32_t* d_nrows,
-                                uint64_t* d_fail, void* stream) {
+                                uint64_t* d_fail, uint32_t nparts, uint32_t part, void* stream) {
+    SPK_CHECK_ARG(nparts >= 1 && part < nparts, "bad partition");
     SPK_CHECK_ARG(d_ukeys && d_urows && d_nrows && d_fail, "null pointer");
     SPK_CHECK_ARG(uslots >= 2, "uslots too small");
     if (n == 0) return SPK_OK;
     SPK_CHECK_ARG(d_keys, "null keys");
     k_union_insert<<<grid_for(n), MX_THREADS, 0, (cudaStream_t)stream>>>(d_keys, n, d_ukeys, d_urows,
-                                                                         uslots, d_nrows, d_fail);
+                                                                         uslots, d_nrows, d_fail, nparts, part);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
@@ -273,13 +279,14 @@ extern "C" int spk_union_insert(const uint64_t* d_keys, uint64_t n, uint64_t* d_
 extern "C" int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n,
                                const uint64_t* d_ukeys, const uint32_t* d_urows, uint64_t uslots,
                                uint32_t* d_matrix, uint64_t* d_row_keys, int ncol, int col,
-                               void* stream) {
+                               uint32_t nparts, uint32_t part, void* stream) {
+    SPK_CHECK_ARG(nparts >= 1 && part < nparts, "bad partition");
     SPK_CHECK_ARG(d_ukeys && d_urows && d_matrix && d_row_keys, "null pointer");
     SPK_CHECK_ARG(ncol >= 1 && col >= 0 && col < ncol, "bad column");
     if (n == 0) return SPK_OK;
     SPK_CHECK_ARG(d_keys && d_counts, "null keys/counts");
     k_matrix_fill<<<grid_for(n), MX_THREADS, 0, (cudaStream_t)stream>>>(
-        d_keys, d_counts, n, d_ukeys, d_urows, uslots, d_matrix, d_row_keys, ncol, col);
+        d_keys, d_counts, n, d_ukeys, d_urows, uslots, d_matrix, d_row_keys, ncol, col, nparts, part);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -232,19 +232,21 @@ class CountMatrix:
         return len(self.lengths)
 
 
-def build_matrix(dumps, labels=None):
-    """JellyfishDumps.to_matrix on the device: union of the dumped k-mers, one column per chromosome."""
+def build_matrix(dumps, labels=None, nparts=1, part=0):
+    """JellyfishDumps.to_matrix on the device: union of the dumped k-mers, one column per chromosome.
+    nparts/part: build only the rows whose k-mer hashes into partition `part` (multi-GPU row sharding)."""
     require_cuda()
     st = _stream()
     n = len(dumps)
     total = sum(len(d) for d in dumps)
-    uslots = max(int(total / 0.5) + 1024, 2048)   # >= 2 x #distinct
+    uslots = max(int(total / 0.5 / nparts * (1.1 if nparts > 1 else 1.0)) + 1024, 2048)   # >= 2 x #distinct
     ukeys = torch.full((uslots,), -1, dtype=torch.int64, device=_dev())
     urows = _empty(uslots, torch.int32)
     nrows = _zeros(1, torch.int32)
     fail = _zeros(1, torch.int64)
     for d in dumps:
-        call("spk_union_insert", _p(d.keys), len(d), _p(ukeys), _p(urows), uslots, _p(nrows), _p(fail), st)
+        call("spk_union_insert", _p(d.keys), len(d), _p(ukeys), _p(urows), uslots, _p(nrows), _p(fail),
+             nparts, part, st)
     U = int(nrows.item())
     if int(fail.item()):
         raise OverflowError("union table full")
@@ -252,7 +254,7 @@ def build_matrix(dumps, labels=None):
     row_keys = _empty(U, torch.int64)
     for i, d in enumerate(dumps):
         call("spk_matrix_fill", _p(d.keys), _p(d.counts), len(d), _p(ukeys), _p(urows), uslots, _p(matrix),
-             _p(row_keys), n, i, st)
+             _p(row_keys), n, i, nparts, part, st)
     k = dumps[0].k if dumps else 0
     return CountMatrix(matrix, row_keys, [d.length for d in dumps], k, labels)
 
@@ -318,6 +320,21 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
     if want_fold_tots and U:
         fold_tots = tot[:U][(flags[:U] & 1).bool()].cpu().numpy()
     return DiffMatrix(keys, norm, otot, cm.k, labels, n_fold, fold_tots)
+
+
+def argsort_keys(keys, key_bits):
+    """Stable ascending argsort of uint64 keys held in an int64 tensor (spk_sort_pairs_u64)."""
+    require_cuda()
+    lib = _lib.load()
+    n = int(keys.numel())
+    idx = torch.arange(n, dtype=torch.int32, device=_dev())
+    if n > 1:
+        k2 = keys.clone()
+        kt, it = _empty(n, torch.int64), _empty(n, torch.int32)
+        ws_bytes = lib.spk_sort_workspace_bytes(n)
+        ws = _empty(ws_bytes, torch.uint8)
+        call("spk_sort_pairs_u64", _p(k2), _p(idx), _p(kt), _p(it), n, int(key_bits), _p(ws), ws_bytes, _stream())
+    return idx.long()
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -55,6 +55,40 @@ def exchange_dumps(local, n, owner, dist, dev, n_kmers_local=0):
     return out, int(meta_h[n][0])
 
 
+def exchange_rows(dm, n_union_local, dist, dev):
+    """Differential-matrix shards (rows hashed over ranks) -> the full matrix, sorted by k-mer, on every rank."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ncol = dm.norm.shape[1]
+    meta = torch.zeros(world + 2, dtype=torch.int64, device=dev)
+    meta[rank] = len(dm)
+    meta[world] = int(n_union_local)
+    meta[world + 1] = int(dm.n_fold_pass)
+    dist.all_reduce(meta)
+    meta_h = meta.cpu().tolist()
+    keys, norm, tot = [], [], []
+    for r in range(world):
+        m = int(meta_h[r])
+        if r == rank:
+            kk, nn, tt = dm.keys.contiguous(), dm.norm.contiguous(), dm.tot.contiguous()
+        else:
+            kk = torch.empty(m, dtype=torch.int64, device=dev)
+            nn = torch.empty(m, ncol, dtype=torch.float64, device=dev)
+            tt = torch.empty(m, dtype=torch.int64, device=dev)
+        if m:
+            dist.broadcast(kk, src=r)
+            dist.broadcast(nn, src=r)
+            dist.broadcast(tt, src=r)
+        keys.append(kk)
+        norm.append(nn)
+        tot.append(tt)
+    keys, norm, tot = torch.cat(keys), torch.cat(norm), torch.cat(tot)
+    # global row order = ascending k-mer, as on one GPU (keys are < 2^63 except k = 32: use the sort kernel)
+    order = engine.argsort_keys(keys, 2 * dm.k)
+    full = engine.DiffMatrix(keys[order].contiguous(), norm[order].contiguous(), tot[order].contiguous(), dm.k,
+                             dm.labels, int(meta_h[world + 1]))
+    return full, int(meta_h[world])
+
+
 def exchange_windows(win_counts, n, nsg, owner, dist, dev):
     """Per-chromosome window count matrices (int64 [W_i, S]) -> present on every rank."""
     rank = dist.get_rank()
@@ -176,16 +210,21 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         n_kmers_total = n_kmers
     dump_list = [dumps[i] for i in range(n)]
 
-    # ---- K3b/K4 matrix + filter -----------------------------------------------------------------------
+    # ---- K3b/K4 matrix + filter: rows are independent -> each rank builds the rows of its hash share ----
     e = t.start("matrix")
-    cm = engine.build_matrix(dump_list, labels)
+    cm = engine.build_matrix(dump_list, labels, nparts=world, part=rank)
     t.stop(e)
     e = t.start("filter")
     dm = engine.filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
                               min_freq=min_freq, max_freq=max_freq)
     t.stop(e)
-    n_union, M = len(cm), len(dm)
+    n_union = len(cm)
     del cm
+    if world > 1:
+        e = t.start("exchange")
+        dm, n_union = exchange_rows(dm, n_union, dist, dev)
+        t.stop(e)
+    M = len(dm)
     if M == 0:
         raise ValueError("0 kmer remained after filtering. Please reset the filter options.")
 
