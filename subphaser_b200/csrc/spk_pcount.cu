@@ -67,8 +67,13 @@ struct PcPlan {
     uint64_t P;
     Mixer mx;
     uint64_t n_tiles;
-    size_t off_buf, off_psize, off_pstart, off_cursor, off_segs, off_out, total;
+    int two_level, b1, b2;        // two-level scatter: 2^b1 buckets x 2^b2 sub-partitions (b1 + b2 = pbits)
+    size_t off_buf, off_buf1, off_psize, off_pstart, off_cursor, off_segs, off_cur1, off_ustart, off_out, total;
 };
+
+constexpr int SC_TILES = 4;                         // tiles per super-tile of the two-level scatter
+constexpr int SC_CHUNK = SC_TILES * SPK_TILE_BASES; // 16384 entries staged in shared memory at a time
+constexpr int SC_MAX_BINS = 2048;
 
 inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -86,9 +91,21 @@ int make_plan(uint64_t n_bases, int k, PcPlan* pl) {
     pl->mx.s = k;
     pl->mx.rbits = 2 * k - pbits;
     pl->n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
+    // two-level scatter when it pays (enough partitions) and the level-1 entry still fits 32 bits
+    pl->b1 = (pbits + 1) / 2;
+    pl->b2 = pbits - pl->b1;
+    const char* e2 = getenv("SPK_PCOUNT_TWO_LEVEL");
+    pl->two_level = (!pl->ent64 && pbits >= 12 && 2 * k - pl->b1 <= 32 && (1 << pl->b1) <= SC_MAX_BINS &&
+                     !(e2 && e2[0] == '0')) ? 1 : 0;
     size_t off = 0;
     pl->off_buf = off;
     off += al256((size_t)(n_bases + 64) * (pl->ent64 ? 8 : 4));
+    pl->off_buf1 = off;
+    if (pl->two_level) off += al256((size_t)(n_bases + 64) * 4);
+    pl->off_cur1 = off;
+    off += al256((size_t)(SC_MAX_BINS + 1) * 4);
+    pl->off_ustart = off;
+    off += al256((size_t)(SC_MAX_BINS + 2) * 4);
     pl->off_psize = off;
     off += al256((size_t)(pl->P + 1) * 4);
     pl->off_pstart = off;
@@ -212,6 +229,212 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const uint32_t* __restrict_
         pstart[i] = e;
         cursor[i] = e;
         if (i == n - 1) pstart[n] = e + x;
+    }
+}
+
+// ---- two-level scatter: shared-memory staged, coalesced runs, no per-k-mer global atomic --------------------
+// Level 1 splits the k-mers of a 4-tile super-tile into 2^b1 buckets, level 2 splits 16384-entry chunks of
+// a bucket into its 2^b2 final partitions.  Both levels: histogram in smem, exclusive scan, ONE global
+// atomicAdd per non-empty bin to reserve a run, counting-sort placement in smem, coalesced write of runs.
+struct ScatterSmem {
+    uint32_t* cnt;     // [nb]   histogram, then running cursor
+    uint32_t* off;     // [nb]   exclusive prefix inside the chunk
+    uint32_t* gbase;   // [nb]   (global run start) - off  (mod 2^32)
+    uint32_t* sorted;  // [SC_CHUNK]
+    uint16_t* bin;     // [SC_CHUNK]
+};
+
+__device__ __forceinline__ ScatterSmem carve_scatter(uint8_t* base, int nb) {
+    ScatterSmem s;
+    s.cnt = (uint32_t*)base;
+    s.off = s.cnt + nb;
+    s.gbase = s.off + nb;
+    s.sorted = s.gbase + nb;
+    s.bin = (uint16_t*)(s.sorted + SC_CHUNK);
+    return s;
+}
+inline size_t scatter_smem_bytes(int nb) { return (size_t)nb * 12 + (size_t)SC_CHUNK * 6; }
+
+// exclusive scan of cnt[nb] into off[nb] by a 256-thread CTA (nb a multiple of 256 or smaller); returns total
+__device__ __forceinline__ uint32_t bins_scan(const uint32_t* cnt, uint32_t* off, int nb, uint32_t* s_warp) {
+    const int per = (nb + SPK_TILE_THREADS - 1) / SPK_TILE_THREADS;
+    const int b0 = threadIdx.x * per;
+    uint32_t sum = 0;
+    for (int q = 0; q < per; q++)
+        if (b0 + q < nb) sum += cnt[b0 + q];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t prefix = 0, total = 0;
+    for (int w = 0; w < SPK_TILE_THREADS / 32; w++) {
+        if (w < (int)(threadIdx.x >> 5)) prefix += s_warp[w];
+        total += s_warp[w];
+    }
+    uint32_t run = prefix + incl - sum;
+    for (int q = 0; q < per; q++)
+        if (b0 + q < nb) {
+            off[b0 + q] = run;
+            run += cnt[b0 + q];
+        }
+    __syncthreads();
+    return total;
+}
+
+// reserve one global run per non-empty bin and turn cnt into the running cursor
+__device__ __forceinline__ void bins_reserve(ScatterSmem& s, int nb, uint32_t* __restrict__ gcursor) {
+    for (int b = threadIdx.x; b < nb; b += SPK_TILE_THREADS) {
+        const uint32_t c = s.cnt[b];
+        if (c) s.gbase[b] = atomicAdd(&gcursor[b], c) - s.off[b];
+        s.cnt[b] = s.off[b];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SPK_TILE_THREADS, 2)
+k_scatter_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k,
+             Mixer mx, int b1, uint32_t* __restrict__ cur1, uint32_t* __restrict__ buf1) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr int PKW = (SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) / 4;   // 1028
+    constexpr int VDW = (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) / 4;     // 516
+    uint32_t* pk = (uint32_t*)s_raw;
+    uint32_t* vd = pk + PKW;
+    uint64_t* bar = (uint64_t*)(vd + VDW + (VDW & 1));
+    const int nb = 1 << b1;
+    ScatterSmem sc = carve_scatter((uint8_t*)(bar + 2), nb);
+    __shared__ uint32_t s_warp[SPK_TILE_THREADS / 32];
+    const int tid = threadIdx.x;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    const int sh1 = 2 * k - b1;                                   // bucket = h >> sh1
+    const uint64_t m1 = (sh1 >= 64) ? ~0ull : ((1ull << sh1) - 1); // level-1 entry = h & m1  (<= 32 bits)
+    if (tid == 0) {
+        spk_mbar_init(bar, 1);
+        spk_fence_mbar_init();
+    }
+    __syncthreads();
+    const uint64_t n_super = (n_tiles + SC_TILES - 1) / SC_TILES;
+    uint32_t it = 0;
+    for (uint64_t st = blockIdx.x; st < n_super; st += gridDim.x, it++) {
+        const uint64_t t0 = st * SC_TILES;
+        const int ntl = (int)min((uint64_t)SC_TILES, n_tiles - t0);
+        if (tid == 0) {
+            const uint32_t pb = ntl * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES;
+            const uint32_t vb = ntl * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES;
+            spk_mbar_expect_tx(bar, pb + vb);
+            spk_bulk_g2s(pk, packed + t0 * SPK_TILE_PACKED_BYTES, pb, bar);
+            spk_bulk_g2s(vd, valid + t0 * SPK_TILE_VALID_BYTES, vb, bar);
+        }
+        for (int b = tid; b < nb; b += SPK_TILE_THREADS) sc.cnt[b] = 0;
+        __syncthreads();
+        spk_mbar_wait(bar, it & 1);
+        // pass A: histogram of bucket ids
+        for (int t = 0; t < ntl; t++) {
+            uint64_t key[SPK_KMERS_PER_THREAD];
+            uint32_t okmask;
+            spk_kmers_from(pk + t * (SPK_TILE_PACKED_BYTES / 4), vd + t * (SPK_TILE_VALID_BYTES / 4), kp, key, okmask);
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+                if ((okmask >> j) & 1u) atomicAdd(&sc.cnt[mx.fwd(key[j]) >> sh1], 1u);
+        }
+        __syncthreads();
+        const uint32_t n_e = bins_scan(sc.cnt, sc.off, nb, s_warp);
+        bins_reserve(sc, nb, cur1);
+        // pass B: counting-sort placement
+        for (int t = 0; t < ntl; t++) {
+            uint64_t key[SPK_KMERS_PER_THREAD];
+            uint32_t okmask;
+            spk_kmers_from(pk + t * (SPK_TILE_PACKED_BYTES / 4), vd + t * (SPK_TILE_VALID_BYTES / 4), kp, key, okmask);
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+                if ((okmask >> j) & 1u) {
+                    const uint64_t h = mx.fwd(key[j]);
+                    const uint32_t b = (uint32_t)(h >> sh1);
+                    const uint32_t p = atomicAdd(&sc.cnt[b], 1u);
+                    sc.sorted[p] = (uint32_t)(h & m1);
+                    sc.bin[p] = (uint16_t)b;
+                }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n_e; i += SPK_TILE_THREADS) buf1[sc.gbase[sc.bin[i]] + i] = sc.sorted[i];
+        __syncthreads();   // smem is reused by the next super-tile (and by the next bulk copy)
+    }
+}
+
+// cursors of the level-1 buckets and the unit table of level 2 (unit = one 16384-entry chunk of a bucket)
+__global__ void __launch_bounds__(1024)
+k_scatter_prepare(const uint32_t* __restrict__ pstart, int b1, int b2, uint32_t* __restrict__ cur1,
+                  uint32_t* __restrict__ ustart) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int nb = 1 << b1;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int b = base + threadIdx.x;
+        uint32_t units = 0;
+        if (b < nb) {
+            const uint32_t bs = pstart[(uint64_t)b << b2], be = pstart[((uint64_t)b + 1) << b2];
+            cur1[b] = bs;
+            units = (be - bs + SC_CHUNK - 1) / SC_CHUNK;
+        }
+        uint32_t tot;
+        const uint32_t excl = block_scan_1024(units, s_warp, &tot);
+        if (b < nb) ustart[b] = s_carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ustart[nb] = s_carry;
+}
+
+__global__ void __launch_bounds__(SPK_TILE_THREADS, 2)
+k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pstart,
+             const uint32_t* __restrict__ ustart, int b1, int b2, int rbits, uint32_t* __restrict__ cursor,
+             uint32_t* __restrict__ buf) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int nb = 1 << b2;
+    ScatterSmem sc = carve_scatter(s_raw, nb);
+    __shared__ uint32_t s_warp[SPK_TILE_THREADS / 32];
+    __shared__ uint32_t s_unit[3];   // bucket, begin, end
+    const int tid = threadIdx.x;
+    const int nb1 = 1 << b1;
+    const uint32_t n_units = ustart[nb1];
+    const uint32_t rmask = (rbits >= 32) ? 0xffffffffu : ((1u << rbits) - 1u);
+    for (uint32_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        if (tid == 0) {
+            int lo = 0, hi = nb1;              // last bucket with ustart[b] <= u
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (ustart[mid] <= u) lo = mid;
+                else hi = mid;
+            }
+            const uint32_t bs = pstart[(uint64_t)lo << b2], be = pstart[((uint64_t)lo + 1) << b2];
+            const uint32_t beg = bs + (u - ustart[lo]) * SC_CHUNK;
+            s_unit[0] = lo;
+            s_unit[1] = beg;
+            s_unit[2] = min(beg + (uint32_t)SC_CHUNK, be);
+        }
+        for (int b = tid; b < nb; b += SPK_TILE_THREADS) sc.cnt[b] = 0;
+        __syncthreads();
+        const uint32_t bucket = s_unit[0], beg = s_unit[1], end = s_unit[2];
+        for (uint32_t i = beg + tid; i < end; i += SPK_TILE_THREADS) atomicAdd(&sc.cnt[buf1[i] >> rbits], 1u);
+        __syncthreads();
+        const uint32_t n_e = bins_scan(sc.cnt, sc.off, nb, s_warp);
+        bins_reserve(sc, nb, cursor + ((uint64_t)bucket << b2));
+        for (uint32_t i = beg + tid; i < end; i += SPK_TILE_THREADS) {
+            const uint32_t v = buf1[i];
+            const uint32_t sub = v >> rbits;
+            const uint32_t p = atomicAdd(&sc.cnt[sub], 1u);
+            sc.sorted[p] = v & rmask;
+            sc.bin[p] = (uint16_t)sub;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n_e; i += SPK_TILE_THREADS) buf[sc.gbase[sc.bin[i]] + i] = sc.sorted[i];
+        __syncthreads();
     }
 }
 
@@ -390,9 +613,34 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
     SPK_LAUNCH_CHECK();
     k_scan_apply<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs, pstart, cursor);
     SPK_LAUNCH_CHECK();
-    k_part_pass<true, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
-                                                                     cursor, buf, d_stats);
-    SPK_LAUNCH_CHECK();
+    if (pl.two_level && !ENT64) {
+        uint32_t* buf1 = (uint32_t*)(ws + pl.off_buf1);
+        uint32_t* cur1 = (uint32_t*)(ws + pl.off_cur1);
+        uint32_t* ustart = (uint32_t*)(ws + pl.off_ustart);
+        k_scatter_prepare<<<1, 1024, 0, st>>>(pstart, pl.b1, pl.b2, cur1, ustart);
+        SPK_LAUNCH_CHECK();
+        const size_t tile_bytes = ((SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) +
+                                   (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) + 8 + 16 + 15) / 16 * 16;
+        const size_t smem1 = tile_bytes + scatter_smem_bytes(1 << pl.b1);
+        const size_t smem2 = scatter_smem_bytes(1 << pl.b2);
+        static bool l_attr = false;
+        if (!l_attr) {
+            SPK_CUDA(cudaFuncSetAttribute(k_scatter_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            SPK_CUDA(cudaFuncSetAttribute(k_scatter_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            l_attr = true;
+        }
+        const uint64_t n_super = (pl.n_tiles + SC_TILES - 1) / SC_TILES;
+        k_scatter_l1<<<(unsigned)min((uint64_t)sms * 2, n_super), SPK_TILE_THREADS, smem1, st>>>(
+            pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1);
+        SPK_LAUNCH_CHECK();
+        k_scatter_l2<<<(unsigned)(sms * 2), SPK_TILE_THREADS, smem2, st>>>(buf1, pstart, ustart, pl.b1, pl.b2,
+                                                                           pl.mx.rbits, cursor, (uint32_t*)buf);
+        SPK_LAUNCH_CHECK();
+    } else {
+        k_part_pass<true, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
+                                                                         cursor, buf, d_stats);
+        SPK_LAUNCH_CHECK();
+    }
     const size_t smem = (size_t)PC_SLOTS * (ENT64 ? 12 : 8);
     static bool attr_set[2] = {false, false};
     if (!attr_set[ENT64 ? 1 : 0]) {

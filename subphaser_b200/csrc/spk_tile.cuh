@@ -62,12 +62,13 @@ __device__ __forceinline__ uint64_t spk_rev2(uint64_t x) {
 // Canonical k-mers of this thread's 16 start positions; bit j of okmask = window j has k valid bases.
 // Forward word: first base most significant (integer order == lexicographic A<C<G<T); the reverse
 // complement is rolled alongside; canonical = min of the two.
-__device__ __forceinline__ void spk_tile_kmers(const SpkTileSmem& s, int buf, const SpkKmerParams& p,
+// `pk` / `vd`: shared-memory words of one tile (260 / 132 words incl. halo).
+__device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_t* vd, const SpkKmerParams& p,
                                                uint64_t (&key)[SPK_KMERS_PER_THREAD],
                                                uint32_t& okmask) {
     const int tid = threadIdx.x;
-    const uint32_t w0 = s.packed[buf][tid], w1 = s.packed[buf][tid + 1], w2 = s.packed[buf][tid + 2];
-    const uint32_t v0 = s.valid[buf][tid >> 1], v1 = s.valid[buf][(tid >> 1) + 1];
+    const uint32_t w0 = pk[tid], w1 = pk[tid + 1], w2 = pk[tid + 2];
+    const uint32_t v0 = vd[tid >> 1], v1 = vd[(tid >> 1) + 1];
     const uint64_t vbits = (((uint64_t)v1 << 32) | v0) >> ((tid & 1) * 16);
     const uint64_t lo = ((uint64_t)w1 << 32) | w0;
 
@@ -89,4 +90,10 @@ __device__ __forceinline__ void spk_tile_kmers(const SpkTileSmem& s, int buf, co
         key[j] = (fwd < rc) ? fwd : rc;
         if (((vbits >> j) & p.vmask) == p.vmask) okmask |= 1u << j;
     }
+}
+
+__device__ __forceinline__ void spk_tile_kmers(const SpkTileSmem& s, int buf, const SpkKmerParams& p,
+                                               uint64_t (&key)[SPK_KMERS_PER_THREAD],
+                                               uint32_t& okmask) {
+    spk_kmers_from(s.packed[buf], s.valid[buf], p, key, okmask);
 }

@@ -109,6 +109,21 @@ def exchange_windows(win_counts, n, nsg, owner, dist, dev):
     return out
 
 
+_PINNED = {}
+
+
+def _to_host_pinned(name, t):
+    """Device tensor -> numpy through a cached pinned staging buffer (async copy; caller synchronises)."""
+    n = t.numel()
+    buf = _PINNED.get(name)
+    if buf is None or buf.numel() < n or buf.dtype != t.dtype:
+        buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+        _PINNED[name] = buf
+    view = buf[:n].view(t.shape)
+    view.copy_(t, non_blocking=True)
+    return view
+
+
 class StageTimer:
     """CUDA-event timers on the launching stream, accumulated per stage name."""
 
@@ -295,4 +310,11 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
                 n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
                 lengths=[d.length for d in dump_list], enrich=enr, dm=dm, pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
                 h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes if return_host else int(allw.numel() * 8 * 4),
-                matrix_host=(engine.u64_numpy(dm.keys), dm.norm.cpu().numpy()) if return_host else None)
+                matrix_host=_matrix_host(dm) if return_host else None)
+
+
+def _matrix_host(dm):
+    k = _to_host_pinned("dm_keys", dm.keys)
+    v = _to_host_pinned("dm_norm", dm.norm)
+    torch.cuda.current_stream().synchronize()
+    return k.numpy().view(np.uint64), v.numpy()

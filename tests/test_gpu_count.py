@@ -105,3 +105,20 @@ def test_larger_than_tile_and_table_growth():
     seq = util.messy_seq(rng, 1_500_000, repeat_unit="ACGGT")
     _check(util.fasta([("big", seq)]), 17, 3)
     _check(util.fasta([("big", seq)]), 21, 1)
+
+
+@pytest.mark.parametrize("k", [15, 17, 21])
+def test_two_level_scatter_path(k):
+    """>= 6.3 M bases switch the partitioned counter to its two-level shared-memory staged scatter."""
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    rng = np.random.default_rng(k)
+    unit = util.random_seq(rng, 3000)
+    parts = []
+    for i in range(30):                      # repeats (counts > 1) between stretches of unique sequence
+        parts.append(util.random_seq(rng, 300000))
+        parts.append(unit if i % 3 else unit[:1500] + "N" * 20 + unit[1500:])
+    seq = "".join(parts)
+    assert len(seq) > 9_000_000
+    _check(util.fasta([("big", seq)]), k, 1)
+    _check(util.fasta([("big", seq)]), k, 3)
