@@ -461,41 +461,88 @@ struct CountOut {
 
 // ENT32: slot u64 = (r << 32) | count, empty = 0 (count >= 1 once occupied).
 // ENT64: key u64 (empty = ~0) and count u32 in separate arrays.
+// The table is cleared once per CTA; every insert that creates a key appends its slot to a list, so the
+// dump visits (and re-clears) only the occupied slots — the zero + full-scan loops of a naive version
+// cost more instructions than the inserts themselves.
+constexpr int PC_LIST = 4096;   // occupied-slot list capacity; beyond it a partition falls back to a full scan
+
 template <bool ENT64>
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
              CountOut o) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint64_t* s_key = (uint64_t*)s_raw;
-    uint32_t* s_cnt = (uint32_t*)(s_raw + (size_t)PC_SLOTS * 8);  // ENT64 only
+    uint16_t* s_list = (uint16_t*)(s_raw + (size_t)PC_SLOTS * 8);
+    uint32_t* s_cnt = (uint32_t*)(s_raw + (size_t)PC_SLOTS * 8 + (size_t)PC_LIST * 2);  // ENT64 only
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_red[4][PC_THREADS / 32];
+    __shared__ uint32_t s_nocc;
     const int tid = threadIdx.x;
     uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0, n_fail = 0;
     uint32_t h1 = 0, h2 = 0;
     if (o.histo) s_hist[tid] = 0;
     const uint64_t EMPTY = ENT64 ? SPK_EMPTY_KEY : 0ull;
+    constexpr uint32_t TMASK = PC_SLOTS - 1;
+    for (uint32_t i = tid; i < PC_SLOTS; i += PC_THREADS) {
+        s_key[i] = EMPTY;
+        if (ENT64) s_cnt[i] = 0;
+    }
+    if (tid == 0) s_nocc = 0;
+    __syncthreads();
+
+    // one slot of the table -> stats / histogram / dump; clears the slot
+    auto visit = [&](uint32_t slot, bool active, uint64_t p) {
+        uint64_t r = 0, cnt = 0;
+        bool occ = false;
+        if (active) {
+            const uint64_t v = s_key[slot];
+            occ = v != EMPTY;
+            if (occ) {
+                r = ENT64 ? v : (v >> 32);
+                cnt = ENT64 ? (uint64_t)s_cnt[slot] : (v & 0xffffffffull);
+                s_key[slot] = EMPTY;
+                if (ENT64) s_cnt[slot] = 0;
+                distinct++;
+                sumall += cnt;
+                if (o.histo) {
+                    const uint64_t b = cnt < (uint64_t)(o.histo_len - 1) ? cnt : (uint64_t)(o.histo_len - 1);
+                    if (b == 1) h1++;
+                    else if (b == 2) h2++;
+                    else if (b < 256) atomicAdd(&s_hist[b], 1u);
+                    else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
+                }
+            }
+        }
+        const bool keep = occ && cnt >= o.lower;
+        if (keep) {
+            nge++;
+            sumge += cnt;
+        }
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (ballot) {
+            const int lane = tid & 31;
+            uint64_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd((unsigned long long*)o.cursor, (unsigned long long)__popc(ballot));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (keep) {
+                const uint64_t at = wbase + __popc(ballot & ((1u << lane) - 1));
+                if (at < o.cap) {
+                    o.keys[at] = mx.inv((p << mx.rbits) | r);
+                    o.counts[at] = (uint32_t)cnt;
+                }
+            }
+        }
+    };
 
     for (uint64_t p = blockIdx.x; p < P; p += gridDim.x) {
         const uint32_t beg = pstart[p], end = pstart[p + 1];
-        const uint32_t n_p = end - beg;
-        if (n_p == 0) continue;
-        // table size: power of two >= 2 * entries, at most PC_SLOTS
-        uint32_t tsz = 64;
-        while (tsz < PC_SLOTS && tsz < 2 * n_p) tsz <<= 1;
-        const uint32_t tmask = tsz - 1;
-        __syncthreads();  // previous partition's scan is finished
-        for (uint32_t i = tid; i < tsz; i += PC_THREADS) {
-            s_key[i] = EMPTY;
-            if (ENT64) s_cnt[i] = 0;
-        }
-        __syncthreads();
+        if (end == beg) continue;
         // ---- insert ----
         for (uint32_t i = beg + tid; i < end; i += PC_THREADS) {
             const uint64_t r = ENT64 ? __ldcs((const uint64_t*)buf + i) : (uint64_t)__ldcs((const uint32_t*)buf + i);
-            uint32_t s = (ENT64 ? (uint32_t)spk_hash64(r) : fmix32((uint32_t)r)) & tmask;
+            uint32_t s = (ENT64 ? (uint32_t)spk_hash64(r) : fmix32((uint32_t)r)) & TMASK;
             bool done = false;
-            for (uint32_t probes = 0; probes < tsz; probes++) {
+            for (uint32_t probes = 0; probes < PC_SLOTS; probes++) {
                 uint64_t c = s_key[s];
                 if (c == EMPTY) {
                     const uint64_t fresh = ENT64 ? r : ((r << 32) | 1ull);
@@ -503,6 +550,8 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
                                                    (unsigned long long)fresh);
                     if (old == EMPTY) {
                         if (ENT64) atomicAdd(&s_cnt[s], 1u);
+                        const uint32_t li = atomicAdd(&s_nocc, 1u);
+                        if (li < PC_LIST) s_list[li] = (uint16_t)s;
                         done = true;
                         break;
                     }
@@ -514,50 +563,24 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
                     done = true;
                     break;
                 }
-                s = (s + 1) & tmask;
+                s = (s + 1) & TMASK;
             }
             if (!done) n_fail++;
         }
         __syncthreads();
-        // ---- scan: stats, histogram, dump ----
-        for (uint32_t base = 0; base < tsz; base += PC_THREADS) {
-            const uint32_t i = base + tid;
-            const uint64_t v = (i < tsz) ? s_key[i] : EMPTY;   // tables smaller than the CTA exist
-            const bool occ = v != EMPTY;
-            uint64_t r = 0, cnt = 0;
-            if (occ) {
-                r = ENT64 ? v : (v >> 32);
-                cnt = ENT64 ? (uint64_t)s_cnt[i] : (v & 0xffffffffull);
-                distinct++;
-                sumall += cnt;
-                if (o.histo) {
-                    const uint64_t b = cnt < (uint64_t)(o.histo_len - 1) ? cnt : (uint64_t)(o.histo_len - 1);
-                    if (b == 1) h1++;
-                    else if (b == 2) h2++;
-                    else if (b < 256) atomicAdd(&s_hist[b], 1u);
-                    else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
-                }
+        // ---- dump + clear ----
+        const uint32_t nocc = s_nocc;
+        if (nocc <= PC_LIST) {
+            for (uint32_t base = 0; base < nocc; base += PC_THREADS) {
+                const uint32_t i = base + tid;
+                visit(i < nocc ? (uint32_t)s_list[i] : 0u, i < nocc, p);
             }
-            const bool keep = occ && cnt >= o.lower;
-            if (keep) {
-                nge++;
-                sumge += cnt;
-            }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-            if (ballot) {
-                const int lane = tid & 31;
-                uint64_t wbase = 0;
-                if (lane == 0) wbase = atomicAdd((unsigned long long*)o.cursor, (unsigned long long)__popc(ballot));
-                wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                if (keep) {
-                    const uint64_t at = wbase + __popc(ballot & ((1u << lane) - 1));
-                    if (at < o.cap) {
-                        o.keys[at] = mx.inv((p << mx.rbits) | r);
-                        o.counts[at] = (uint32_t)cnt;
-                    }
-                }
-            }
+        } else {
+            for (uint32_t base = 0; base < PC_SLOTS; base += PC_THREADS) visit(base + tid, true, p);
         }
+        __syncthreads();
+        if (tid == 0) s_nocc = 0;
+        __syncthreads();
     }
     // ---- per-CTA totals ----
     __syncthreads();
@@ -641,7 +664,7 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
                                                                          cursor, buf, d_stats);
         SPK_LAUNCH_CHECK();
     }
-    const size_t smem = (size_t)PC_SLOTS * (ENT64 ? 12 : 8);
+    const size_t smem = (size_t)PC_SLOTS * (ENT64 ? 12 : 8) + (size_t)PC_LIST * 2;
     static bool attr_set[2] = {false, false};
     if (!attr_set[ENT64 ? 1 : 0]) {
         SPK_CUDA(cudaFuncSetAttribute(k_part_count<ENT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -17,17 +17,11 @@ torch.cuda.synchronize()
 for rep in range(3):
     t0 = time.perf_counter(); seq = engine.pack_fasta(d, n, trim=False); torch.cuda.synchronize(); t1 = time.perf_counter()
     print("pack: %.1f ms  %.2f Gbases/s" % ((t1 - t0) * 1e3, n / (t1 - t0) / 1e9))
-tab = engine.CountTable(n, k)
-print("layout", tab.layout, "table GB", tab.table_bytes / 1e9)
-for rep in range(3):
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
-    st = engine._stream()
-    _lib.call("spk_count_table_init", engine._p(tab.table), tab.table_bytes, k, tab.layout, st)
-    tab.stats.zero_()
-    e0.record()
-    _lib.call("spk_count_canonical", engine._p(seq.packed), engine._p(seq.valid), seq.n_bases, k, engine._p(tab.table), tab.table_bytes, tab.layout, engine._p(tab.stats), st)
-    e1.record()
-    _lib.call("spk_table_stats", engine._p(tab.table), tab.table_bytes, k, tab.layout, 3, engine._p(tab.stats[4:]), engine._p(tab.block_counts), None, 0, st)
-    e2.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print("count: %.1f ms  %.2f G kmers/s   scan %.1f ms  stats %s" % (ms, n / ms / 1e6, e1.elapsed_time(e2), tab.stats.tolist()))
+for mode in ("partitioned", "global"):
+    tab = engine.CountTable(n, k, 3, mode=mode)
+    for rep in range(3):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); dump = engine.count_packed(seq, k, 3, table=tab); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print("%s count+dump: %.1f ms  %.2f G kmers/s (distinct %d)" % (mode, ms, n / ms / 1e6, dump.n_distinct))
+    del tab
