@@ -258,9 +258,14 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_count_canonical", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm",
+                "kernel": "spk_pcount_canonical = k_part_pass<hist> + k_scatter_l1 + k_scatter_l2 + k_part_count "
+                          "(one call per chromosome)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_unit": BYTES_PER_KMER, "units_per_launch": res["n_kmers_local"] / max(len(mine), 1),
+                "bytes_per_unit": BYTES_PER_KMER, "bytes_per_unit_source": "SURVEY.md 8(d) sector model of a global table",
+                "design_bytes_per_unit": 16.75,
+                "units_per_launch": res["n_kmers_local"] / max(len(mine), 1),
                 "launches": stage_n.get("count", 0), "avg_launch_ms": stage_ms.get("count", 0.0) / max(stage_n.get("count", 1), 1)}
 
     # ---- end-to-end arm: host (pinned) FASTA bytes -> H2D inside the timed region -> results D2H ----
