@@ -97,6 +97,17 @@ int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint
                          uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
                          uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
                          uint32_t histo_len, void* stream);
+/* _ex: the same counter with (i) a caller-fixed number of partition bits `pbits` (0 = automatic;
+ * otherwise >= spk_pcount_pbits(n_bases, k), <= min(2k, 22)), so that every chromosome of a genome is split
+ * by the SAME function of the k-mer, and (ii) the partition index of the dump: the entries of partition p are
+ * contiguous, d_pindex (uint32[2 << pbits], optional) receives [2p] = index of the first entry, [2p+1] =
+ * number of entries.  This is what lets spk_pmatrix_filter merge the chromosomes partition by partition. */
+int spk_pcount_pbits(uint64_t n_bases, int k);
+size_t spk_pcount_workspace_bytes_ex(uint64_t n_bases, int k, int pbits);
+int spk_pcount_canonical_ex(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                            uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
+                            uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
+                            uint32_t histo_len, int pbits, uint32_t* d_pindex, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3  table scan: `jellyfish dump -c -L lower_count` + the dump parse of Jellyfish.py:90-98
@@ -164,6 +175,23 @@ int spk_filter_select(const uint64_t* d_row_keys, const uint8_t* d_flags, uint64
 int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint32_t* d_rows,
                     uint64_t m, int ncol, const uint64_t* d_lengths, double* d_out_norm,
                     uint64_t* d_out_tot, void* stream);
+/* spk_pmatrix_filter: JellyfishDumps.to_matrix + filter (Jellyfish.py:439-512,611-648) for dumps that carry a
+ * partition index with a common `pbits` (spk_pcount_canonical_ex): the union of partition p over the n
+ * chromosomes is merged in shared memory, every row goes through the same fp64 test as
+ * spk_filter_differential, and only rows with min_freq <= tot <= max_freq that pass the fold test are
+ * written: d_out_keys[i], d_out_tot[i], d_out_counts[i*n + c] (raw counts, arbitrary row order; rows beyond
+ * `cap` are dropped).  d_keys / d_counts / d_pindex: device arrays of n device pointers.  nparts/part: only
+ * partitions p % nparts == part (multi-GPU row sharding).  d_fold_tots (optional, uint64[fold_cap]): totals of
+ * all fold-passing rows (the histogram of Jellyfish.py:499-511).  d_counters (uint64[8], overwritten):
+ * [0] union rows (= len(d_mat)), [1] fold-passing rows, [2] kept rows, [3] table overflows (must be 0;
+ * otherwise use the plain path), [4] rows written, [5] fold totals written. */
+int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
+                       const uint32_t* const* d_pindex, int n, int pbits, uint32_t nparts, uint32_t part,
+                       const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets, const int32_t* d_grp_off,
+                       int n_groups, const int32_t* d_members, double min_fold, int baseline, int by_count,
+                       double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
+                       uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap, uint64_t* d_fold_tots,
+                       uint64_t fold_cap, uint64_t* d_counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).
@@ -212,6 +240,24 @@ int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_b
                  const uint32_t* d_filter, uint64_t filter_bits, int pack_vals, uint64_t bin_size,
                  uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
                  uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream);
+/* Bucketed quotient table — the shipped layout of the same map (Seqs.py:209-244 lookups), sized to stay
+ * L2-resident and to answer a position with ONE 16- or 32-byte load.  f = bijective mixer on the 2k-bit
+ * canonical word; bucket = top bucket_bits of f(u); a slot holds (remainder << sgbits) | subgenome id
+ * (uint16 or uint32 slots, all-ones = empty); a bucket = 7 entry slots + 1 overflow marker.  Keys whose
+ * bucket is full go to the open-addressed stash d_skeys/d_svals (as in spk_sig_table_build, pre-filled
+ * with 0xFF), probed only for marked buckets; membership is exact.
+ * spk_qtable_plan picks slot_bits (16|32) and bucket_bits for n_keys, k, S (SPK_EINVAL: no such layout,
+ * use spk_sig_table_build / spk_map_bins).  d_buckets: (8 << bucket_bits) slots pre-filled with 0xFF.
+ * spk_map_bins_q: same contract as spk_map_bins; d_hit_flags (optional) is uint8[(8 << bucket_bits) + sslots]. */
+int spk_qtable_plan(uint64_t n_keys, int k, int S, int* slot_bits, int* bucket_bits);
+int spk_qtable_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, int k, int S, void* d_buckets,
+                     int slot_bits, int bucket_bits, uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,
+                     int pack_vals, uint64_t* d_fail, void* stream);
+int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                   const void* d_buckets, int slot_bits, int bucket_bits, const uint64_t* d_skeys,
+                   const uint8_t* d_svals, uint64_t sslots, int pack_vals, int S, uint64_t bin_size,
+                   uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines, uint8_t* d_hit_flags,
+                   uint64_t* d_nhits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10  per-window Fisher exact test (right tail) + Benjamini-Hochberg

@@ -80,7 +80,7 @@ def _sig_table(d_kmers, k, sg_names):
     dev = engine._dev()
     dk = torch.from_numpy(np.ascontiguousarray(keys).view(np.int64).copy()).to(dev)
     dv = torch.from_numpy(np.ascontiguousarray(vals)).to(dev)
-    return engine.SigTable(dk, dv, k), k
+    return engine.SigTable(dk, dv, k, S=len(names)), k
 
 
 def _lines_of(seq_len, k, bin_size, chunk_size):

@@ -30,6 +30,12 @@ SIGNATURES = {
     "spk_count_canonical": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_sz, c_i, c_p, c_p]),
     "spk_pcount_workspace_bytes": (c_sz, [c_u64, c_i]),
     "spk_pcount_canonical": (c_i, [c_p, c_p, c_u64, c_i, c_u32, c_p, c_sz, c_p, c_p, c_u64, c_p, c_p, c_u32, c_p]),
+    "spk_pcount_pbits": (c_i, [c_u64, c_i]),
+    "spk_pcount_workspace_bytes_ex": (c_sz, [c_u64, c_i, c_i]),
+    "spk_pcount_canonical_ex": (c_i, [c_p, c_p, c_u64, c_i, c_u32, c_p, c_sz, c_p, c_p, c_u64, c_p, c_p, c_u32,
+                                      c_i, c_p, c_p]),
+    "spk_pmatrix_filter": (c_i, [c_p, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p, c_p, c_i, c_p, c_i, c_p, c_d, c_i, c_i,
+                                 c_d, c_d, c_d, c_p, c_p, c_p, c_u64, c_p, c_u64, c_p, c_p]),
     "spk_table_scan_blocks": (c_i, []),
     "spk_table_stats": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u32, c_p]),
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),
@@ -47,6 +53,10 @@ SIGNATURES = {
     "spk_map_num_lines": (c_u64, [c_u64, c_i, c_u64, c_u64]),
     "spk_map_bins": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p, c_u64, c_i, c_p, c_u64, c_i, c_u64, c_u64, c_p,
                            c_u64, c_p, c_p, c_p]),
+    "spk_qtable_plan": (c_i, [c_u64, c_i, c_i, c_p, c_p]),
+    "spk_qtable_build": (c_i, [c_p, c_p, c_u64, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_u64, c_i, c_p, c_p]),
+    "spk_map_bins_q": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_i, c_i, c_p, c_p, c_u64, c_i, c_i, c_u64, c_u64,
+                             c_p, c_u64, c_p, c_p, c_p]),
     "spk_fisher_right_tail": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_colsum_i64": (c_i, [c_p, c_u64, c_i, c_p, c_p]),
     "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),
@@ -72,7 +82,7 @@ SIGNATURES = {
 
 # functions returning an SPK_* status code
 _STATUS = {n for n, (r, _) in SIGNATURES.items() if r is c_i} - {
-    "spk_version", "spk_sm_count", "spk_count_layout", "spk_table_scan_blocks"}
+    "spk_version", "spk_sm_count", "spk_count_layout", "spk_table_scan_blocks", "spk_qtable_plan", "spk_pcount_pbits"}
 
 
 class SpkError(RuntimeError):

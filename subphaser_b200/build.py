@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-diag-suppress", "550",
 ]
 # files whose fp64 arithmetic must reproduce numpy / Python operation by operation
-NO_FMA = {"spk_matrix.cu", "spk_stats.cu", "spk_cluster.cu"}
+NO_FMA = {"spk_matrix.cu", "spk_pmatrix.cu", "spk_stats.cu", "spk_cluster.cu"}
 
 
 def _nvcc():

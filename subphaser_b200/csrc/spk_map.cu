@@ -7,6 +7,7 @@
 // canonical keys only (half the size, stays L2-resident).
 #include "spk_common.cuh"
 #include "spk_tile.cuh"
+#include "spk_mixer.cuh"
 
 namespace {
 
@@ -187,6 +188,269 @@ k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid
     if ((tid & 31) == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
 }
 
+// ---- bucketed quotient table ---------------------------------------------------------------------------
+// The per-position lookup is an L2 random-access problem (1.4e10 lookups for wheat), so the table is
+// made as small and as one-touch as possible: f = bijective mixer on the 2k-bit canonical word, bucket =
+// top `bbits` of f(u), and only the remainder (rbits = 2k - bbits bits) plus the subgenome id are stored:
+//   slot = (remainder << sgbits) | sg        all-ones = empty (the sg field of a real entry is < S)
+// A bucket is 8 slots = ONE 16-byte (u16 slots) or 32-byte (u32 slots) load: 7 entries + 1 overflow
+// marker.  Membership is exact (f is a bijection); the ~1 % of keys whose bucket is full live in a small
+// open-addressed stash that is probed only when the marker is set.  3.6e6 wheat k-mers: 16 MB, fully
+// L2-resident, one 16-B load per position instead of a filter load + dependent 8-B probes of a 58-MB table.
+constexpr int QT_SLOTS = 8;            // slots per bucket (7 entries + marker)
+
+struct QtArgs {
+    const void* buckets;
+    int slot_bits;            // 16 or 32
+    int bbits, sgbits;
+    Mixer mx;
+    const uint64_t* skeys;    // stash (open-addressed, full keys; value in the top byte or in svals)
+    const uint8_t* svals;
+    uint64_t sslots;
+    int pack_vals;
+};
+
+template <typename SlotT>
+__global__ void __launch_bounds__(256)
+k_qt_build(const uint64_t* __restrict__ keys, const uint8_t* __restrict__ vals, uint64_t n, SlotT* __restrict__ buckets,
+           int sgbits, Mixer mx, uint64_t* __restrict__ skeys, uint8_t* __restrict__ svals, uint64_t sslots,
+           int pack_vals, uint64_t* __restrict__ fail) {
+    const SlotT EMPTY = (SlotT)~(SlotT)0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = keys[i];
+        const uint64_t h = mx.fwd_light(key);
+        const uint64_t b = (mx.rbits >= 64) ? 0 : (h >> mx.rbits);
+        const uint64_t rem = (mx.rbits >= 64) ? h : (h & ((1ull << mx.rbits) - 1));
+        const SlotT word = (SlotT)((rem << sgbits) | (uint64_t)vals[i]);
+        SlotT* bk = buckets + b * QT_SLOTS;
+        bool done = false;
+        for (int s = 0; s < QT_SLOTS - 1 && !done; s++) {
+            const SlotT old = atomicCAS(bk + s, EMPTY, word);
+            if (old == EMPTY || (old >> sgbits) == (word >> sgbits)) done = true;
+        }
+        if (done) continue;
+        bk[QT_SLOTS - 1] = 0;            // marker: this bucket overflowed into the stash
+        const uint64_t sw = pack_vals ? (key | ((uint64_t)vals[i] << 56)) : key;
+        const uint64_t kmask = pack_vals ? 0x00ffffffffffffffull : ~0ull;
+        uint64_t slot = spk_slot_of(spk_hash64(key), sslots);
+        for (uint64_t p = 0; p < sslots; p++) {
+            const uint64_t old = atomicCAS((unsigned long long*)(skeys + slot), (unsigned long long)SPK_EMPTY_KEY,
+                                           (unsigned long long)sw);
+            if (old == SPK_EMPTY_KEY || (old & kmask) == key) {
+                if (!pack_vals) svals[slot] = vals[i];
+                done = true;
+                break;
+            }
+            slot++;
+            if (slot == sslots) slot = 0;
+        }
+        if (!done) atomicAdd((unsigned long long*)fail, 1ull);
+    }
+}
+
+// match a loaded bucket against q = remainder << sgbits: subgenome id or -1; `at` = slot of the hit,
+// `over` = the bucket overflowed into the stash at build time
+template <bool S16>
+struct QtBucket;
+template <>
+struct QtBucket<true> {
+    uint4 v;
+    __device__ __forceinline__ void load(const void* buckets, uint32_t b) {
+        v = __ldg(reinterpret_cast<const uint4*>(buckets) + b);
+    }
+    __device__ __forceinline__ void none() { v = make_uint4(~0u, ~0u, ~0u, ~0u); }
+    __device__ __forceinline__ int match(uint32_t q, uint32_t S, int& at, bool& over) const {
+        const uint32_t qq = q * 0x10001u;
+        const uint32_t w[4] = {v.x ^ qq, v.y ^ qq, v.z ^ qq, v.w ^ qq};
+        int sg = -1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+            if (lo < S) { sg = (int)lo; at = 2 * i; }
+            if (i < 3 && hi < S) { sg = (int)hi; at = 2 * i + 1; }
+        }
+        over = (v.w >> 16) != 0xffffu;
+        return sg;
+    }
+};
+template <>
+struct QtBucket<false> {
+    uint4 v0, v1;
+    __device__ __forceinline__ void load(const void* buckets, uint32_t b) {
+        v0 = __ldg(reinterpret_cast<const uint4*>(buckets) + 2 * (uint64_t)b);
+        v1 = __ldg(reinterpret_cast<const uint4*>(buckets) + 2 * (uint64_t)b + 1);
+    }
+    __device__ __forceinline__ void none() { v0 = v1 = make_uint4(~0u, ~0u, ~0u, ~0u); }
+    __device__ __forceinline__ int match(uint32_t q, uint32_t S, int& at, bool& over) const {
+        const uint32_t w[7] = {v0.x ^ q, v0.y ^ q, v0.z ^ q, v0.w ^ q, v1.x ^ q, v1.y ^ q, v1.z ^ q};
+        int sg = -1;
+#pragma unroll
+        for (int i = 0; i < 7; i++)
+            if (w[i] < S) { sg = (int)w[i]; at = i; }
+        over = v1.w != 0xffffffffu;
+        return sg;
+    }
+};
+
+// rare: the bucket overflowed at build time -> the key may be in the stash
+__device__ __noinline__ int qt_stash_lookup(const QtArgs& a, uint64_t key, uint64_t& sl_out) {
+    const uint64_t kmask = a.pack_vals ? 0x00ffffffffffffffull : ~0ull;
+    uint64_t sl = spk_slot_of(spk_hash64(key), a.sslots);
+    uint64_t c = __ldg(a.skeys + sl);
+    while (c != SPK_EMPTY_KEY && (c & kmask) != key) {
+        sl++;
+        if (sl == a.sslots) sl = 0;
+        c = __ldg(a.skeys + sl);
+    }
+    if (c == SPK_EMPTY_KEY) return -1;
+    sl_out = sl;
+    return a.pack_vals ? (int)(c >> 56) : (int)a.svals[sl];
+}
+
+template <bool S16>
+__global__ void __launch_bounds__(SPK_TILE_THREADS, 3)
+k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_bases, int k,
+             MapArgs a, QtArgs qa) {
+    __shared__ SpkTileSmem sm;
+    __shared__ uint32_t s_cnt[MP_SMEM_LINES * MP_MAX_S];
+    __shared__ uint64_t s_line0;
+    const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
+    const int tid = threadIdx.x;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    spk_tile_init(sm);
+    uint64_t n_hit = 0;
+    const int S = a.S;
+    const uint64_t rmask = (qa.mx.rbits >= 64) ? ~0ull : ((1ull << qa.mx.rbits) - 1);
+
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) spk_tile_issue(sm, packed, valid, tile, 0);
+
+    for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
+        const int buf = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) s_cnt[i] = 0;
+        if (tid == 0) s_line0 = line_of(tile * SPK_TILE_BASES, k, a.bin_size, a.chunk_size);
+        __syncthreads();  // buffer buf^1 free, counters cleared, line0 visible
+        if (tid == 0 && tile + gridDim.x < n_tiles)
+            spk_tile_issue(sm, packed, valid, tile + gridDim.x, buf ^ 1);
+        spk_mbar_wait(&sm.bar[buf], parity);
+
+        uint64_t key[SPK_KMERS_PER_THREAD];
+        uint32_t okmask;
+        spk_tile_kmers(sm, buf, kp, key, okmask);
+
+        // bucket lookups in batches of QB independent 16/32-byte loads (issued before any is consumed)
+        uint32_t hm = 0;              // bit j: position j hit
+        uint64_t sgp[2] = {0, 0};     // subgenome id of hit j, 8 bits each
+        constexpr int QB = S16 ? 8 : 4;
+#pragma unroll
+        for (int j0 = 0; j0 < SPK_KMERS_PER_THREAD; j0 += QB) {
+            QtBucket<S16> bk[QB];
+            uint32_t qv[QB];
+#pragma unroll
+            for (int jj = 0; jj < QB; jj++) {
+                const int j = j0 + jj;
+                const uint64_t h = qa.mx.fwd_light(key[j]);
+                qv[jj] = (uint32_t)((h & rmask) << qa.sgbits);
+                if ((okmask >> j) & 1u) bk[jj].load(qa.buckets, (qa.mx.rbits >= 64) ? 0u : (uint32_t)(h >> qa.mx.rbits));
+                else bk[jj].none();
+            }
+#pragma unroll
+            for (int jj = 0; jj < QB; jj++) {
+                const int j = j0 + jj;
+                int at = 0;
+                bool over;
+                int sg = bk[jj].match(qv[jj], (uint32_t)S, at, over);
+                const bool okj = (okmask >> j) & 1u;
+                if (okj && ((sg < 0 && over) || (sg >= 0 && a.hit_flags))) {   // rare / logging-only paths
+                    uint64_t where;
+                    if (sg < 0) {
+                        uint64_t sl = 0;
+                        sg = qt_stash_lookup(qa, key[j], sl);
+                        where = ((uint64_t)QT_SLOTS << qa.bbits) + sl;
+                    } else {
+                        const uint64_t h = qa.mx.fwd_light(key[j]);
+                        where = ((qa.mx.rbits >= 64) ? 0ull : (h >> qa.mx.rbits)) * QT_SLOTS + at;
+                    }
+                    if (sg >= 0 && a.hit_flags && !a.hit_flags[where]) a.hit_flags[where] = 1;
+                }
+                if (okj && sg >= 0) {
+                    hm |= 1u << j;
+                    sgp[j >> 3] |= (uint64_t)sg << (8 * (j & 7));
+                }
+            }
+        }
+        n_hit += __popc(hm);
+
+        // line bookkeeping for this thread's 16 consecutive positions
+        const uint64_t pos0 = tile * SPK_TILE_BASES + (uint64_t)tid * SPK_KMERS_PER_THREAD;
+        uint64_t bin = pos0 / a.bin_size;
+        uint64_t brem = pos0 - bin * a.bin_size;
+        uint64_t chk = 0, crem = 0;
+        if (a.chunk_size) {
+            chk = (pos0 + (uint64_t)(k - 1)) / a.chunk_size;
+            crem = (pos0 + (uint64_t)(k - 1)) - chk * a.chunk_size;
+        }
+        const uint64_t line0 = s_line0;
+        // fast path: the whole warp (512 positions) falls on one line -> warp-reduce the per-subgenome
+        // hit counts and let one lane add them (the slow path would serialise ~hits same-address atomics)
+        const bool one_line = (brem + SPK_KMERS_PER_THREAD <= a.bin_size) &&
+                              (!a.chunk_size || crem + SPK_KMERS_PER_THREAD <= a.chunk_size);
+        const uint64_t rel_t = bin + chk - line0;
+        const uint32_t rel32 = rel_t < 0xffffffffull ? (uint32_t)rel_t : 0xffffffffu;
+        const uint32_t rel_first = __shfl_sync(0xffffffffu, rel32, 0);
+        const bool warp_one_line = __all_sync(0xffffffffu, one_line && rel32 == rel_first) && S <= 4;
+        if (warp_one_line) {
+            uint32_t c01 = 0, c23 = 0;   // four 16-bit counters (<= 16 per thread, <= 512 per warp)
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
+                const uint32_t hit = (hm >> j) & 1u;
+                const uint32_t inc = hit << ((sg & 1u) * 16);
+                if (sg & 2u) c23 += inc;
+                else c01 += inc;
+            }
+            c01 = __reduce_add_sync(0xffffffffu, c01);
+            c23 = __reduce_add_sync(0xffffffffu, c23);
+            if ((tid & 31) == 0) {
+                const uint32_t c[4] = {c01 & 0xffffu, c01 >> 16, c23 & 0xffffu, c23 >> 16};
+                const uint64_t line = line0 + rel_first;
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                    if (c[s] && s < S) {
+                        if (rel_first < MP_SMEM_LINES) atomicAdd(&s_cnt[rel_first * MP_MAX_S + s], c[s]);
+                        else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + s], c[s]);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                if ((hm >> j) & 1u) {
+                    const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
+                    const uint64_t line = bin + chk;
+                    const uint64_t rel = line - line0;
+                    if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
+                    else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
+                }
+                if (++brem == a.bin_size) { brem = 0; bin++; }
+                if (a.chunk_size && ++crem == a.chunk_size) { crem = 0; chk++; }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) {
+            const uint32_t c = s_cnt[i];
+            if (c) {
+                const uint64_t line = line0 + i / MP_MAX_S;
+                const int sg = i % MP_MAX_S;
+                if (line < a.n_lines && sg < a.S) atomicAdd(&a.line_counts[line * a.S + sg], c);
+            }
+        }
+    }
+    n_hit = spk_warp_sum_u64(n_hit);
+    if ((tid & 31) == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
+}
+
 // Circos._bed_density(stack=True) (Circos.py:737-741): window row += bin row
 __global__ void __launch_bounds__(256)
 k_stack_windows(const int64_t* __restrict__ line_counts, const uint32_t* __restrict__ line_window,
@@ -299,6 +563,93 @@ extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, u
               d_line_counts, n_lines, d_hit_flags, d_nhits};
     k_map_bins<<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+// ---- bucketed quotient table: plan / build / map ---------------------------------------------------------
+static int qt_sgbits(int S) {
+    int b = 1;
+    while ((1 << b) < S + 1) b++;
+    return b;
+}
+
+extern "C" int spk_qtable_plan(uint64_t n_keys, int k, int S, int* slot_bits, int* bucket_bits) {
+    SPK_CHECK_ARG(slot_bits && bucket_bits, "null pointer");
+    SPK_CHECK_ARG(k >= 1 && k <= 32 && S >= 1 && S <= MP_MAX_S, "bad k or S");
+    const int sgbits = qt_sgbits(S);
+    int bn = 4;                                        // mean occupancy <= 3.5 of 7 entry slots
+    while (bn < 40 && (double)n_keys / (double)(1ull << bn) > 3.5) bn++;
+    if (bn > 2 * k) bn = 2 * k;
+    int b16 = bn;
+    if (2 * k + sgbits - 16 > b16) b16 = 2 * k + sgbits - 16;
+    if (b16 <= 2 * k && b16 <= 21) {                   // <= 32 MB
+        *slot_bits = 16;
+        *bucket_bits = b16;
+        return SPK_OK;
+    }
+    int b32 = bn;
+    if (2 * k + sgbits - 32 > b32) b32 = 2 * k + sgbits - 32;
+    if (b32 <= 2 * k && b32 <= 24) {                   // <= 512 MB
+        *slot_bits = 32;
+        *bucket_bits = b32;
+        return SPK_OK;
+    }
+    spk_set_error("spk_qtable_plan: no bucketed layout for k=%d, S=%d, %llu keys", k, S, (unsigned long long)n_keys);
+    return SPK_EINVAL;
+}
+
+extern "C" int spk_qtable_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, int k, int S,
+                                void* d_buckets, int slot_bits, int bucket_bits, uint64_t* d_skeys,
+                                uint8_t* d_svals, uint64_t sslots, int pack_vals, uint64_t* d_fail, void* stream) {
+    SPK_CHECK_ARG(d_buckets && d_skeys && d_svals && d_fail, "null pointer");
+    SPK_CHECK_ARG(slot_bits == 16 || slot_bits == 32, "slot_bits must be 16 or 32");
+    SPK_CHECK_ARG(k >= 1 && k <= 32 && bucket_bits >= 0 && bucket_bits <= 2 * k && bucket_bits <= 30, "bad geometry");
+    SPK_CHECK_ARG(2 * k - bucket_bits + qt_sgbits(S) <= slot_bits, "remainder does not fit the slot");
+    SPK_CHECK_ARG(sslots >= 2, "stash too small");
+    SPK_CHECK_ARG(!pack_vals || k <= 28, "packed values need k <= 28");
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_keys && d_vals, "null keys/vals");
+    const Mixer mx = spk_make_mixer(k, bucket_bits);
+    const uint64_t blocks = (n + 255) / 256;
+    const unsigned grid = (unsigned)min(blocks, (uint64_t)spk_num_sms() * 16);
+    if (slot_bits == 16)
+        k_qt_build<unsigned short><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            d_keys, d_vals, n, (unsigned short*)d_buckets, qt_sgbits(S), mx, d_skeys, d_svals, sslots, pack_vals, d_fail);
+    else
+        k_qt_build<unsigned int><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            d_keys, d_vals, n, (unsigned int*)d_buckets, qt_sgbits(S), mx, d_skeys, d_svals, sslots, pack_vals, d_fail);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                              const void* d_buckets, int slot_bits, int bucket_bits, const uint64_t* d_skeys,
+                              const uint8_t* d_svals, uint64_t sslots, int pack_vals, int S, uint64_t bin_size,
+                              uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
+                              uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
+    SPK_CHECK_ARG(d_packed && d_valid && d_buckets && d_skeys && d_svals && d_line_counts, "null pointer");
+    SPK_CHECK_ARG(slot_bits == 16 || slot_bits == 32, "slot_bits must be 16 or 32");
+    SPK_CHECK_ARG(k >= 1 && k <= 32 && bucket_bits >= 0 && bucket_bits <= 2 * k && bucket_bits <= 30, "bad geometry");
+    SPK_CHECK_ARG(S >= 1 && S <= MP_MAX_S, "S must be in [1, 32]");
+    SPK_CHECK_ARG(2 * k - bucket_bits + qt_sgbits(S) <= slot_bits, "remainder does not fit the slot");
+    SPK_CHECK_ARG(bin_size >= 1, "bin_size must be >= 1");
+    SPK_CHECK_ARG(sslots >= 2, "stash too small");
+    SPK_CHECK_ARG(!pack_vals || k <= 28, "packed values need k <= 28");
+    SPK_CHECK_ARG(n_lines >= spk_map_num_lines(n_bases, k, bin_size, chunk_size), "n_lines too small");
+    if (n_bases < (uint64_t)k) return SPK_OK;
+    const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
+    const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
+    MapArgs a{d_skeys, d_svals, sslots, nullptr, 0, pack_vals, S, bin_size, chunk_size,
+              d_line_counts, n_lines, d_hit_flags, d_nhits};
+    QtArgs qa{d_buckets, slot_bits, bucket_bits, qt_sgbits(S), spk_make_mixer(k, bucket_bits), d_skeys, d_svals,
+              sslots, pack_vals};
+    if (slot_bits == 16)
+        k_map_bins_q<true><<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
+            (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a, qa);
+    else
+        k_map_bins_q<false><<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
+            (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a, qa);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

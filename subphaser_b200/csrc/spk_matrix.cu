@@ -5,11 +5,11 @@
 // 611-648).  The fp64 arithmetic of _filter_kmer is reproduced operation by operation (this file is
 // compiled with -fmad=false): int sums, one IEEE division per group, `max/(min+1e-20) >= min_fold`.
 #include "spk_common.cuh"
+#include "spk_filter.cuh"
 
 namespace {
 
 constexpr int MX_THREADS = 256;
-constexpr int MX_MAX_GROUPS_PER_SET = 32;
 
 __global__ void __launch_bounds__(MX_THREADS)
 k_union_insert(const uint64_t* __restrict__ keys, uint64_t n, uint64_t* __restrict__ ukeys,
@@ -73,19 +73,6 @@ k_matrix_fill(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ co
     }
 }
 
-struct FilterCfg {
-    const int32_t* set_off;
-    const int32_t* grp_off;
-    const int32_t* members;
-    int n_sets;
-    double min_fold;
-    int baseline;
-    int by_count;
-    double ratio;
-    double min_freq;
-    double max_freq;
-};
-
 // One thread per matrix row.  Mirrors _filter_kmer (Jellyfish.py:611-648) with outfig set.
 __global__ void __launch_bounds__(MX_THREADS)
 k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
@@ -94,47 +81,8 @@ k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
     uint64_t n_fold = 0, n_keep = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
          r += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t* row = matrix + r * ncol;
-        uint64_t tot = 0;
-        for (int c = 0; c < ncol; c++) tot += row[c];
-        int include = 0, all = 0;
-        for (int s = 0; s < cfg.n_sets; s++) {
-            const int g0 = cfg.set_off[s], g1 = cfg.set_off[s + 1];
-            const int ng = g1 - g0;
-            if (ng < 2) continue;  // singleton sets are ignored (Jellyfish.py:622-623)
-            all++;
-            double f[MX_MAX_GROUPS_PER_SET];
-            for (int g = g0; g < g1; g++) {
-                uint64_t cs = 0, ls = 0;
-                for (int m = cfg.grp_off[g]; m < cfg.grp_off[g + 1]; m++) {
-                    const int c = cfg.members[m];
-                    cs += row[c];
-                    ls += lengths[c];
-                }
-                // count/lens or sum(count)/sum(lens); by_count: the raw (summed) count
-                f[g - g0] = cfg.by_count ? (double)cs : (double)cs / (double)ls;
-            }
-            // sorted(freqs, reverse=1): insertion sort, descending
-            for (int i = 1; i < ng; i++) {
-                const double v = f[i];
-                int j = i - 1;
-                while (j >= 0 && f[j] < v) {
-                    f[j + 1] = f[j];
-                    j--;
-                }
-                f[j + 1] = v;
-            }
-            const double fmax = f[0];
-            const double fmin = f[cfg.baseline >= 0 ? cfg.baseline : ng + cfg.baseline];
-            if (1.0 * fmax / (fmin + 1e-20) >= cfg.min_fold) include++;
-        }
-        uint8_t fl = 0;
-        const double rr = 1.0 * (double)include / (double)all;
-        if (!(rr < cfg.ratio)) {
-            fl |= 1;
-            const double t = (double)tot;
-            if (!(t < cfg.min_freq || t > cfg.max_freq)) fl |= 2;
-        }
+        uint64_t tot;
+        const uint8_t fl = spk_filter_row(matrix + r * ncol, ncol, lengths, cfg, tot);
         flags[r] = fl;
         tot_out[r] = tot;
         n_fold += fl & 1;

@@ -112,16 +112,25 @@ __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t*
     }
 }
 
-// single-CTA exclusive max-scan (int64) / sum-scan (u32 -> u64); tile counts are small (bytes/4096)
+// single-CTA exclusive max-scan (int64) / sum-scan (u32 -> u64) over the per-tile values (bytes/4096 of
+// them); 8 consecutive elements per thread per round keep the number of latency-bound rounds small
+constexpr int SCAN_PER = 8;
+
 __global__ void __launch_bounds__(1024) k_scan_max_excl(int64_t* data, size_t n) {
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry;
     if (threadIdx.x == 0) s_carry = -1;
     __syncthreads();
-    for (size_t base = 0; base < n; base += 1024) {
-        const size_t i = base + threadIdx.x;
-        const int64_t v = (i < n) ? data[i] : -1;
-        int64_t incl = v;
+    for (size_t base = 0; base < n; base += 1024 * SCAN_PER) {
+        const size_t i0 = base + (size_t)threadIdx.x * SCAN_PER;
+        int64_t loc[SCAN_PER];
+        int64_t mine = -1;
+#pragma unroll
+        for (int q = 0; q < SCAN_PER; q++) {
+            loc[q] = (i0 + q < n) ? data[i0 + q] : -1;
+            mine = max(mine, loc[q]);
+        }
+        int64_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -133,8 +142,12 @@ __global__ void __launch_bounds__(1024) k_scan_max_excl(int64_t* data, size_t n)
         for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix = max(prefix, s_warp[w]);
         int64_t excl = __shfl_up_sync(0xffffffffu, incl, 1);
         if ((threadIdx.x & 31) == 0) excl = -1;
-        excl = max(excl, prefix);
-        if (i < n) data[i] = excl;
+        int64_t run = max(excl, prefix);
+#pragma unroll
+        for (int q = 0; q < SCAN_PER; q++) {
+            if (i0 + q < n) data[i0 + q] = run;
+            run = max(run, loc[q]);
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = max(prefix, incl);
         __syncthreads();
@@ -146,10 +159,16 @@ __global__ void __launch_bounds__(1024) k_scan_sum_excl(const uint32_t* in, uint
     __shared__ uint64_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (size_t base = 0; base < n; base += 1024) {
-        const size_t i = base + threadIdx.x;
-        const uint64_t v = (i < n) ? in[i] : 0;
-        uint64_t incl = v;
+    for (size_t base = 0; base < n; base += 1024 * SCAN_PER) {
+        const size_t i0 = base + (size_t)threadIdx.x * SCAN_PER;
+        uint32_t loc[SCAN_PER];
+        uint64_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < SCAN_PER; q++) {
+            loc[q] = (i0 + q < n) ? in[i0 + q] : 0u;
+            mine += loc[q];
+        }
+        uint64_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint64_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -159,7 +178,12 @@ __global__ void __launch_bounds__(1024) k_scan_sum_excl(const uint32_t* in, uint
         __syncthreads();
         uint64_t prefix = s_carry;
         for (int w = 0; w < (int)(threadIdx.x >> 5); w++) prefix += s_warp[w];
-        if (i < n) out[i] = prefix + incl - v;
+        uint64_t run = prefix + incl - mine;
+#pragma unroll
+        for (int q = 0; q < SCAN_PER; q++) {
+            if (i0 + q < n) out[i0 + q] = run;
+            run += loc[q];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = prefix + incl;
         __syncthreads();
@@ -203,6 +227,48 @@ __device__ __forceinline__ void classify16(const uint4& v, size_t pos, size_t nb
         }
         kept++;
     }
+}
+
+// ---- SWAR fast path --------------------------------------------------------------------------------------
+// 0x80 in every byte of y that is zero (exact: no borrow between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) {
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c) { return zero_bytes(w ^ (c * 0x01010101u)); }
+
+// Same result as classify16 for 16 in-range bytes that are not inside a header line and contain no '>':
+// four bytes per 32-bit operation instead of a 16-step byte loop (the byte loop made K1 ALU-bound).
+// Returns false when the bytes need the general path.
+__device__ __forceinline__ bool classify16_fast(const uint4& v, uint32_t& bits, uint32_t& vbits, int& kept,
+                                                int& valid) {
+    uint32_t skm = 0, gt = 0;
+    bits = vbits = 0;
+#pragma unroll
+    for (int wi = 0; wi < 4; wi++) {
+        const uint32_t w = word_of(v, wi);
+        gt |= eq_bytes(w, '>');
+        const uint32_t sk = eq_bytes(w, '\n') | eq_bytes(w, '\r');
+        const uint32_t u = w & 0xdfdfdfdfu;                                       // upper-case
+        const uint32_t va = eq_bytes(u, 'A') | eq_bytes(u, 'C') | eq_bytes(u, 'G') | eq_bytes(u, 'T');
+        const uint32_t vb = va >> 7;                                              // 0/1 per byte
+        const uint32_t x = (w >> 1) & 0x03030303u;                                // A0 C1 G3 T2
+        const uint32_t code = (x ^ ((x >> 1) & 0x01010101u)) & (vb | (vb << 1));  // A0 C1 G2 T3, 0 if invalid
+        bits |= ((code * 0x01041040u) >> 24) << (8 * wi);                         // 4 x 2 bits
+        vbits |= (((vb * 0x01020408u) >> 24) & 0xfu) << (4 * wi);                 // 4 x 1 bit
+        skm |= ((((sk >> 7) * 0x01020408u) >> 24) & 0xfu) << (4 * wi);
+    }
+    if (gt) return false;
+    valid = __popc(vbits);
+    kept = 16 - __popc(skm);
+    while (skm) {                                   // drop the skipped bytes ('\n', '\r'), highest first
+        const int q = 31 - __clz(skm);
+        skm &= ~(1u << q);
+        const uint32_t lo2 = bits & ((1u << (2 * q)) - 1u), lo1 = vbits & ((1u << q) - 1u);
+        const uint32_t hi2 = (q == 15) ? 0u : (bits >> (2 * q + 2)), hi1 = vbits >> (q + 1);
+        bits = lo2 | (hi2 << (2 * q));
+        vbits = lo1 | (hi1 << q);
+    }
+    return true;
 }
 
 // exclusive max-scan of per-thread last-newline offsets (int, tile-local; -1 none) inside a CTA
@@ -255,6 +321,8 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
     __shared__ int s_wi[PK_THREADS / 32];
     __shared__ uint32_t s_w32[PK_THREADS / 32];
     __shared__ int s_carry_hdr;
+    __shared__ uint32_t s_pk[EMIT ? PK_TILE / 16 + 4 : 1];
+    __shared__ uint32_t s_vd[EMIT ? PK_TILE / 32 + 2 : 1];
     uint64_t my_valid = 0, my_hdr = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t tbase = tile * PK_TILE;
@@ -287,8 +355,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
             hdr = bol ? false : (((size_t)(carry + 1) >= tbase) ? (in[carry + 1] == '>') : (s_carry_hdr != 0));
         }
         uint32_t bits, vbits;
-        int kept, nvalid, headers;
-        classify16(v, pos, nbytes, bol, hdr, bits, vbits, kept, nvalid, headers);
+        int kept, nvalid, headers = 0;
+        if (!(pos + 16 <= nbytes && !hdr && classify16_fast(v, bits, vbits, kept, nvalid)))
+            classify16(v, pos, nbytes, bol, hdr, bits, vbits, kept, nvalid, headers);
         if (!EMIT) {
             uint32_t tot;
             block_excl_sum((uint32_t)kept, s_w32, &tot);
@@ -296,22 +365,44 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
             my_valid += nvalid;
             my_hdr += headers;
         } else {
+            // Stage the tile's output words in shared memory (OR of <= 4 words per thread), then write whole
+            // words with coalesced plain stores; only the two words a tile may share with its neighbours
+            // go through a global atomicOr (the outputs are zero-initialised).
             const uint32_t off = block_excl_sum((uint32_t)kept, s_w32, nullptr);
+            const uint64_t o0 = tile_off[tile];
+            const uint32_t T = (uint32_t)(tile_off[tile + 1] - o0);      // kept bases of this tile
+            const uint32_t lb = (uint32_t)(o0 & 31);                     // local bit origin: valid word o0/32
+            for (int i = threadIdx.x; i < PK_TILE / 16 + 4; i += PK_THREADS) s_pk[i] = 0;
+            for (int i = threadIdx.x; i < PK_TILE / 32 + 2; i += PK_THREADS) s_vd[i] = 0;
+            __syncthreads();
             if (kept) {
-                const uint64_t o = tile_off[tile] + off;
-                // 2-bit codes: up to 32 payload bits starting at bit 2*(o%16) of word o/16
-                const uint64_t w = o >> 4;
-                const int sh = 2 * (int)(o & 15);
+                const uint32_t l = lb + off;
+                const int sh = 2 * (int)(l & 15);
                 if (bits) {
-                    if (bits << sh) atomicOr(&packed[w], bits << sh);
-                    if (sh && (bits >> (32 - sh))) atomicOr(&packed[w + 1], bits >> (32 - sh));
+                    if (bits << sh) atomicOr(&s_pk[l >> 4], bits << sh);
+                    if (sh && (bits >> (32 - sh))) atomicOr(&s_pk[(l >> 4) + 1], bits >> (32 - sh));
                 }
-                // validity: up to 16 bits starting at bit o%32 of word o/32
                 if (vbits) {
-                    const uint64_t vw = o >> 5;
-                    const int vs = (int)(o & 31);
-                    atomicOr(&valid_out[vw], vbits << vs);
-                    if (vs > 16 && (vbits >> (32 - vs))) atomicOr(&valid_out[vw + 1], vbits >> (32 - vs));
+                    const int vs = (int)(l & 31);
+                    atomicOr(&s_vd[l >> 5], vbits << vs);
+                    if (vs > 16 && (vbits >> (32 - vs))) atomicOr(&s_vd[(l >> 5) + 1], vbits >> (32 - vs));
+                }
+            }
+            __syncthreads();
+            if (T) {
+                const uint32_t npw = ((lb + T - 1) >> 4) + 1;            // packed words touched (from word 2*(o0/32))
+                const uint32_t nvw = ((lb + T - 1) >> 5) + 1;
+                uint32_t* gp = packed + (o0 >> 5) * 2;
+                uint32_t* gv = valid_out + (o0 >> 5);
+                for (uint32_t i = threadIdx.x; i < npw; i += PK_THREADS) {
+                    const uint32_t wv = s_pk[i];
+                    if (i < 2 || i + 1 >= npw) { if (wv) atomicOr(&gp[i], wv); }
+                    else gp[i] = wv;
+                }
+                for (uint32_t i = threadIdx.x; i < nvw; i += PK_THREADS) {
+                    const uint32_t wv = s_vd[i];
+                    if (i == 0 || i + 1 == nvw) { if (wv) atomicOr(&gv[i], wv); }
+                    else gv[i] = wv;
                 }
             }
         }

@@ -18,50 +18,17 @@
 // remainder r = the rest; the dump applies f^-1, so keys are exact and the result is bit-identical to
 // the v1 kernel / the jellyfish semantics (only the dump ORDER differs, which is arbitrary anyway).
 #include <stdlib.h>
+#include <type_traits>
 #include "spk_common.cuh"
 #include "spk_tile.cuh"
+#include "spk_mixer.cuh"
 
 namespace {
 
 constexpr int PC_SLOTS = 8192;          // smem table slots per CTA (64 KB as u64, 96 KB for wide keys)
-constexpr int PC_TARGET = 3072;         // planned mean entries per partition (all distinct -> load 0.375)
+constexpr int PC_TARGET = 4096;         // planned max mean entries per partition (all distinct -> load 0.5)
 constexpr int PC_MAX_PBITS = 22;
 constexpr int PC_THREADS = 256;
-constexpr uint64_t PC_C1 = 0xff51afd7ed558ccdULL;
-constexpr uint64_t PC_C2 = 0xc4ceb9fe1a85ec53ULL;
-
-constexpr uint64_t inv64(uint64_t a) {  // multiplicative inverse of odd a modulo 2^64 (Newton)
-    uint64_t x = a;
-    for (int i = 0; i < 6; i++) x *= 2 - a * x;
-    return x;
-}
-constexpr uint64_t PC_C1_INV = inv64(PC_C1);
-constexpr uint64_t PC_C2_INV = inv64(PC_C2);
-static_assert(PC_C1 * PC_C1_INV == 1ull && PC_C2 * PC_C2_INV == 1ull, "inverse constants");
-
-struct Mixer {
-    uint64_t mask;  // 2k low bits
-    int s;          // xorshift distance k = (2k)/2: x ^= x >> s is an involution on 2k-bit words
-    int rbits;      // remainder bits = 2k - pbits
-    __host__ __device__ uint64_t fwd(uint64_t u) const {
-        uint64_t x = u;
-        x ^= x >> s;
-        x = (x * PC_C1) & mask;
-        x ^= x >> s;
-        x = (x * PC_C2) & mask;
-        x ^= x >> s;
-        return x;
-    }
-    __host__ __device__ uint64_t inv(uint64_t x) const {
-        x ^= x >> s;
-        x = (x * PC_C2_INV) & mask;
-        x ^= x >> s;
-        x = (x * PC_C1_INV) & mask;
-        x ^= x >> s;
-        return x;
-    }
-};
-
 struct PcPlan {
     int k, pbits, ent64;
     uint64_t P;
@@ -77,13 +44,24 @@ constexpr int SC_MAX_BINS = 2048;
 
 inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
-int make_plan(uint64_t n_bases, int k, PcPlan* pl) {
-    if (k < 1 || k > 32) return SPK_EINVAL;
-    if (n_bases >= 0xffffffffull) return SPK_EINVAL;  // 32-bit partition offsets
-    pl->k = k;
+int auto_pbits(uint64_t n_bases, int k) {
     int pbits = 2;
     while (pbits < PC_MAX_PBITS && (n_bases >> pbits) > (uint64_t)PC_TARGET) pbits++;
     if (pbits > 2 * k) pbits = 2 * k;  // tiny k: at most 4^k distinct words
+    return pbits;
+}
+
+// pbits_req > 0: the caller fixes the number of partition bits (>= the automatic choice, so that partitions
+// only get smaller) — every chromosome of a genome is then split by the same function of the k-mer.
+int make_plan(uint64_t n_bases, int k, int pbits_req, PcPlan* pl) {
+    if (k < 1 || k > 32) return SPK_EINVAL;
+    if (n_bases >= 0xffffffffull) return SPK_EINVAL;  // 32-bit partition offsets
+    pl->k = k;
+    int pbits = auto_pbits(n_bases, k);
+    if (pbits_req > 0) {
+        if (pbits_req < pbits || pbits_req > PC_MAX_PBITS || pbits_req > 2 * k) return SPK_EINVAL;
+        pbits = pbits_req;
+    }
     pl->pbits = pbits;
     pl->P = 1ull << pbits;
     pl->ent64 = (2 * k - pbits > 32) ? 1 : 0;
@@ -295,9 +273,66 @@ __device__ __forceinline__ void bins_reserve(ScatterSmem& s, int nb, uint32_t* _
     __syncthreads();
 }
 
+// Bucket-level histogram (2^b1 bins, privatised in shared memory) — all the two-level scatter needs before
+// level 1 can reserve its runs.  The P-bin histogram of the final partitions is accumulated by level 1
+// itself (its REDs to L2 hide under that kernel's shared-memory work), so the separate full-histogram
+// traversal (L2-atomic bound, as long as level 1 itself) is gone.
+__global__ void __launch_bounds__(SPK_TILE_THREADS, 4)
+k_hist1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k, Mixer mx,
+        int b1, uint32_t* __restrict__ bsize, uint64_t* __restrict__ stats) {
+    __shared__ SpkTileSmem sm;
+    __shared__ uint32_t s_bins[SC_MAX_BINS];
+    const int tid = threadIdx.x;
+    const int nb = 1 << b1;
+    const int sh1 = 2 * k - b1;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    for (int b = tid; b < nb; b += SPK_TILE_THREADS) s_bins[b] = 0;
+    spk_tile_init(sm);
+    uint64_t n_valid = 0;
+    uint64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) spk_tile_issue(sm, packed, valid, tile, 0);
+    for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
+        const int b = it & 1;
+        __syncthreads();
+        if (tid == 0 && tile + gridDim.x < n_tiles) spk_tile_issue(sm, packed, valid, tile + gridDim.x, b ^ 1);
+        spk_mbar_wait(&sm.bar[b], (it >> 1) & 1);
+        uint64_t key[SPK_KMERS_PER_THREAD];
+        uint32_t okmask;
+        spk_tile_kmers(sm, b, kp, key, okmask);
+        n_valid += __popc(okmask);
+#pragma unroll
+        for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+            if ((okmask >> j) & 1u) atomicAdd(&s_bins[mx.fwd(key[j]) >> sh1], 1u);
+    }
+    __syncthreads();
+    for (int b = tid; b < nb; b += SPK_TILE_THREADS)
+        if (s_bins[b]) atomicAdd(&bsize[b], s_bins[b]);
+    n_valid = spk_warp_sum_u64(n_valid);
+    if ((tid & 31) == 0 && n_valid) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_valid);
+}
+
+// exclusive scan of the <= SC_MAX_BINS bucket sizes -> level-1 run cursors (single CTA)
+__global__ void __launch_bounds__(1024) k_bucket_scan(const uint32_t* __restrict__ bsize, int nb,
+                                                       uint32_t* __restrict__ cur1) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        const int b = base + threadIdx.x;
+        uint32_t tot;
+        const uint32_t excl = block_scan_1024(b < nb ? bsize[b] : 0u, s_warp, &tot);
+        if (b < nb) cur1[b] = s_carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(SPK_TILE_THREADS, 2)
 k_scatter_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k,
-             Mixer mx, int b1, uint32_t* __restrict__ cur1, uint32_t* __restrict__ buf1) {
+             Mixer mx, int b1, uint32_t* __restrict__ cur1, uint32_t* __restrict__ buf1,
+             uint32_t* __restrict__ psize) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr int PKW = (SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) / 4;   // 1028
     constexpr int VDW = (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) / 4;     // 516
@@ -353,6 +388,7 @@ k_scatter_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                 if ((okmask >> j) & 1u) {
                     const uint64_t h = mx.fwd(key[j]);
                     const uint32_t b = (uint32_t)(h >> sh1);
+                    atomicAdd(&psize[h >> mx.rbits], 1u);          // final-partition histogram (RED to L2)
                     const uint32_t p = atomicAdd(&sc.cnt[b], 1u);
                     sc.sorted[p] = (uint32_t)(h & m1);
                     sc.bin[p] = (uint16_t)b;
@@ -421,16 +457,35 @@ k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pst
         for (int b = tid; b < nb; b += SPK_TILE_THREADS) sc.cnt[b] = 0;
         __syncthreads();
         const uint32_t bucket = s_unit[0], beg = s_unit[1], end = s_unit[2];
-        for (uint32_t i = beg + tid; i < end; i += SPK_TILE_THREADS) atomicAdd(&sc.cnt[buf1[i] >> rbits], 1u);
+        for (uint32_t base = beg; base < end; base += 8 * SPK_TILE_THREADS) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t i = base + u * SPK_TILE_THREADS + tid;
+                v[u] = i < end ? __ldg(buf1 + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (base + u * SPK_TILE_THREADS + tid < end) atomicAdd(&sc.cnt[v[u] >> rbits], 1u);
+        }
         __syncthreads();
         const uint32_t n_e = bins_scan(sc.cnt, sc.off, nb, s_warp);
         bins_reserve(sc, nb, cursor + ((uint64_t)bucket << b2));
-        for (uint32_t i = beg + tid; i < end; i += SPK_TILE_THREADS) {
-            const uint32_t v = buf1[i];
-            const uint32_t sub = v >> rbits;
-            const uint32_t p = atomicAdd(&sc.cnt[sub], 1u);
-            sc.sorted[p] = v & rmask;
-            sc.bin[p] = (uint16_t)sub;
+        for (uint32_t base = beg; base < end; base += 8 * SPK_TILE_THREADS) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t i = base + u * SPK_TILE_THREADS + tid;
+                v[u] = i < end ? __ldg(buf1 + i) : 0u;     // second read of the chunk: L1/L2 hit
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (base + u * SPK_TILE_THREADS + tid < end) {
+                    const uint32_t sub = v[u] >> rbits;
+                    const uint32_t p = atomicAdd(&sc.cnt[sub], 1u);
+                    sc.sorted[p] = v[u] & rmask;
+                    sc.bin[p] = (uint16_t)sub;
+                }
         }
         __syncthreads();
         for (uint32_t i = tid; i < n_e; i += SPK_TILE_THREADS) buf[sc.gbase[sc.bin[i]] + i] = sc.sorted[i];
@@ -457,6 +512,7 @@ struct CountOut {
     uint64_t* histo;
     uint32_t histo_len;
     uint32_t lower;
+    uint32_t* pindex;   // optional [2P]: first dump index / number of dumped entries of every partition
 };
 
 // ENT32: slot u64 = (r << 32) | count, empty = 0 (count >= 1 once occupied).
@@ -464,6 +520,8 @@ struct CountOut {
 // The table is cleared once per CTA; every insert that creates a key appends its slot to a list, so the
 // dump visits (and re-clears) only the occupied slots — the zero + full-scan loops of a naive version
 // cost more instructions than the inserts themselves.
+// The dump of a partition is contiguous (one reservation per partition, recorded in pindex): the
+// partitioned union/filter (spk_pmatrix.cu) merges the same partition of every chromosome on-chip.
 constexpr int PC_LIST = 4096;   // occupied-slot list capacity; beyond it a partition falls back to a full scan
 
 template <bool ENT64>
@@ -475,10 +533,12 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
     uint16_t* s_list = (uint16_t*)(s_raw + (size_t)PC_SLOTS * 8);
     uint32_t* s_cnt = (uint32_t*)(s_raw + (size_t)PC_SLOTS * 8 + (size_t)PC_LIST * 2);  // ENT64 only
     __shared__ uint32_t s_hist[256];
-    __shared__ uint64_t s_red[4][PC_THREADS / 32];
-    __shared__ uint32_t s_nocc;
+    __shared__ uint64_t s_red[2][PC_THREADS / 32];
+    __shared__ uint32_t s_nocc, s_nkeep, s_wr;
+    __shared__ uint64_t s_base;
     const int tid = threadIdx.x;
-    uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0, n_fail = 0;
+    const int lane = tid & 31;
+    uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0, n_fail = 0;   // distinct/sumall: thread 0 only
     uint32_t h1 = 0, h2 = 0;
     if (o.histo) s_hist[tid] = 0;
     const uint64_t EMPTY = ENT64 ? SPK_EMPTY_KEY : 0ull;
@@ -487,23 +547,27 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
         s_key[i] = EMPTY;
         if (ENT64) s_cnt[i] = 0;
     }
-    if (tid == 0) s_nocc = 0;
+    if (tid == 0) {
+        s_nocc = 0;
+        s_nkeep = 0;
+        s_wr = 0;
+    }
     __syncthreads();
 
-    // one slot of the table -> stats / histogram / dump; clears the slot
+    auto slot_count = [&](uint32_t slot, uint64_t& r) -> uint64_t {   // 0: empty
+        const uint64_t v = s_key[slot];
+        if (v == EMPTY) return 0;
+        r = ENT64 ? v : (v >> 32);
+        return ENT64 ? (uint64_t)s_cnt[slot] : (v & 0xffffffffull);
+    };
+    // one slot of the table -> histogram / dump; clears the slot
     auto visit = [&](uint32_t slot, bool active, uint64_t p) {
         uint64_t r = 0, cnt = 0;
-        bool occ = false;
         if (active) {
-            const uint64_t v = s_key[slot];
-            occ = v != EMPTY;
-            if (occ) {
-                r = ENT64 ? v : (v >> 32);
-                cnt = ENT64 ? (uint64_t)s_cnt[slot] : (v & 0xffffffffull);
+            cnt = slot_count(slot, r);
+            if (cnt) {
                 s_key[slot] = EMPTY;
                 if (ENT64) s_cnt[slot] = 0;
-                distinct++;
-                sumall += cnt;
                 if (o.histo) {
                     const uint64_t b = cnt < (uint64_t)(o.histo_len - 1) ? cnt : (uint64_t)(o.histo_len - 1);
                     if (b == 1) h1++;
@@ -513,19 +577,16 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
                 }
             }
         }
-        const bool keep = occ && cnt >= o.lower;
-        if (keep) {
-            nge++;
-            sumge += cnt;
-        }
+        const bool keep = cnt >= o.lower && cnt > 0;
         const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
         if (ballot) {
-            const int lane = tid & 31;
-            uint64_t wbase = 0;
-            if (lane == 0) wbase = atomicAdd((unsigned long long*)o.cursor, (unsigned long long)__popc(ballot));
+            uint32_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_wr, (uint32_t)__popc(ballot));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             if (keep) {
-                const uint64_t at = wbase + __popc(ballot & ((1u << lane) - 1));
+                nge++;
+                sumge += cnt;
+                const uint64_t at = s_base + wbase + __popc(ballot & ((1u << lane) - 1));
                 if (at < o.cap) {
                     o.keys[at] = mx.inv((p << mx.rbits) | r);
                     o.counts[at] = (uint32_t)cnt;
@@ -534,60 +595,125 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
         }
     };
 
-    for (uint64_t p = blockIdx.x; p < P; p += gridDim.x) {
-        const uint32_t beg = pstart[p], end = pstart[p + 1];
-        if (end == beg) continue;
-        // ---- insert ----
-        for (uint32_t i = beg + tid; i < end; i += PC_THREADS) {
-            const uint64_t r = ENT64 ? __ldcs((const uint64_t*)buf + i) : (uint64_t)__ldcs((const uint32_t*)buf + i);
-            uint32_t s = (ENT64 ? (uint32_t)spk_hash64(r) : fmix32((uint32_t)r)) & TMASK;
-            bool done = false;
-            for (uint32_t probes = 0; probes < PC_SLOTS; probes++) {
-                uint64_t c = s_key[s];
-                if (c == EMPTY) {
-                    const uint64_t fresh = ENT64 ? r : ((r << 32) | 1ull);
-                    const uint64_t old = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)EMPTY,
-                                                   (unsigned long long)fresh);
-                    if (old == EMPTY) {
-                        if (ENT64) atomicAdd(&s_cnt[s], 1u);
-                        const uint32_t li = atomicAdd(&s_nocc, 1u);
-                        if (li < PC_LIST) s_list[li] = (uint16_t)s;
-                        done = true;
-                        break;
-                    }
-                    c = old;
-                }
-                if (ENT64 ? (c == r) : ((c >> 32) == r)) {
+    // insert one remainder into the shared-memory table
+    auto insert = [&](uint64_t r) {
+        uint32_t s = (ENT64 ? (uint32_t)spk_hash64(r) : fmix32((uint32_t)r)) & TMASK;
+        bool done = false;
+        for (uint32_t probes = 0; probes < PC_SLOTS; probes++) {
+            uint64_t c = s_key[s];
+            if (c == EMPTY) {
+                const uint64_t fresh = ENT64 ? r : ((r << 32) | 1ull);
+                const uint64_t old = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)EMPTY,
+                                               (unsigned long long)fresh);
+                if (old == EMPTY) {
                     if (ENT64) atomicAdd(&s_cnt[s], 1u);
-                    else atomicAdd((unsigned int*)&s_key[s], 1u);   // low word = count (little endian)
+                    const uint32_t li = atomicAdd(&s_nocc, 1u);
+                    if (li < PC_LIST) s_list[li] = (uint16_t)s;
                     done = true;
                     break;
                 }
-                s = (s + 1) & TMASK;
+                c = old;
             }
-            if (!done) n_fail++;
+            if (ENT64 ? (c == r) : ((c >> 32) == r)) {
+                if (ENT64) atomicAdd(&s_cnt[s], 1u);
+                else atomicAdd((unsigned int*)&s_key[s], 1u);   // low word = count (little endian)
+                done = true;
+                break;
+            }
+            s = (s + 1) & TMASK;
+        }
+        if (!done) n_fail++;
+    };
+    using RegT = typename std::conditional<ENT64, uint64_t, uint32_t>::type;
+    auto load_r = [&](uint32_t i) -> RegT { return __ldcs((const RegT*)buf + i); };
+
+    // The partition stream is software-pipelined through registers: while partition p is inserted, the
+    // first PC_PF * 256 entries of the CTA's next partition (and the extents of the one after) are already
+    // in flight, so the global-load latency (the top stall of the unpipelined version) is hidden.
+    constexpr int PC_PF = ENT64 ? 8 : 16;
+    const uint64_t G = gridDim.x;
+    uint64_t p = blockIdx.x;
+    uint32_t beg = 0, end = 0, nbeg = 0, nend = 0;
+    if (p < P) { beg = pstart[p]; end = pstart[p + 1]; }
+    if (p + G < P) { nbeg = pstart[p + G]; nend = pstart[p + G + 1]; }
+    RegT cur[PC_PF];
+#pragma unroll
+    for (int u = 0; u < PC_PF; u++) {
+        const uint32_t i = beg + u * PC_THREADS + tid;
+        cur[u] = i < end ? load_r(i) : 0;
+    }
+    for (; p < P; p += G) {
+        RegT nxt[PC_PF];
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++) {
+            const uint32_t i = nbeg + u * PC_THREADS + tid;
+            nxt[u] = i < nend ? load_r(i) : 0;
+        }
+        uint32_t nnbeg = 0, nnend = 0;
+        if (p + 2 * G < P) { nnbeg = pstart[p + 2 * G]; nnend = pstart[p + 2 * G + 1]; }
+        // ---- insert ----
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++)
+            if (beg + u * PC_THREADS + tid < end) insert(cur[u]);
+        for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
+            RegT t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = base + u * PC_THREADS + tid;
+                t[u] = i < end ? load_r(i) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (base + u * PC_THREADS + tid < end) insert(t[u]);
         }
         __syncthreads();
-        // ---- dump + clear ----
+        // ---- dump pass 1: how many entries does this partition dump? (one reservation per partition) ----
         const uint32_t nocc = s_nocc;
-        if (nocc <= PC_LIST) {
-            for (uint32_t base = 0; base < nocc; base += PC_THREADS) {
-                const uint32_t i = base + tid;
-                visit(i < nocc ? (uint32_t)s_list[i] : 0u, i < nocc, p);
+        const bool listed = nocc <= PC_LIST;
+        const uint32_t nvis = listed ? nocc : (uint32_t)PC_SLOTS;
+        uint32_t myk = 0;
+        for (uint32_t i = tid; i < nvis; i += PC_THREADS) {
+            uint64_t r;
+            const uint64_t cnt = slot_count(listed ? (uint32_t)s_list[i] : i, r);
+            myk += (cnt >= o.lower && cnt > 0) ? 1u : 0u;
+        }
+        myk = spk_warp_sum_u32(myk);
+        if (lane == 0 && myk) atomicAdd(&s_nkeep, myk);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t nk = s_nkeep;
+            const uint64_t base = nk ? atomicAdd((unsigned long long*)o.cursor, (unsigned long long)nk) : 0ull;
+            s_base = base;
+            if (o.pindex) {
+                o.pindex[2 * p] = (uint32_t)base;
+                o.pindex[2 * p + 1] = nk;
             }
-        } else {
-            for (uint32_t base = 0; base < PC_SLOTS; base += PC_THREADS) visit(base + tid, true, p);
+            distinct += nocc;
+            sumall += end - beg;
         }
         __syncthreads();
-        if (tid == 0) s_nocc = 0;
+        // ---- dump pass 2: histogram, write, clear ----
+        for (uint32_t base = 0; base < nvis; base += PC_THREADS) {
+            const uint32_t i = base + tid;
+            visit(listed ? (i < nocc ? (uint32_t)s_list[i] : 0u) : i, i < nvis, p);
+        }
         __syncthreads();
+        if (tid == 0) {
+            s_nocc = 0;
+            s_nkeep = 0;
+            s_wr = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++) cur[u] = nxt[u];
+        beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
     }
     // ---- per-CTA totals ----
     __syncthreads();
     if (o.histo) {
         h1 = spk_warp_sum_u32(h1);
         h2 = spk_warp_sum_u32(h2);
-        if ((tid & 31) == 0) {
+        if (lane == 0) {
             if (h1) atomicAdd(&s_hist[1], h1);
             if (h2) atomicAdd(&s_hist[2], h2);
         }
@@ -595,26 +721,30 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
         if ((uint32_t)tid < o.histo_len && s_hist[tid])
             atomicAdd((unsigned long long*)&o.histo[tid], (unsigned long long)s_hist[tid]);
     }
-    uint64_t v[4] = {distinct, nge, sumge, sumall};
+    uint64_t v[2] = {nge, sumge};
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2; q++) {
         v[q] = spk_warp_sum_u64(v[q]);
-        if ((tid & 31) == 0) s_red[q][tid >> 5] = v[q];
+        if (lane == 0) s_red[q][tid >> 5] = v[q];
     }
     n_fail = spk_warp_sum_u64(n_fail);
-    if ((tid & 31) == 0 && n_fail) atomicAdd((unsigned long long*)&o.stats[1], (unsigned long long)n_fail);
+    if (lane == 0 && n_fail) atomicAdd((unsigned long long*)&o.stats[1], (unsigned long long)n_fail);
     __syncthreads();
-    if (tid < 4) {
+    if (tid < 2) {
         uint64_t s = 0;
         for (int w = 0; w < PC_THREADS / 32; w++) s += s_red[tid][w];
-        if (s) atomicAdd((unsigned long long*)&o.stats[4 + tid], (unsigned long long)s);
+        if (s) atomicAdd((unsigned long long*)&o.stats[5 + tid], (unsigned long long)s);
+    }
+    if (tid == 0) {
+        if (distinct) atomicAdd((unsigned long long*)&o.stats[4], (unsigned long long)distinct);
+        if (sumall) atomicAdd((unsigned long long*)&o.stats[7], (unsigned long long)sumall);
     }
 }
 
 template <bool ENT64>
 int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lower, char* ws, uint64_t* d_keys,
              uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo, uint32_t histo_len,
-             cudaStream_t st) {
+             uint32_t* d_pindex, cudaStream_t st) {
     void* buf = ws + pl.off_buf;
     uint32_t* psize = (uint32_t*)(ws + pl.off_psize);
     uint32_t* pstart = (uint32_t*)(ws + pl.off_pstart);
@@ -626,21 +756,17 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
     if (pl.n_tiles == 0) return SPK_OK;
     const int sms = spk_num_sms();
     const unsigned pass_grid = (unsigned)min((uint64_t)sms * 4, pl.n_tiles);
-    k_part_pass<false, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
-                                                                      nullptr, nullptr, d_stats);
-    SPK_LAUNCH_CHECK();
     const uint64_t nseg = (pl.P + 1023) / 1024;
-    k_scan_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs);
-    SPK_LAUNCH_CHECK();
-    k_scan_segs<<<1, 1024, 0, st>>>(segs, nseg);
-    SPK_LAUNCH_CHECK();
-    k_scan_apply<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs, pstart, cursor);
-    SPK_LAUNCH_CHECK();
     if (pl.two_level && !ENT64) {
         uint32_t* buf1 = (uint32_t*)(ws + pl.off_buf1);
         uint32_t* cur1 = (uint32_t*)(ws + pl.off_cur1);
         uint32_t* ustart = (uint32_t*)(ws + pl.off_ustart);
-        k_scatter_prepare<<<1, 1024, 0, st>>>(pstart, pl.b1, pl.b2, cur1, ustart);
+        uint32_t* bsize = ustart;                      // bucket sizes live in ustart until k_scatter_prepare
+        const int nb1 = 1 << pl.b1;
+        SPK_CUDA(cudaMemsetAsync(bsize, 0, (size_t)nb1 * 4, st));
+        k_hist1<<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, bsize, d_stats);
+        SPK_LAUNCH_CHECK();
+        k_bucket_scan<<<1, 1024, 0, st>>>(bsize, nb1, cur1);
         SPK_LAUNCH_CHECK();
         const size_t tile_bytes = ((SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) +
                                    (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) + 8 + 16 + 15) / 16 * 16;
@@ -654,12 +780,29 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         }
         const uint64_t n_super = (pl.n_tiles + SC_TILES - 1) / SC_TILES;
         k_scatter_l1<<<(unsigned)min((uint64_t)sms * 2, n_super), SPK_TILE_THREADS, smem1, st>>>(
-            pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1);
+            pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1, psize);
+        SPK_LAUNCH_CHECK();
+        k_scan_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs);
+        SPK_LAUNCH_CHECK();
+        k_scan_segs<<<1, 1024, 0, st>>>(segs, nseg);
+        SPK_LAUNCH_CHECK();
+        k_scan_apply<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs, pstart, cursor);
+        SPK_LAUNCH_CHECK();
+        k_scatter_prepare<<<1, 1024, 0, st>>>(pstart, pl.b1, pl.b2, cur1, ustart);
         SPK_LAUNCH_CHECK();
         k_scatter_l2<<<(unsigned)(sms * 2), SPK_TILE_THREADS, smem2, st>>>(buf1, pstart, ustart, pl.b1, pl.b2,
                                                                            pl.mx.rbits, cursor, (uint32_t*)buf);
         SPK_LAUNCH_CHECK();
     } else {
+        k_part_pass<false, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
+                                                                          nullptr, nullptr, d_stats);
+        SPK_LAUNCH_CHECK();
+        k_scan_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs);
+        SPK_LAUNCH_CHECK();
+        k_scan_segs<<<1, 1024, 0, st>>>(segs, nseg);
+        SPK_LAUNCH_CHECK();
+        k_scan_apply<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs, pstart, cursor);
+        SPK_LAUNCH_CHECK();
         k_part_pass<true, ENT64><<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, psize,
                                                                          cursor, buf, d_stats);
         SPK_LAUNCH_CHECK();
@@ -670,7 +813,7 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         SPK_CUDA(cudaFuncSetAttribute(k_part_count<ENT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[ENT64 ? 1 : 0] = true;
     }
-    CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower};
+    CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower, d_pindex};
     const unsigned cgrid = (unsigned)min((uint64_t)sms * (ENT64 ? 2 : 3), pl.P);
     k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
     SPK_LAUNCH_CHECK();
@@ -679,16 +822,25 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
 
 }  // namespace
 
-extern "C" size_t spk_pcount_workspace_bytes(uint64_t n_bases, int k) {
+extern "C" int spk_pcount_pbits(uint64_t n_bases, int k) {
+    if (k < 1 || k > 32 || n_bases >= 0xffffffffull) return -1;
+    return auto_pbits(n_bases, k);
+}
+
+extern "C" size_t spk_pcount_workspace_bytes_ex(uint64_t n_bases, int k, int pbits) {
     PcPlan pl;
-    if (make_plan(n_bases, k, &pl) != SPK_OK) return 0;
+    if (make_plan(n_bases, k, pbits, &pl) != SPK_OK) return 0;
     return pl.total;
 }
 
-extern "C" int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
-                                    uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
-                                    uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
-                                    uint32_t histo_len, void* stream) {
+extern "C" size_t spk_pcount_workspace_bytes(uint64_t n_bases, int k) {
+    return spk_pcount_workspace_bytes_ex(n_bases, k, 0);
+}
+
+extern "C" int spk_pcount_canonical_ex(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                                       uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
+                                       uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
+                                       uint32_t histo_len, int pbits, uint32_t* d_pindex, void* stream) {
     SPK_CHECK_ARG(d_packed && d_valid && d_ws && d_stats, "null pointer");
     SPK_CHECK_ARG(cap == 0 || (d_keys && d_counts), "null output");
     SPK_CHECK_ARG(k >= 1 && k <= 32, "k must be in [1, 32]");
@@ -697,8 +849,9 @@ extern "C" int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_
     SPK_CHECK_ARG(((uintptr_t)d_packed & 15) == 0 && ((uintptr_t)d_valid & 15) == 0 && ((uintptr_t)d_ws & 255) == 0,
                   "buffers must be aligned (16 B sequence, 256 B workspace)");
     PcPlan pl;
-    if (make_plan(n_bases, k, &pl) != SPK_OK) {
-        spk_set_error("spk_pcount_canonical: cannot plan");
+    if (make_plan(n_bases, k, pbits, &pl) != SPK_OK) {
+        spk_set_error("spk_pcount_canonical: cannot plan (pbits=%d must be 0 or >= spk_pcount_pbits and <= min(2k, %d))",
+                      pbits, PC_MAX_PBITS);
         return SPK_EINVAL;
     }
     if (ws_bytes < pl.total) {
@@ -707,10 +860,21 @@ extern "C" int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_
     }
     cudaStream_t st = (cudaStream_t)stream;
     SPK_CUDA(cudaMemsetAsync(d_stats, 0, 8 * sizeof(uint64_t), st));
-    if (n_bases < (uint64_t)k) return SPK_OK;
+    if (n_bases < (uint64_t)k) {
+        if (d_pindex) SPK_CUDA(cudaMemsetAsync(d_pindex, 0, (size_t)pl.P * 8, st));
+        return SPK_OK;
+    }
     if (pl.ent64)
         return run_plan<true>(pl, (const uint8_t*)d_packed, (const uint8_t*)d_valid, lower_count, (char*)d_ws, d_keys,
-                              d_counts, cap, d_stats, d_histo, histo_len, st);
+                              d_counts, cap, d_stats, d_histo, histo_len, d_pindex, st);
     return run_plan<false>(pl, (const uint8_t*)d_packed, (const uint8_t*)d_valid, lower_count, (char*)d_ws, d_keys,
-                           d_counts, cap, d_stats, d_histo, histo_len, st);
+                           d_counts, cap, d_stats, d_histo, histo_len, d_pindex, st);
+}
+
+extern "C" int spk_pcount_canonical(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_bases, int k,
+                                    uint32_t lower_count, void* d_ws, size_t ws_bytes, uint64_t* d_keys,
+                                    uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo,
+                                    uint32_t histo_len, void* stream) {
+    return spk_pcount_canonical_ex(d_packed, d_valid, n_bases, k, lower_count, d_ws, ws_bytes, d_keys, d_counts, cap,
+                                   d_stats, d_histo, histo_len, 0, nullptr, stream);
 }

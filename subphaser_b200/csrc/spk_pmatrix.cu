@@ -1,0 +1,232 @@
+// K3b+K4 (partitioned): union of the per-chromosome dumps -> count rows -> differential filter, one hash
+// partition at a time, entirely in shared memory.
+//
+// Replaces JellyfishDumps.to_matrix + JellyfishDumps.filter / _filter_kmer (Jellyfish.py:439-512,611-648)
+// for dumps produced by spk_pcount_canonical_ex with a COMMON number of partition bits: partition p of
+// every chromosome holds exactly the k-mers u with (f(u) >> rbits) == p, and its dump entries are
+// contiguous (pindex).  So the union of partition p over the n chromosomes is a few hundred rows: they are
+// merged in a shared-memory table (key -> n counters), every row is put through the same fp64 test as
+// spk_filter_differential (spk_filter.cuh, -fmad=false) and only the surviving rows (typically ~2 %) are
+// written to HBM.  The multi-GB union table and the [U x n] matrix of the plain path (spk_matrix.cu:
+// ~6 random HBM accesses per dump entry) never exist; HBM sees one coalesced read of the dumps.
+#include "spk_common.cuh"
+#include "spk_filter.cuh"
+
+namespace {
+
+constexpr int PM_THREADS = 256;
+constexpr int PM_MAX_COLS = 256;
+
+struct PmArgs {
+    const uint64_t* const* keys;      // [n] device pointers to the dump keys of every chromosome
+    const uint32_t* const* counts;    // [n]
+    const uint32_t* const* pindex;    // [n] uint32[2P]: first entry / number of entries of partition p
+    int n;
+    uint64_t P;
+    uint32_t nparts, part;            // this call handles partitions p % nparts == part
+    const uint64_t* lengths;
+    FilterCfg cfg;
+    uint64_t* out_keys;               // surviving rows (flag bit 1), arbitrary order
+    uint32_t* out_counts;             // [cap x n]
+    uint64_t* out_tot;
+    uint64_t cap;
+    uint64_t* fold_tots;              // optional: totals of every fold-passing row (histogram input)
+    uint64_t fold_cap;
+    uint64_t* counters;               // [0] union rows [1] fold-pass rows [2] kept rows [3] table overflows
+    uint32_t tslots;                  // table slots (power of two)
+};
+
+__device__ __forceinline__ uint32_t pm_hash(uint64_t key) { return (uint32_t)(spk_hash64(key) >> 32); }
+
+__global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int n = a.n;
+    const uint32_t TS = a.tslots, TM = TS - 1;
+    uint64_t* s_key = (uint64_t*)s_raw;                        // [TS]
+    uint32_t* s_cnt = (uint32_t*)(s_key + TS);                 // [TS x n]
+    uint32_t* s_start = s_cnt + (size_t)TS * n;                // [n]   first entry of this partition
+    uint32_t* s_off = s_start + n;                             // [n+1] prefix of entry counts
+    __shared__ uint32_t s_fail;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    for (uint32_t i = tid; i < TS; i += PM_THREADS) s_key[i] = SPK_EMPTY_KEY;
+    for (uint32_t i = tid; i < TS * (uint32_t)n; i += PM_THREADS) s_cnt[i] = 0;
+    if (tid == 0) s_fail = 0;
+    uint64_t n_union = 0, n_fold = 0, n_keep = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * a.nparts;
+    uint64_t p = (uint64_t)blockIdx.x * a.nparts + a.part;
+    // index of the CTA's next partition, prefetched while the current one is processed (threads c < n)
+    uint32_t nx_start = 0, nx_len = 0;
+    if (p < a.P)
+        for (int c = tid; c < n; c += PM_THREADS) {          // n <= PM_MAX_COLS = blockDim: one c per thread
+            nx_start = a.pindex[c][2 * p];
+            nx_len = a.pindex[c][2 * p + 1];
+        }
+    __syncthreads();
+    for (; p < a.P; p += stride) {
+        if (tid < n) {
+            s_start[tid] = nx_start;
+            s_off[tid + 1] = nx_len;
+        }
+        const uint64_t pn = p + stride;
+        if (pn < a.P && tid < n) {
+            nx_start = a.pindex[tid][2 * pn];
+            nx_len = a.pindex[tid][2 * pn + 1];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            s_off[0] = 0;
+            for (int c = 0; c < n; c++) {
+                const uint32_t l = s_off[c + 1];
+                s_off[c + 1] = run + l;
+                run += l;
+            }
+        }
+        __syncthreads();
+        const uint32_t E = s_off[n];
+        // rows <= E: when the partition could crowd the table it is processed in `rounds` key-hash classes
+        uint32_t rounds = 1;
+        while ((uint64_t)E > (uint64_t)rounds * (TS - TS / 8)) rounds <<= 1;
+        for (uint32_t rd = 0; rd < rounds; rd++) {
+            // ---- insert: (key, count of chromosome c) -> table row ----
+            int c = 0;
+            for (uint32_t e = tid; e < E; e += PM_THREADS) {
+                while (e >= s_off[c + 1]) c++;
+                const uint32_t i = s_start[c] + (e - s_off[c]);
+                const uint64_t key = __ldg(a.keys[c] + i);
+                const uint32_t h = pm_hash(key);
+                if (rounds > 1 && ((h >> 20) & (rounds - 1)) != rd) continue;
+                const uint32_t cnt = __ldg(a.counts[c] + i);
+                uint32_t s = h & TM;
+                bool done = false;
+                for (uint32_t pr = 0; pr < TS; pr++) {
+                    uint64_t cur = s_key[s];
+                    if (cur == SPK_EMPTY_KEY) {
+                        cur = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)SPK_EMPTY_KEY,
+                                        (unsigned long long)key);
+                        if (cur == SPK_EMPTY_KEY) cur = key;
+                    }
+                    if (cur == key) {
+                        s_cnt[(size_t)s * n + c] = cnt;      // one entry per (k-mer, chromosome)
+                        done = true;
+                        break;
+                    }
+                    s = (s + 1) & TM;
+                }
+                if (!done) s_fail = 1;
+            }
+            __syncthreads();
+            // ---- filter every row, emit the survivors, clear the table ----
+            for (uint32_t s0 = 0; s0 < TS; s0 += PM_THREADS) {
+                const uint32_t s = s0 + tid;
+                const uint64_t key = s_key[s];
+                uint8_t fl = 0;
+                uint64_t tot = 0;
+                const bool occ = key != SPK_EMPTY_KEY;
+                if (occ) {
+                    fl = spk_filter_row(s_cnt + (size_t)s * n, n, a.lengths, a.cfg, tot);
+                    n_union++;
+                    n_fold += fl & 1;
+                    n_keep += (fl >> 1) & 1;
+                }
+                if (a.fold_tots) {
+                    const uint32_t bf = __ballot_sync(0xffffffffu, fl & 1);
+                    if (bf) {
+                        uint64_t wb = 0;
+                        if (lane == 0) wb = atomicAdd((unsigned long long*)&a.counters[5], (unsigned long long)__popc(bf));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        const uint64_t at = wb + __popc(bf & ((1u << lane) - 1));
+                        if ((fl & 1) && at < a.fold_cap) a.fold_tots[at] = tot;
+                    }
+                }
+                const uint32_t bk = __ballot_sync(0xffffffffu, fl & 2);
+                if (bk) {
+                    uint64_t wb = 0;
+                    if (lane == 0) wb = atomicAdd((unsigned long long*)&a.counters[4], (unsigned long long)__popc(bk));
+                    wb = __shfl_sync(0xffffffffu, wb, 0);
+                    const uint64_t at = wb + __popc(bk & ((1u << lane) - 1));
+                    if ((fl & 2) && at < a.cap) {
+                        a.out_keys[at] = key;
+                        a.out_tot[at] = tot;
+                        for (int cc = 0; cc < n; cc++) a.out_counts[at * n + cc] = s_cnt[(size_t)s * n + cc];
+                    }
+                }
+                if (occ) {
+                    s_key[s] = SPK_EMPTY_KEY;
+                    for (int cc = 0; cc < n; cc++) s_cnt[(size_t)s * n + cc] = 0;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    n_union = spk_warp_sum_u64(n_union);
+    n_fold = spk_warp_sum_u64(n_fold);
+    n_keep = spk_warp_sum_u64(n_keep);
+    if (lane == 0) {
+        if (n_union) atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)n_union);
+        if (n_fold) atomicAdd((unsigned long long*)&a.counters[1], (unsigned long long)n_fold);
+        if (n_keep) atomicAdd((unsigned long long*)&a.counters[2], (unsigned long long)n_keep);
+    }
+    __syncthreads();
+    if (tid == 0 && s_fail) atomicAdd((unsigned long long*)&a.counters[3], 1ull);
+}
+
+uint32_t pm_table_slots(int n) {
+    // largest power of two whose table (8-byte key + n 4-byte counters per slot) stays under ~100 KB,
+    // so that two CTAs share an SM
+    uint32_t ts = 4096;
+    while (ts > 256 && (size_t)ts * (8 + 4 * (size_t)n) > 100 * 1024) ts >>= 1;
+    return ts;
+}
+
+}  // namespace
+
+extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
+                                  const uint32_t* const* d_pindex, int n, int pbits, uint32_t nparts, uint32_t part,
+                                  const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
+                                  const int32_t* d_grp_off, int n_groups, const int32_t* d_members, double min_fold,
+                                  int baseline, int by_count, double ratio, double min_freq, double max_freq,
+                                  uint64_t* d_out_keys, uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap,
+                                  uint64_t* d_fold_tots, uint64_t fold_cap, uint64_t* d_counters, void* stream) {
+    SPK_CHECK_ARG(d_keys && d_counts && d_pindex && d_lengths && d_set_off && d_grp_off && d_members && d_counters,
+                  "null pointer");
+    SPK_CHECK_ARG(n >= 1 && n <= PM_MAX_COLS, "1 <= n <= 256 chromosomes");
+    SPK_CHECK_ARG(pbits >= 0 && pbits <= 30, "bad pbits");
+    SPK_CHECK_ARG(nparts >= 1 && part < nparts, "bad partition");
+    SPK_CHECK_ARG(n_sets >= 1 && n_groups >= 1, "bad shape");
+    SPK_CHECK_ARG(baseline < MX_MAX_GROUPS_PER_SET && baseline >= -MX_MAX_GROUPS_PER_SET, "baseline out of range");
+    SPK_CHECK_ARG(cap == 0 || (d_out_keys && d_out_counts && d_out_tot), "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPK_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(uint64_t), st));
+    PmArgs a;
+    a.keys = d_keys;
+    a.counts = d_counts;
+    a.pindex = d_pindex;
+    a.n = n;
+    a.P = 1ull << pbits;
+    a.nparts = nparts;
+    a.part = part;
+    a.lengths = d_lengths;
+    a.cfg = FilterCfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio, min_freq, max_freq};
+    a.out_keys = d_out_keys;
+    a.out_counts = d_out_counts;
+    a.out_tot = d_out_tot;
+    a.cap = cap;
+    a.fold_tots = d_fold_tots;
+    a.fold_cap = d_fold_tots ? fold_cap : 0;
+    a.counters = d_counters;
+    a.tslots = pm_table_slots(n);
+    const size_t smem = (size_t)a.tslots * (8 + 4 * (size_t)n) + (size_t)(2 * n + 2) * 4;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const uint64_t mine = (a.P + nparts - 1 - part) / nparts;
+    if (mine == 0) return SPK_OK;
+    const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 2, mine);
+    k_pmatrix_filter<<<grid, PM_THREADS, smem, st>>>(a);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}

@@ -58,11 +58,23 @@ __device__ __forceinline__ uint64_t spk_rev2(uint64_t x) {
     x = __brevll(x);
     return ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
 }
+// reverse the order of the 16 2-bit groups of x
+__device__ __forceinline__ uint32_t spk_rev2_32(uint32_t x) {
+    x = __brev(x);
+    return ((x & 0xAAAAAAAAu) >> 1) | ((x & 0x55555555u) << 1);
+}
 
 // Canonical k-mers of this thread's 16 start positions; bit j of okmask = window j has k valid bases.
-// Forward word: first base most significant (integer order == lexicographic A<C<G<T); the reverse
-// complement is rolled alongside; canonical = min of the two.
+// Forward word: first base most significant (integer order == lexicographic A<C<G<T); canonical = min of
+// the forward word and its reverse complement.
 // `pk` / `vd`: shared-memory words of one tile (260 / 132 words incl. halo).
+//
+// No rolling state: with W = the thread's 48-base window as packed (base 0 in the low bits),
+//   revcomp_j = (~W >> 2j) & kmask                      (complementing = NOT, and the little-endian packing
+//                                                         already is "last base most significant")
+//   forward_j = (rev2(W) >> 2(48-k-j)) & kmask          (rev2 = order of the 2-bit groups reversed)
+// rev2(W) is shifted once per thread by the k-dependent 2(33-k) bits, so every per-position shift is a
+// compile-time constant: 2 funnel shifts + 2 masks per word instead of a 64-bit shift/or/and chain.
 __device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_t* vd, const SpkKmerParams& p,
                                                uint64_t (&key)[SPK_KMERS_PER_THREAD],
                                                uint32_t& okmask) {
@@ -70,26 +82,37 @@ __device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_
     const uint32_t w0 = pk[tid], w1 = pk[tid + 1], w2 = pk[tid + 2];
     const uint32_t v0 = vd[tid >> 1], v1 = vd[(tid >> 1) + 1];
     const uint64_t vbits = (((uint64_t)v1 << 32) | v0) >> ((tid & 1) * 16);
-    const uint64_t lo = ((uint64_t)w1 << 32) | w0;
+    const uint32_t klo = (uint32_t)p.kmask, khi = (uint32_t)(p.kmask >> 32);
 
-    // state before the k-th base is shifted in: the first k-1 bases (base 0 in the low bits of `lo`)
-    const uint64_t le = lo & (p.kmask >> 2);
-    uint64_t fwd = (p.k > 1) ? (spk_rev2(le) >> (64 - 2 * (p.k - 1))) : 0;
-    uint64_t rc = (p.k > 1) ? (((~le) & (p.kmask >> 2)) << 2) : 0;
-    // the next 16 bases (indices k-1 .. k+14)
-    uint64_t st = lo >> p.top_shift;
-    if (p.top_shift > 0) st |= (uint64_t)w2 << (64 - p.top_shift);
-    const uint32_t nxt = (uint32_t)st;
+    const uint32_t n0 = ~w0, n1 = ~w1, n2 = ~w2;
+    uint32_t a0 = spk_rev2_32(w2), a1 = spk_rev2_32(w1), a2 = spk_rev2_32(w0);
+    const int s = 2 * (33 - p.k);            // 2 .. 64
+    if (s >= 64) { a0 = a2; a1 = 0; a2 = 0; }
+    else if (s >= 32) { a0 = a1; a1 = a2; a2 = 0; }
+    const uint32_t sl = (uint32_t)s & 31u;
+    const uint32_t f0 = __funnelshift_r(a0, a1, sl), f1 = __funnelshift_r(a1, a2, sl), f2 = a2 >> sl;
 
-    okmask = 0;
 #pragma unroll
     for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
-        const uint64_t b = (nxt >> (2 * j)) & 3u;
-        fwd = ((fwd << 2) | b) & p.kmask;
-        rc = (rc >> 2) | ((3ull - b) << p.top_shift);
+        const uint32_t flo = __funnelshift_r(f0, f1, 2 * (15 - j)) & klo;
+        const uint32_t fhi = __funnelshift_r(f1, f2, 2 * (15 - j)) & khi;
+        const uint32_t rlo = __funnelshift_r(n0, n1, 2 * j) & klo;
+        const uint32_t rhi = __funnelshift_r(n1, n2, 2 * j) & khi;
+        const uint64_t fwd = ((uint64_t)fhi << 32) | flo, rc = ((uint64_t)rhi << 32) | rlo;
         key[j] = (fwd < rc) ? fwd : rc;
-        if (((vbits >> j) & p.vmask) == p.vmask) okmask |= 1u << j;
     }
+    // validity: window j needs bits j .. j+k-1 of vbits set.  inv smeared down by k-1 marks the bad starts.
+    const uint64_t need = (1ull << (15 + p.k)) - 1;   // 15 + k <= 47
+    uint64_t x = ~vbits & need;
+    if (x != 0) {
+        int covered = 1;
+        while (covered < p.k) {
+            const int sh = min(covered, p.k - covered);
+            x |= x >> sh;
+            covered += sh;
+        }
+    }
+    okmask = (uint32_t)(~x) & 0xffffu;
 }
 
 __device__ __forceinline__ void spk_tile_kmers(const SpkTileSmem& s, int buf, const SpkKmerParams& p,

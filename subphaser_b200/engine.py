@@ -110,8 +110,10 @@ def pack_fasta(d_ascii, nbytes, name=None, trim=True):
 class KmerDump:
     """`jellyfish dump -c -L` content of one chromosome, resident on the device."""
 
-    def __init__(self, keys, counts, k, length, n_valid_kmers, n_distinct, name=None, histo=None):
+    def __init__(self, keys, counts, k, length, n_valid_kmers, n_distinct, name=None, histo=None,
+                 pindex=None, pbits=0):
         self.keys, self.counts, self.k = keys, counts, int(k)
+        self.pindex, self.pbits = pindex, int(pbits)   # partition index of the dump (spk_pcount_canonical_ex)
         self.length = int(length)              # sum of dumped counts == lengths[i] (Jellyfish.py:97)
         self.n_valid_kmers = int(n_valid_kmers)
         self.n_distinct = int(n_distinct)
@@ -132,7 +134,7 @@ class CountTable:
     mode "global": the v1 single open-addressed table in HBM (spk_count.cu); used for chromosomes of
     2^32 bases or more, or when SPK_COUNT_MODE=global."""
 
-    def __init__(self, max_bases, k, lower_count=1, mode=None):
+    def __init__(self, max_bases, k, lower_count=1, mode=None, common_pbits=True, genome_max_bases=None):
         require_cuda()
         lib = _lib.load()
         self.k = int(k)
@@ -144,8 +146,14 @@ class CountTable:
             mode = "global"
         self.mode = mode
         self.stats = _zeros(8, torch.int64)
+        self.pbits = 0
         if mode == "partitioned":
-            self.ws_bytes = lib.spk_pcount_workspace_bytes(self.max_bases, self.k)
+            # common_pbits: every chromosome counted with this table uses the partition bits of the
+            # largest one, and its dump carries a partition index (-> engine.pmatrix_filter)
+            # genome_max_bases: the largest chromosome of the whole genome (other ranks included)
+            gmax = max(self.max_bases, int(genome_max_bases or 0))
+            self.pbits = lib.spk_pcount_pbits(gmax, self.k) if (common_pbits and gmax < 2**32 - 1) else 0
+            self.ws_bytes = lib.spk_pcount_workspace_bytes_ex(self.max_bases, self.k, self.pbits)
             self.ws = _empty(self.ws_bytes, torch.uint8)
             self.cap = self.max_bases // self.lower_count + 1024
             self.out_keys = _empty(self.cap, torch.int64)
@@ -174,9 +182,10 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
     histo = _zeros(histo_len, torch.int64) if histo_len else None
     if table.mode == "partitioned":
         e = tick("count")
-        call("spk_pcount_canonical", _p(seq.packed), _p(seq.valid), seq.n_bases, k, lower_count, _p(table.ws),
+        pindex = _empty(2 << table.pbits, torch.int32) if table.pbits else None
+        call("spk_pcount_canonical_ex", _p(seq.packed), _p(seq.valid), seq.n_bases, k, lower_count, _p(table.ws),
              table.ws_bytes, _p(table.out_keys), _p(table.out_counts), table.cap, _p(table.stats), _p(histo),
-             histo_len, st)
+             histo_len, table.pbits, _p(pindex), st)
         tock(e)
         n_valid, n_fail, _, _, distinct, n_ge, sum_ge, _ = (int(x) for x in table.stats.cpu().tolist())
         if n_fail:
@@ -187,7 +196,7 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
         keys = table.out_keys[:n_ge].clone()
         counts = table.out_counts[:n_ge].clone()
         tock(e)
-        return KmerDump(keys, counts, k, sum_ge, n_valid, distinct, seq.name, histo)
+        return KmerDump(keys, counts, k, sum_ge, n_valid, distinct, seq.name, histo, pindex, table.pbits)
     e = tick("table_init")
     call("spk_count_table_init", _p(table.table), table.table_bytes, k, table.layout, st)
     table.stats.zero_()
@@ -322,6 +331,55 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
     return DiffMatrix(keys, norm, otot, cm.k, labels, n_fold, fold_tots)
 
 
+def can_pmatrix(dumps):
+    """True when every dump carries a partition index with the same partition bits."""
+    return (len(dumps) > 0 and len(dumps) <= 256 and all(d.pindex is not None and d.pbits > 0 for d in dumps)
+            and len({d.pbits for d in dumps}) == 1 and os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain")
+
+
+def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200, max_freq=10000,
+                   by_count=False, want_fold_tots=False, nparts=1, part=0, lengths=None):
+    """to_matrix + filter in one partition-by-partition pass (spk_pmatrix_filter) -> (DiffMatrix, n_union).
+    Rows come back sorted by k-mer, normalised by `lengths` exactly like filter_matrix."""
+    require_cuda()
+    st = _stream()
+    n = len(dumps)
+    k, pbits = dumps[0].k, dumps[0].pbits
+    lengths = [d.length for d in dumps] if lengths is None else list(lengths)
+    set_off, grp_off, members = flatten_sgs(sgs, labels)
+    d_set, d_grp, d_mem = (torch.from_numpy(a).to(_dev()) for a in (set_off, grp_off, members))
+    d_len = torch.tensor(lengths, dtype=torch.int64, device=_dev())
+    ptrs = torch.tensor([[d.keys.data_ptr() for d in dumps], [d.counts.data_ptr() for d in dumps],
+                         [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
+    counters = _zeros(8, torch.int64)
+    total = sum(len(d) for d in dumps)
+    cap = max(total // (64 * nparts), 1 << 16)          # survivors are a few % of the union; grown on demand
+    fold_cap = 0
+    while True:
+        okeys, otot = _empty(cap, torch.int64), _empty(cap, torch.int64)
+        ocnt = _empty(cap * n, torch.int32).view(cap, n)
+        ftot = _empty(fold_cap, torch.int64) if fold_cap else None
+        call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), n, pbits, nparts, part, _p(d_len),
+             _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), float(min_fold), int(baseline),
+             int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt), _p(otot),
+             cap, _p(ftot), fold_cap, _p(counters), st)
+        n_union, n_fold, n_keep, n_over = (int(x) for x in counters[:4].cpu().tolist())
+        if n_over:
+            raise OverflowError("partition table overflow in spk_pmatrix_filter")
+        if n_keep <= cap and (not want_fold_tots or n_fold <= fold_cap):
+            break
+        cap = max(cap, n_keep)
+        fold_cap = n_fold if want_fold_tots else 0
+    cm = CountMatrix(ocnt[:n_keep], okeys[:n_keep], lengths, k, labels)
+    dm = filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio, min_freq=min_freq,
+                       max_freq=max_freq, by_count=by_count)       # sort by k-mer + normalise (every row passes again)
+    assert len(dm) == n_keep
+    dm.n_fold_pass = n_fold
+    if want_fold_tots:
+        dm.fold_tots = ftot[:n_fold].cpu().numpy() if n_fold else np.zeros(0, np.int64)
+    return dm, n_union
+
+
 def argsort_keys(keys, key_bits):
     """Stable ascending argsort of uint64 keys held in an int64 tensor (spk_sort_pairs_u64)."""
     require_cuda()
@@ -438,27 +496,52 @@ def pca_gram(G, ncomp):
 # K9: map specific k-mers to bins
 # ----------------------------------------------------------------------------------------------------
 class SigTable:
-    """canonical specific k-mer -> subgenome index, open-addressed on the device."""
+    """canonical specific k-mer -> subgenome index on the device.
 
-    def __init__(self, keys, vals, k, track_hits=True):
+    Shipped layout: bucketed quotient table (spk_qtable_*, one 16/32-byte load per lookup, L2-resident)
+    with a small open-addressed stash; `layout="open"` (or no bucketed layout for this k / S / size)
+    uses the plain open-addressed table + one-hash bitmap of spk_sig_table_build."""
+
+    def __init__(self, keys, vals, k, track_hits=True, S=None, layout=None):
         require_cuda()
+        lib = _lib.load()
         n = int(keys.numel())
         self.k = int(k)
         self.pack_vals = 1 if self.k <= 28 else 0
         self.n = n
-        self.slots = max(2 * n + 64, 1024)
-        self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
-        self.svals = _zeros(self.slots, torch.uint8)
-        self.filter_bits = 1024
-        while self.filter_bits < 16 * n:
-            self.filter_bits *= 2
-        self.filter = _zeros(self.filter_bits // 32, torch.int32)
+        self.S = int(S) if S is not None else (int(vals.max().item()) + 1 if n else 1)
+        layout = layout or os.environ.get("SPK_MAP_LAYOUT", "bucket")
+        self.bucket = False
         fail = _zeros(1, torch.int64)
-        call("spk_sig_table_build", _p(keys), _p(vals), n, _p(self.skeys), _p(self.svals), self.slots,
-             _p(self.filter), self.filter_bits, self.pack_vals, _p(fail), _stream())
+        if layout == "bucket":
+            sb, bb = ctypes.c_int(0), ctypes.c_int(0)
+            if lib.spk_qtable_plan(n, self.k, self.S, ctypes.byref(sb), ctypes.byref(bb)) == 0:
+                self.bucket = True
+                self.slot_bits, self.bucket_bits = sb.value, bb.value
+        if self.bucket:
+            nslots = 8 << self.bucket_bits
+            self.buckets = torch.full((nslots,), -1, dtype=torch.int16 if self.slot_bits == 16 else torch.int32,
+                                      device=_dev())
+            self.slots = max(n // 4 + 64, 1024)           # stash: ~1 % of the keys land here
+            self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
+            self.svals = _zeros(self.slots, torch.uint8)
+            call("spk_qtable_build", _p(keys), _p(vals), n, self.k, self.S, _p(self.buckets), self.slot_bits,
+                 self.bucket_bits, _p(self.skeys), _p(self.svals), self.slots, self.pack_vals, _p(fail), _stream())
+            nflags = nslots + self.slots
+        else:
+            self.slots = max(2 * n + 64, 1024)
+            self.skeys = torch.full((self.slots,), -1, dtype=torch.int64, device=_dev())
+            self.svals = _zeros(self.slots, torch.uint8)
+            self.filter_bits = 1024
+            while self.filter_bits < 16 * n:
+                self.filter_bits *= 2
+            self.filter = _zeros(self.filter_bits // 32, torch.int32)
+            call("spk_sig_table_build", _p(keys), _p(vals), n, _p(self.skeys), _p(self.svals), self.slots,
+                 _p(self.filter), self.filter_bits, self.pack_vals, _p(fail), _stream())
+            nflags = self.slots
         if int(fail.item()):
             raise OverflowError("specific k-mer table full")
-        self.hit_flags = _zeros(self.slots, torch.uint8) if track_hits else None
+        self.hit_flags = _zeros(nflags, torch.uint8) if track_hits else None
 
     def n_mapped(self):
         return int(self.hit_flags.sum().item()) if self.hit_flags is not None else 0
@@ -471,7 +554,13 @@ def map_bins(seq, sig, S, bin_size, chunk_size):
     n_lines = lib.spk_map_num_lines(seq.n_bases, sig.k, int(bin_size), int(chunk_size))
     counts = _zeros(max(n_lines, 1) * S, torch.int32).view(max(n_lines, 1), S)
     nhits = _zeros(1, torch.int64)
-    if seq.n_bases:
+    if seq.n_bases and sig.bucket:
+        if S < sig.S:
+            raise ValueError("map_bins: table holds %d subgenomes, S=%d" % (sig.S, S))
+        call("spk_map_bins_q", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.buckets), sig.slot_bits,
+             sig.bucket_bits, _p(sig.skeys), _p(sig.svals), sig.slots, sig.pack_vals, sig.S, int(bin_size),
+             int(chunk_size), _p(counts), max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())
+    elif seq.n_bases:
         call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
              sig.slots, S, _p(sig.filter), sig.filter_bits, sig.pack_vals, int(bin_size), int(chunk_size), _p(counts),
              max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())

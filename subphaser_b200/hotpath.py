@@ -55,6 +55,25 @@ def exchange_dumps(local, n, owner, dist, dev, n_kmers_local=0):
     return out, int(meta_h[n][0])
 
 
+def exchange_pindex(local, n, owner, dist, dev, pbits_local):
+    """Partition indices of the dumps (int32 [2 << pbits] each) -> present on every rank.  All ranks must use
+    the same partition bits (the table is sized for the largest chromosome of the genome); returns ({}, 0)
+    when any rank has none."""
+    rank = dist.get_rank()
+    ok = all(v is not None for v in local.values())
+    meta = torch.tensor([int(pbits_local) if ok else -1, -(int(pbits_local) if ok else -1)], dtype=torch.int64, device=dev)
+    dist.all_reduce(meta, op=dist.ReduceOp.MAX)
+    pmax, pmin = int(meta[0].item()), -int(meta[1].item())
+    if pmax != pmin or pmax <= 0:
+        return {}, 0
+    out = {}
+    for i in range(n):
+        t = local[i] if owner[i] == rank else torch.empty(2 << pmax, dtype=torch.int32, device=dev)
+        dist.broadcast(t, src=owner[i])
+        out[i] = t
+    return out, pmax
+
+
 def exchange_rows(dm, n_union_local, dist, dev):
     """Differential-matrix shards (rows hashed over ranks) -> the full matrix, sorted by k-mer, on every rank."""
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -172,7 +191,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
 
     # ---- K1-K3 per chromosome -----------------------------------------------------------------------
     max_bytes = max([chrom_inputs[i][1] for i in mine] + [1])
-    table = engine.CountTable(max_bytes, k, lower_count)
+    table = engine.CountTable(max_bytes, k, lower_count, genome_max_bases=max([c[1] for c in chrom_inputs] + [1]))
     seqs, dumps = {}, {}
     n_kmers = 0
     # host inputs: the H2D copy of chromosome j+1 runs on a side stream while chromosome j is counted
@@ -216,25 +235,34 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         e = t.start("exchange")
         local = {i: (dumps[i].keys, dumps[i].counts, dumps[i].length) for i in mine}
         everything, n_kmers_total = exchange_dumps(local, n, owner, dist, dev, n_kmers)
+        pidx, pbits = exchange_pindex({i: dumps[i].pindex for i in mine}, n, owner, dist, dev,
+                                      dumps[mine[0]].pbits if mine else 0)
         for i in range(n):
             if owner[i] != rank:
                 kk, cc, length = everything[i]
-                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i])
+                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx.get(i), pbits)
         t.stop(e)
     else:
         n_kmers_total = n_kmers
     dump_list = [dumps[i] for i in range(n)]
 
-    # ---- K3b/K4 matrix + filter: rows are independent -> each rank builds the rows of its hash share ----
-    e = t.start("matrix")
-    cm = engine.build_matrix(dump_list, labels, nparts=world, part=rank)
-    t.stop(e)
-    e = t.start("filter")
-    dm = engine.filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
-                              min_freq=min_freq, max_freq=max_freq)
-    t.stop(e)
-    n_union = len(cm)
-    del cm
+    # ---- K3b/K4 matrix + filter: rows are independent -> each rank builds the rows of its share ----------
+    if engine.can_pmatrix(dump_list):
+        # partitioned union + filter in shared memory (rank r: partitions p % world == r)
+        e = t.start("matrix")
+        dm, n_union = engine.pmatrix_filter(dump_list, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
+                                            min_freq=min_freq, max_freq=max_freq, nparts=world, part=rank)
+        t.stop(e)
+    else:
+        e = t.start("matrix")
+        cm = engine.build_matrix(dump_list, labels, nparts=world, part=rank)
+        t.stop(e)
+        e = t.start("filter")
+        dm = engine.filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
+                                  min_freq=min_freq, max_freq=max_freq)
+        t.stop(e)
+        n_union = len(cm)
+        del cm
     if world > 1:
         e = t.start("exchange")
         dm, n_union = exchange_rows(dm, n_union, dist, dev)
@@ -273,7 +301,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
 
     # ---- K9 map ----------------------------------------------------------------------------------------
     e = t.start("sigtable")
-    sig = engine.SigTable(sig_keys, sig_vals, k, track_hits=False)
+    sig = engine.SigTable(sig_keys, sig_vals, k, track_hits=False, S=nsg)
     t.stop(e)
     win_counts = {}
     for i in mine:

@@ -67,6 +67,53 @@ def test_union_matrix_matches_oracle():
     np.testing.assert_array_equal(cm.matrix.cpu().numpy()[order].astype(np.int64), mat)
 
 
+@pytest.mark.parametrize("k,lower,chr_len,min_freq", [(13, 2, 20000, 8), (17, 1, 60000, 20), (21, 3, 30000, 10)])
+def test_partitioned_union_filter_equals_plain_path(k, lower, chr_len, min_freq):
+    """spk_pmatrix_filter (shared-memory union + filter per hash partition, dumps indexed by
+    spk_pcount_canonical_ex with common partition bits) == spk_union_insert/matrix_fill/filter_* and the
+    oracle restatement of to_matrix + filter, bit for bit."""
+    from oracle import kmers, restate
+    from subphaser_b200 import engine
+    import spk_testutil as util
+    records, sgs = util.subgenome_genome(k, n_sg=3, chr_per_sg=2, chr_len=chr_len)
+    labels = [r[0] for r in records]
+    packed = []
+    for name, seq in records:
+        d, n = engine.to_device_bytes(util.fasta([(name, seq)]))
+        packed.append(engine.pack_fasta(d, n))
+    table = engine.CountTable(max(p.n_bases for p in packed), k, lower)
+    dumps = [engine.count_packed(p, k, lower, table=table) for p in packed]
+    assert engine.can_pmatrix(dumps)
+    # the partition index covers the dump exactly once
+    for d in dumps:
+        idx = d.pindex.cpu().numpy().astype(np.int64).reshape(-1, 2)
+        assert idx[:, 1].sum() == len(d)
+        nz = idx[idx[:, 1] > 0]
+        order = np.argsort(nz[:, 0])
+        assert np.array_equal(nz[order, 0], np.concatenate([[0], np.cumsum(nz[order, 1])[:-1]]))
+    kw = dict(min_fold=2, baseline=1, ratio=1, min_freq=min_freq, max_freq=10000)
+    cm = engine.build_matrix(dumps, labels)
+    want = engine.filter_matrix(cm, sgs, labels, want_fold_tots=True, **kw)
+    got, n_union = engine.pmatrix_filter(dumps, sgs, labels, want_fold_tots=True, **kw)
+    assert n_union == len(cm) and len(got) == len(want) > 0
+    assert got.n_fold_pass == want.n_fold_pass
+    np.testing.assert_array_equal(engine.u64_numpy(got.keys), engine.u64_numpy(want.keys))
+    assert got.norm.cpu().numpy().tobytes() == want.norm.cpu().numpy().tobytes()
+    np.testing.assert_array_equal(got.tot.cpu().numpy(), want.tot.cpu().numpy())
+    assert sorted(got.fold_tots.tolist()) == sorted(want.fold_tots.tolist())
+    # two "ranks": the row shards partition the result
+    parts = [engine.pmatrix_filter(dumps, sgs, labels, nparts=2, part=r, **kw) for r in range(2)]
+    assert parts[0][1] + parts[1][1] == n_union
+    both = np.sort(np.concatenate([engine.u64_numpy(p[0].keys) for p in parts]))
+    np.testing.assert_array_equal(both, engine.u64_numpy(want.keys))
+    # and the oracle
+    dumps_o = [kmers.count_fasta(util.fasta([r]), k, lower)[:2] for r in records]
+    allk, mat, lengths = restate.to_matrix(dumps_o)
+    okeys, onorm, otot, _ = restate.filter_matrix(allk, mat, lengths, labels, sgs, **kw)
+    np.testing.assert_array_equal(engine.u64_numpy(got.keys), okeys)
+    assert got.norm.cpu().numpy().tobytes() == onorm.tobytes()
+
+
 # ---- sort -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,bits", [(1, 8), (2, 64), (1000, 34), (2049, 64), (300000, 42), (1 << 20, 30)])
 def test_radix_sort(n, bits):
