@@ -165,7 +165,7 @@ int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts, uint64_t n
                     uint32_t part, void* stream);
 int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
                             const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
-                            const int32_t* d_grp_off, int n_groups, const int32_t* d_members,
+                            const int32_t* d_grp_off, int n_groups, const int32_t* d_members, int n_members,
                             double min_fold, int baseline, int by_count, double ratio,
                             double min_freq, double max_freq, uint8_t* d_flags, uint64_t* d_tot,
                             uint64_t* d_counters, void* stream);
@@ -188,7 +188,7 @@ int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint3
 int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
                        const uint32_t* const* d_pindex, int n, int pbits, uint32_t nparts, uint32_t part,
                        const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets, const int32_t* d_grp_off,
-                       int n_groups, const int32_t* d_members, double min_fold, int baseline, int by_count,
+                       int n_groups, const int32_t* d_members, int n_members, double min_fold, int baseline, int by_count,
                        double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
                        uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap, uint64_t* d_fold_tots,
                        uint64_t fold_cap, uint64_t* d_counters, void* stream);

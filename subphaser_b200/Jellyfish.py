@@ -68,13 +68,22 @@ def run_jellyfish_dumps(seqfiles, ncpu=4, **kargs):
     """Jellyfish.py:671-676.  Chromosomes are counted one after another on the current GPU (each count
     already fills the device); `ncpu` is accepted for compatibility."""
     dumpfiles = []
+    # one scratch table sized for the largest chromosome: every dump then uses the same hash partitions and
+    # carries a partition index, which is what JellyfishDumps.to_matrix/filter merge on chip
+    table = None
+    try:
+        sizes = [os.path.getsize(f) for f in seqfiles if isinstance(f, str) and not f.endswith(".gz")]
+        if len(sizes) == len(seqfiles) and sizes and "k" in kargs:
+            table = engine.CountTable(max(sizes), int(kargs["k"]), int(kargs.get("lower_count", 2)))
+    except (OSError, engine._lib.SpkError):
+        table = None
     for seqfile in seqfiles:
-        dumpfiles += [run_jellyfish_dump(seqfile, **kargs)]
+        dumpfiles += [run_jellyfish_dump(seqfile, _table=table, **kargs)]
     return dumpfiles
 
 
 def run_jellyfish_dump(seqfile, threads=4, k=17, prefix=None, lower_count=2, method="jellyfish",
-                       overwrite=False):
+                       overwrite=False, _table=None):
     """Jellyfish.py:681-704 without the shell-out.  Returns the dump path `<prefix>_<k>.fa`."""
     if isinstance(seqfile, (list, tuple, set)):
         files = list(seqfile)
@@ -109,14 +118,17 @@ def run_jellyfish_dump(seqfile, threads=4, k=17, prefix=None, lower_count=2, met
     d_ascii, nbytes = engine.to_device_bytes(buf)
     seq = engine.pack_fasta(d_ascii, nbytes, name=os.path.basename(_seqfile))
     del d_ascii
-    dump = engine.count_packed(seq, int(k), int(lower_count), histo_len=100002)
+    dump = engine.count_packed(seq, int(k), int(lower_count), table=_table, histo_len=100002)
     if len(files) == 1:
         _registry.put_seq(files[0], seq)
     _registry.put_dump(output, dump)
     keys, counts = dump.to_host()
+    extra = {}
+    if dump.pindex is not None:
+        extra = dict(pindex=dump.pindex.cpu().numpy(), pbits=np.int64(dump.pbits))
     np.savez(side, keys=keys, counts=counts, k=np.int64(k), lower_count=np.int64(lower_count),
              length=np.int64(dump.length), n_valid_kmers=np.int64(dump.n_valid_kmers),
-             n_distinct=np.int64(dump.n_distinct))
+             n_distinct=np.int64(dump.n_distinct), **extra)
     histo = dump.histo.cpu().numpy()
     with open("{}_{}.histo".format(prefix, k), "w") as f:
         for c in np.nonzero(histo)[0]:
@@ -139,12 +151,15 @@ def load_dump(dumpfile):
     if d is not None:
         return d
     engine.require_cuda()
+    pindex, pbits = None, 0
     side = dumpfile + SIDE_SUFFIX
     if os.path.exists(side):
         with np.load(side) as z:
             keys, counts, k = z["keys"], z["counts"], int(z["k"])
             length = int(z["length"])
             nv, nd = int(z["n_valid_kmers"]), int(z["n_distinct"])
+            if "pindex" in z.files:
+                pindex, pbits = z["pindex"], int(z["pbits"])
     else:
         keys, counts, k = _parse_text_dump(dumpfile)
         length = int(counts.sum(dtype=np.int64))
@@ -152,7 +167,8 @@ def load_dump(dumpfile):
     dev = engine._dev()
     dk = torch.from_numpy(keys.view(np.int64).copy()).to(dev)
     dc = torch.from_numpy(counts.view(np.int32).copy()).to(dev)
-    d = engine.KmerDump(dk, dc, k, length, nv, nd, os.path.basename(dumpfile))
+    dp = torch.from_numpy(np.ascontiguousarray(pindex).view(np.int32).copy()).to(dev) if pindex is not None else None
+    d = engine.KmerDump(dk, dc, k, length, nv, nd, os.path.basename(dumpfile), None, dp, pbits)
     _registry.put_dump(dumpfile, d)
     return d
 
@@ -176,7 +192,10 @@ class JellyfishDumps:
         for dumpfile in self.dumpfiles:
             logger.info("Loading " + dumpfile)
             dumps.append(load_dump(dumpfile))
-        cm = engine.build_matrix(dumps, self.labels)
+        if engine.can_pmatrix(dumps):      # dumps counted with common partition bits: no union table at all
+            cm = engine.LazyUnion(dumps, self.labels)
+        else:
+            cm = engine.build_matrix(dumps, self.labels)
         self.lengths = list(cm.lengths)
         return cm
 
@@ -209,14 +228,21 @@ class JellyfishDumps:
                 raise IndexError("list index out of range")
             if len(sg) > 32:
                 raise ValueError("more than 32 groups in one homoeologous set is not supported")
-        if not isinstance(d_mat, engine.CountMatrix):
+        if isinstance(d_mat, engine.LazyUnion):
+            dm, n_all = engine.pmatrix_filter(d_mat.dumps, sgs, list(self.labels), min_fold=min_fold,
+                                              baseline=baseline, ratio=ratio, min_freq=min_freq, max_freq=max_freq,
+                                              by_count=by_count, want_fold_tots=outfig is not None,
+                                              lengths=list(lengths))
+            d_mat._len = n_all
+        elif isinstance(d_mat, engine.CountMatrix):
+            if list(lengths) != list(d_mat.lengths):
+                d_mat = engine.CountMatrix(d_mat.matrix, d_mat.row_keys, lengths, d_mat.k, d_mat.labels)
+            n_all = len(d_mat)
+            dm = engine.filter_matrix(d_mat, sgs, list(self.labels), min_fold=min_fold, baseline=baseline,
+                                      ratio=ratio, min_freq=min_freq, max_freq=max_freq, by_count=by_count,
+                                      want_fold_tots=outfig is not None)
+        else:
             raise TypeError("d_mat must come from JellyfishDumps.to_matrix()")
-        if list(lengths) != list(d_mat.lengths):
-            d_mat = engine.CountMatrix(d_mat.matrix, d_mat.row_keys, lengths, d_mat.k, d_mat.labels)
-        n_all = len(d_mat)
-        dm = engine.filter_matrix(d_mat, sgs, list(self.labels), min_fold=min_fold, baseline=baseline,
-                                  ratio=ratio, min_freq=min_freq, max_freq=max_freq, by_count=by_count,
-                                  want_fold_tots=outfig is not None)
         remain = len(dm)
         # without outfig the reference gates on frequency first and only counts kept k-mers (:617,502)
         total = dm.n_fold_pass if outfig is not None else remain

@@ -34,14 +34,14 @@ SIGNATURES = {
     "spk_pcount_workspace_bytes_ex": (c_sz, [c_u64, c_i, c_i]),
     "spk_pcount_canonical_ex": (c_i, [c_p, c_p, c_u64, c_i, c_u32, c_p, c_sz, c_p, c_p, c_u64, c_p, c_p, c_u32,
                                       c_i, c_p, c_p]),
-    "spk_pmatrix_filter": (c_i, [c_p, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p, c_p, c_i, c_p, c_i, c_p, c_d, c_i, c_i,
+    "spk_pmatrix_filter": (c_i, [c_p, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_d, c_i, c_i,
                                  c_d, c_d, c_d, c_p, c_p, c_p, c_u64, c_p, c_u64, c_p, c_p]),
     "spk_table_scan_blocks": (c_i, []),
     "spk_table_stats": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u32, c_p]),
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),
     "spk_union_insert": (c_i, [c_p, c_u64, c_p, c_p, c_u64, c_p, c_p, c_u32, c_u32, c_p]),
     "spk_matrix_fill": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_u64, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p]),
-    "spk_filter_differential": (c_i, [c_p, c_u64, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_d, c_i, c_i,
+    "spk_filter_differential": (c_i, [c_p, c_u64, c_i, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_d, c_i, c_i,
                                       c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "spk_filter_select": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_p, c_u64, c_p]),
     "spk_filter_emit": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_p, c_p, c_p, c_p]),

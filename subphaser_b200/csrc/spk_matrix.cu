@@ -76,8 +76,11 @@ k_matrix_fill(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ co
 // One thread per matrix row.  Mirrors _filter_kmer (Jellyfish.py:611-648) with outfig set.
 __global__ void __launch_bounds__(MX_THREADS)
 k_filter(const uint32_t* __restrict__ matrix, uint64_t nrows, int ncol,
-         const uint64_t* __restrict__ lengths, FilterCfg cfg, uint8_t* __restrict__ flags,
+         const uint64_t* __restrict__ lengths_g, FilterCfg cfg_g, int n_groups, uint8_t* __restrict__ flags,
          uint64_t* __restrict__ tot_out, uint64_t* __restrict__ counters) {
+    extern __shared__ __align__(16) uint8_t s_cfg[];
+    const uint64_t* lengths;
+    const FilterCfg cfg = spk_filter_stage(cfg_g, n_groups, ncol, lengths_g, s_cfg, &lengths);
     uint64_t n_fold = 0, n_keep = 0;
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nrows;
          r += (uint64_t)gridDim.x * blockDim.x) {
@@ -242,7 +245,7 @@ extern "C" int spk_matrix_fill(const uint64_t* d_keys, const uint32_t* d_counts,
 extern "C" int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows, int ncol,
                                        const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
                                        const int32_t* d_grp_off, int n_groups,
-                                       const int32_t* d_members, double min_fold, int baseline,
+                                       const int32_t* d_members, int n_members, double min_fold, int baseline,
                                        int by_count, double ratio, double min_freq, double max_freq,
                                        uint8_t* d_flags, uint64_t* d_tot, uint64_t* d_counters,
                                        void* stream) {
@@ -254,9 +257,12 @@ extern "C" int spk_filter_differential(const uint32_t* d_matrix, uint64_t nrows,
     if (nrows == 0) return SPK_OK;
     SPK_CHECK_ARG(d_matrix, "null matrix");
     FilterCfg cfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio,
-                  min_freq, max_freq};
-    k_filter<<<grid_for(nrows), MX_THREADS, 0, (cudaStream_t)stream>>>(d_matrix, nrows, ncol, d_lengths,
-                                                                       cfg, d_flags, d_tot, d_counters);
+                  min_freq, max_freq, nullptr, 0, 0};
+    SPK_CHECK_ARG(n_members >= n_groups, "n_members must be the length of d_members");
+    const size_t smem = spk_filter_stage_bytes(n_sets, n_groups, n_members, ncol);   // configuration staged in smem
+    SPK_CHECK_ARG(smem <= 48 * 1024, "homoeolog configuration too large");
+    k_filter<<<grid_for(nrows), MX_THREADS, smem, (cudaStream_t)stream>>>(d_matrix, nrows, ncol, d_lengths,
+                                                                          cfg, n_groups, d_flags, d_tot, d_counters);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -16,6 +16,7 @@ namespace {
 
 constexpr int PM_THREADS = 256;
 constexpr int PM_MAX_COLS = 256;
+constexpr int PM_B = 4;              // dump entries in flight per thread
 
 struct PmArgs {
     const uint64_t* const* keys;      // [n] device pointers to the dump keys of every chromosome
@@ -26,6 +27,8 @@ struct PmArgs {
     uint32_t nparts, part;            // this call handles partitions p % nparts == part
     const uint64_t* lengths;
     FilterCfg cfg;
+    int n_groups;
+    int union_only;                   // 1: count the union rows only (no filter, nothing written)
     uint64_t* out_keys;               // surviving rows (flag bit 1), arbitrary order
     uint32_t* out_counts;             // [cap x n]
     uint64_t* out_tot;
@@ -46,12 +49,20 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
     uint32_t* s_cnt = (uint32_t*)(s_key + TS);                 // [TS x n]
     uint32_t* s_start = s_cnt + (size_t)TS * n;                // [n]   first entry of this partition
     uint32_t* s_off = s_start + n;                             // [n+1] prefix of entry counts
-    __shared__ uint32_t s_fail;
+    uint16_t* s_rows = (uint16_t*)(s_off + n + 2);             // [TS]  occupied slots of the current round
+    uint8_t* s_cfg = (uint8_t*)(s_rows + TS);                  // staged filter configuration (8-byte aligned)
+    __shared__ uint32_t s_fail, s_nrows;
+    const uint64_t* lengths = a.lengths;
+    FilterCfg cfg = a.cfg;
+    if (!a.union_only) cfg = spk_filter_stage(a.cfg, a.n_groups, n, a.lengths, s_cfg, &lengths);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     for (uint32_t i = tid; i < TS; i += PM_THREADS) s_key[i] = SPK_EMPTY_KEY;
     for (uint32_t i = tid; i < TS * (uint32_t)n; i += PM_THREADS) s_cnt[i] = 0;
-    if (tid == 0) s_fail = 0;
+    if (tid == 0) {
+        s_fail = 0;
+        s_nrows = 0;
+    }
     uint64_t n_union = 0, n_fold = 0, n_keep = 0;
     const uint64_t stride = (uint64_t)gridDim.x * a.nparts;
     uint64_t p = (uint64_t)blockIdx.x * a.nparts + a.part;
@@ -89,44 +100,66 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
         uint32_t rounds = 1;
         while ((uint64_t)E > (uint64_t)rounds * (TS - TS / 8)) rounds <<= 1;
         for (uint32_t rd = 0; rd < rounds; rd++) {
-            // ---- insert: (key, count of chromosome c) -> table row ----
-            int c = 0;
-            for (uint32_t e = tid; e < E; e += PM_THREADS) {
-                while (e >= s_off[c + 1]) c++;
-                const uint32_t i = s_start[c] + (e - s_off[c]);
-                const uint64_t key = __ldg(a.keys[c] + i);
-                const uint32_t h = pm_hash(key);
-                if (rounds > 1 && ((h >> 20) & (rounds - 1)) != rd) continue;
-                const uint32_t cnt = __ldg(a.counts[c] + i);
-                uint32_t s = h & TM;
-                bool done = false;
-                for (uint32_t pr = 0; pr < TS; pr++) {
-                    uint64_t cur = s_key[s];
-                    if (cur == SPK_EMPTY_KEY) {
-                        cur = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)SPK_EMPTY_KEY,
-                                        (unsigned long long)key);
-                        if (cur == SPK_EMPTY_KEY) cur = key;
+            // ---- insert: (key, count of chromosome c) -> table row.  Loads are issued in batches of PM_B per
+            //      thread before any of them is consumed (the entries of a partition are 2n short runs scattered
+            //      over the dumps: their DRAM latency must overlap) ----
+            for (uint32_t e0 = 0; e0 < E; e0 += PM_B * PM_THREADS) {
+                uint64_t key[PM_B];
+                uint32_t cnt[PM_B];
+                int col[PM_B];
+                int c = 0;
+#pragma unroll
+                for (int u = 0; u < PM_B; u++) {
+                    const uint32_t e = e0 + u * PM_THREADS + tid;
+                    col[u] = -1;
+                    if (e < E) {
+                        while (e >= s_off[c + 1]) c++;
+                        const uint32_t i = s_start[c] + (e - s_off[c]);
+                        key[u] = __ldg(a.keys[c] + i);
+                        cnt[u] = __ldg(a.counts[c] + i);
+                        col[u] = c;
                     }
-                    if (cur == key) {
-                        s_cnt[(size_t)s * n + c] = cnt;      // one entry per (k-mer, chromosome)
-                        done = true;
-                        break;
-                    }
-                    s = (s + 1) & TM;
                 }
-                if (!done) s_fail = 1;
+#pragma unroll
+                for (int u = 0; u < PM_B; u++) {
+                    if (col[u] < 0) continue;
+                    const uint32_t h = pm_hash(key[u]);
+                    if (rounds > 1 && ((h >> 20) & (rounds - 1)) != rd) continue;
+                    uint32_t s = h & TM;
+                    bool done = false;
+                    for (uint32_t pr = 0; pr < TS; pr++) {
+                        uint64_t cur = s_key[s];
+                        if (cur == SPK_EMPTY_KEY) {
+                            cur = atomicCAS((unsigned long long*)&s_key[s], (unsigned long long)SPK_EMPTY_KEY,
+                                            (unsigned long long)key[u]);
+                            if (cur == SPK_EMPTY_KEY) {
+                                cur = key[u];
+                                s_rows[atomicAdd(&s_nrows, 1u)] = (uint16_t)s;     // new row
+                            }
+                        }
+                        if (cur == key[u]) {
+                            s_cnt[(size_t)s * n + col[u]] = cnt[u];   // one entry per (k-mer, chromosome)
+                            done = true;
+                            break;
+                        }
+                        s = (s + 1) & TM;
+                    }
+                    if (!done) s_fail = 1;
+                }
             }
             __syncthreads();
-            // ---- filter every row, emit the survivors, clear the table ----
-            for (uint32_t s0 = 0; s0 < TS; s0 += PM_THREADS) {
-                const uint32_t s = s0 + tid;
-                const uint64_t key = s_key[s];
+            // ---- filter every row (dense list of occupied slots), emit the survivors, clear the table ----
+            const uint32_t nrows = s_nrows;
+            if (tid == 0) n_union += nrows;
+            for (uint32_t r0 = 0; r0 < nrows; r0 += PM_THREADS) {
+                const uint32_t r = r0 + tid;
+                const bool occ = r < nrows;
+                const uint32_t s = occ ? (uint32_t)s_rows[r] : 0u;
                 uint8_t fl = 0;
-                uint64_t tot = 0;
-                const bool occ = key != SPK_EMPTY_KEY;
+                uint64_t tot = 0, key = 0;
                 if (occ) {
-                    fl = spk_filter_row(s_cnt + (size_t)s * n, n, a.lengths, a.cfg, tot);
-                    n_union++;
+                    key = s_key[s];
+                    if (!a.union_only) fl = spk_filter_row(s_cnt + (size_t)s * n, n, lengths, cfg, tot);
                     n_fold += fl & 1;
                     n_keep += (fl >> 1) & 1;
                 }
@@ -158,6 +191,8 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
                 }
             }
             __syncthreads();
+            if (tid == 0) s_nrows = 0;
+            __syncthreads();
         }
     }
     n_union = spk_warp_sum_u64(n_union);
@@ -170,6 +205,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
     }
     __syncthreads();
     if (tid == 0 && s_fail) atomicAdd((unsigned long long*)&a.counters[3], 1ull);
+    (void)lengths;
 }
 
 uint32_t pm_table_slots(int n) {
@@ -185,16 +221,18 @@ uint32_t pm_table_slots(int n) {
 extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
                                   const uint32_t* const* d_pindex, int n, int pbits, uint32_t nparts, uint32_t part,
                                   const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets,
-                                  const int32_t* d_grp_off, int n_groups, const int32_t* d_members, double min_fold,
-                                  int baseline, int by_count, double ratio, double min_freq, double max_freq,
+                                  const int32_t* d_grp_off, int n_groups, const int32_t* d_members, int n_members,
+                                  double min_fold, int baseline, int by_count, double ratio, double min_freq,
+                                  double max_freq,
                                   uint64_t* d_out_keys, uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap,
                                   uint64_t* d_fold_tots, uint64_t fold_cap, uint64_t* d_counters, void* stream) {
-    SPK_CHECK_ARG(d_keys && d_counts && d_pindex && d_lengths && d_set_off && d_grp_off && d_members && d_counters,
-                  "null pointer");
+    SPK_CHECK_ARG(d_keys && d_counts && d_pindex && d_counters, "null pointer");
+    SPK_CHECK_ARG(n_sets == 0 || (d_lengths && d_set_off && d_grp_off && d_members), "null configuration");
     SPK_CHECK_ARG(n >= 1 && n <= PM_MAX_COLS, "1 <= n <= 256 chromosomes");
     SPK_CHECK_ARG(pbits >= 0 && pbits <= 30, "bad pbits");
     SPK_CHECK_ARG(nparts >= 1 && part < nparts, "bad partition");
-    SPK_CHECK_ARG(n_sets >= 1 && n_groups >= 1, "bad shape");
+    SPK_CHECK_ARG((n_sets >= 1 && n_groups >= 1 && n_members >= n_groups) || (n_sets == 0 && cap == 0),
+                  "bad shape (n_sets == 0 with cap == 0 counts the union only)");
     SPK_CHECK_ARG(baseline < MX_MAX_GROUPS_PER_SET && baseline >= -MX_MAX_GROUPS_PER_SET, "baseline out of range");
     SPK_CHECK_ARG(cap == 0 || (d_out_keys && d_out_counts && d_out_tot), "null output");
     cudaStream_t st = (cudaStream_t)stream;
@@ -208,7 +246,10 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     a.nparts = nparts;
     a.part = part;
     a.lengths = d_lengths;
-    a.cfg = FilterCfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio, min_freq, max_freq};
+    a.cfg = FilterCfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio, min_freq, max_freq,
+                      nullptr, 0, 0};
+    a.n_groups = n_groups;
+    a.union_only = (cap == 0 && !d_fold_tots && n_sets == 0) ? 1 : 0;
     a.out_keys = d_out_keys;
     a.out_counts = d_out_counts;
     a.out_tot = d_out_tot;
@@ -217,7 +258,10 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     a.fold_cap = d_fold_tots ? fold_cap : 0;
     a.counters = d_counters;
     a.tslots = pm_table_slots(n);
-    const size_t smem = (size_t)a.tslots * (8 + 4 * (size_t)n) + (size_t)(2 * n + 2) * 4;
+    size_t smem = (size_t)a.tslots * (8 + 4 * (size_t)n) + (size_t)(2 * n + 2) * 4 + (size_t)a.tslots * 2;
+    smem = (smem + 7) / 8 * 8;
+    if (!a.union_only) smem += spk_filter_stage_bytes(n_sets, n_groups, n_members, n);
+    SPK_CHECK_ARG(smem <= 200 * 1024, "homoeolog configuration too large");
     static size_t smem_set = 0;
     if (smem > smem_set) {
         SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -309,7 +309,7 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
     tot = _empty(max(U, 1), torch.int64)
     counters = _zeros(4, torch.int64)
     call("spk_filter_differential", _p(cm.matrix), U, n, _p(d_len), _p(d_set), len(set_off) - 1, _p(d_grp),
-         len(grp_off) - 1, _p(d_mem), float(min_fold), int(baseline), int(bool(by_count)), float(ratio),
+         len(grp_off) - 1, _p(d_mem), len(members), float(min_fold), int(baseline), int(bool(by_count)), float(ratio),
          float(min_freq), float(max_freq), _p(flags), _p(tot), _p(counters), st)
     n_fold, n_keep = (int(x) for x in counters[:2].cpu().tolist())
     scan = _empty(U + 2 + U // 8192 + 1, torch.int32)
@@ -337,6 +337,36 @@ def can_pmatrix(dumps):
             and len({d.pbits for d in dumps}) == 1 and os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain")
 
 
+def pmatrix_union_size(dumps):
+    """len(d_mat) of JellyfishDumps.to_matrix without building it: union rows counted per hash partition."""
+    require_cuda()
+    ptrs = torch.tensor([[d.keys.data_ptr() for d in dumps], [d.counts.data_ptr() for d in dumps],
+                         [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
+    counters = _zeros(8, torch.int64)
+    call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), len(dumps), dumps[0].pbits, 1, 0, None,
+         None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, None, 0, None, 0, _p(counters), _stream())
+    n_union, _, _, n_over = (int(x) for x in counters[:4].cpu().tolist())
+    if n_over:
+        raise OverflowError("partition table overflow in spk_pmatrix_filter")
+    return n_union
+
+
+class LazyUnion:
+    """d_mat of the partitioned path: the dumps themselves; the union is merged partition by partition inside
+    spk_pmatrix_filter and never materialised.  len() = number of distinct dumped k-mers (Jellyfish.py:417)."""
+
+    def __init__(self, dumps, labels=None):
+        self.dumps, self.labels = list(dumps), labels
+        self.lengths = [d.length for d in dumps]
+        self.k = dumps[0].k
+        self._len = None
+
+    def __len__(self):
+        if self._len is None:
+            self._len = pmatrix_union_size(self.dumps)
+        return self._len
+
+
 def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200, max_freq=10000,
                    by_count=False, want_fold_tots=False, nparts=1, part=0, lengths=None):
     """to_matrix + filter in one partition-by-partition pass (spk_pmatrix_filter) -> (DiffMatrix, n_union).
@@ -360,7 +390,7 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
         ocnt = _empty(cap * n, torch.int32).view(cap, n)
         ftot = _empty(fold_cap, torch.int64) if fold_cap else None
         call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), n, pbits, nparts, part, _p(d_len),
-             _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), float(min_fold), int(baseline),
+             _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), len(members), float(min_fold), int(baseline),
              int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt), _p(otot),
              cap, _p(ftot), fold_cap, _p(counters), st)
         n_union, n_fold, n_keep, n_over = (int(x) for x in counters[:4].cpu().tolist())
