@@ -175,23 +175,24 @@ int spk_filter_select(const uint64_t* d_row_keys, const uint8_t* d_flags, uint64
 int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint32_t* d_rows,
                     uint64_t m, int ncol, const uint64_t* d_lengths, double* d_out_norm,
                     uint64_t* d_out_tot, void* stream);
-/* spk_pmatrix_filter: JellyfishDumps.to_matrix + filter (Jellyfish.py:439-512,611-648) for dumps that carry a
- * partition index with a common `pbits` (spk_pcount_canonical_ex): the union of partition p over the n
- * chromosomes is merged in shared memory, every row goes through the same fp64 test as
- * spk_filter_differential, and only rows with min_freq <= tot <= max_freq that pass the fold test are
- * written: d_out_keys[i], d_out_tot[i], d_out_counts[i*n + c] (raw counts, arbitrary row order; rows beyond
- * `cap` are dropped).  d_keys / d_counts / d_pindex: device arrays of n device pointers.  nparts/part: only
- * partitions p % nparts == part (multi-GPU row sharding).  d_fold_tots (optional, uint64[fold_cap]): totals of
- * all fold-passing rows (the histogram of Jellyfish.py:499-511).  d_counters (uint64[8], overwritten):
- * [0] union rows (= len(d_mat)), [1] fold-passing rows, [2] kept rows, [3] table overflows (must be 0;
- * otherwise use the plain path), [4] rows written, [5] fold totals written. */
+/* spk_pmatrix_filter: JellyfishDumps.to_matrix + the first, integer stage of filter (Jellyfish.py:439-512,
+ * 611-648) for dumps that carry a partition index with a common `pbits` (spk_pcount_canonical_ex): the union
+ * of partition p over the n chromosomes is merged in shared memory and every row goes through the exact
+ * integer pre-screen of the differential test (a homoeologous set whose counts are all zero cannot pass the
+ * fold test; if too few sets remain to reach `ratio` the row is rejected).  The candidates (~2 % of a real
+ * union) are written as a compact count matrix d_out_keys[i], d_out_counts[i*n + c] (arbitrary row order; rows
+ * beyond `cap` are dropped) for spk_filter_differential / _select / _emit; every rejected row fails the fold
+ * test, so fold-pass and kept counts of the compact matrix are those of the whole union.
+ * d_keys / d_counts / d_pindex: device arrays of n device pointers.  nparts/part: only partitions
+ * p % nparts == part (multi-GPU row sharding).  n_sets == 0 with cap == 0: count the union rows only.
+ * d_counters (uint64[8], overwritten): [0] union rows (= len(d_mat)), [2] candidate rows, [3] table overflows
+ * (must be 0; otherwise use the plain path), [4] rows written. */
 int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
                        const uint32_t* const* d_pindex, int n, int pbits, uint32_t nparts, uint32_t part,
                        const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets, const int32_t* d_grp_off,
-                       int n_groups, const int32_t* d_members, int n_members, double min_fold, int baseline, int by_count,
-                       double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
-                       uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap, uint64_t* d_fold_tots,
-                       uint64_t fold_cap, uint64_t* d_counters, void* stream);
+                       int n_groups, const int32_t* d_members, int n_members, double min_fold, int baseline,
+                       int by_count, double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
+                       uint32_t* d_out_counts, uint64_t cap, uint64_t* d_counters, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).

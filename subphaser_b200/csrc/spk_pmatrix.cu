@@ -5,10 +5,13 @@
 // for dumps produced by spk_pcount_canonical_ex with a COMMON number of partition bits: partition p of
 // every chromosome holds exactly the k-mers u with (f(u) >> rbits) == p, and its dump entries are
 // contiguous (pindex).  So the union of partition p over the n chromosomes is a few hundred rows: they are
-// merged in a shared-memory table (key -> n counters), every row is put through the same fp64 test as
-// spk_filter_differential (spk_filter.cuh, -fmad=false) and only the surviving rows (typically ~2 %) are
-// written to HBM.  The multi-GB union table and the [U x n] matrix of the plain path (spk_matrix.cu:
-// ~6 random HBM accesses per dump entry) never exist; HBM sees one coalesced read of the dumps.
+// merged in a shared-memory table (key -> n counters) and every row goes through the exact integer
+// pre-screen of the differential test (spk_filter_prescreen: a row with too many all-zero homoeologous sets
+// cannot pass the fold test).  Only the candidates (typically ~2 % of the union) are written to HBM as a
+// compact count matrix, on which the ordinary filter kernels (spk_filter_differential ... spk_filter_emit)
+// then run at full occupancy — the fp64 work of a handful of candidates per partition would otherwise
+// serialise whole CTAs behind two or three active lanes.  The multi-GB union table and the [U x n] matrix
+// of the plain path (spk_matrix.cu: ~6 random HBM accesses per dump entry) never exist.
 #include "spk_common.cuh"
 #include "spk_filter.cuh"
 
@@ -29,13 +32,10 @@ struct PmArgs {
     FilterCfg cfg;
     int n_groups;
     int union_only;                   // 1: count the union rows only (no filter, nothing written)
-    uint64_t* out_keys;               // surviving rows (flag bit 1), arbitrary order
+    uint64_t* out_keys;               // candidate rows (integer pre-screen passed), arbitrary order
     uint32_t* out_counts;             // [cap x n]
-    uint64_t* out_tot;
     uint64_t cap;
-    uint64_t* fold_tots;              // optional: totals of every fold-passing row (histogram input)
-    uint64_t fold_cap;
-    uint64_t* counters;               // [0] union rows [1] fold-pass rows [2] kept rows [3] table overflows
+    uint64_t* counters;               // [0] union rows [2] candidate rows [3] table overflows [4] rows written
     uint32_t tslots;                  // table slots (power of two)
 };
 
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
         s_fail = 0;
         s_nrows = 0;
     }
-    uint64_t n_union = 0, n_fold = 0, n_keep = 0;
+    uint64_t n_union = 0, n_keep = 0;
     const uint64_t stride = (uint64_t)gridDim.x * a.nparts;
     uint64_t p = (uint64_t)blockIdx.x * a.nparts + a.part;
     // index of the CTA's next partition, prefetched while the current one is processed (threads c < n)
@@ -155,33 +155,21 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
                 const uint32_t r = r0 + tid;
                 const bool occ = r < nrows;
                 const uint32_t s = occ ? (uint32_t)s_rows[r] : 0u;
-                uint8_t fl = 0;
-                uint64_t tot = 0, key = 0;
+                bool cand = false;
+                uint64_t key = 0;
                 if (occ) {
                     key = s_key[s];
-                    if (!a.union_only) fl = spk_filter_row(s_cnt + (size_t)s * n, n, lengths, cfg, tot);
-                    n_fold += fl & 1;
-                    n_keep += (fl >> 1) & 1;
+                    if (!a.union_only) cand = spk_filter_prescreen(s_cnt + (size_t)s * n, cfg);
+                    n_keep += cand ? 1 : 0;
                 }
-                if (a.fold_tots) {
-                    const uint32_t bf = __ballot_sync(0xffffffffu, fl & 1);
-                    if (bf) {
-                        uint64_t wb = 0;
-                        if (lane == 0) wb = atomicAdd((unsigned long long*)&a.counters[5], (unsigned long long)__popc(bf));
-                        wb = __shfl_sync(0xffffffffu, wb, 0);
-                        const uint64_t at = wb + __popc(bf & ((1u << lane) - 1));
-                        if ((fl & 1) && at < a.fold_cap) a.fold_tots[at] = tot;
-                    }
-                }
-                const uint32_t bk = __ballot_sync(0xffffffffu, fl & 2);
+                const uint32_t bk = __ballot_sync(0xffffffffu, cand);
                 if (bk) {
                     uint64_t wb = 0;
                     if (lane == 0) wb = atomicAdd((unsigned long long*)&a.counters[4], (unsigned long long)__popc(bk));
                     wb = __shfl_sync(0xffffffffu, wb, 0);
                     const uint64_t at = wb + __popc(bk & ((1u << lane) - 1));
-                    if ((fl & 2) && at < a.cap) {
+                    if (cand && at < a.cap) {
                         a.out_keys[at] = key;
-                        a.out_tot[at] = tot;
                         for (int cc = 0; cc < n; cc++) a.out_counts[at * n + cc] = s_cnt[(size_t)s * n + cc];
                     }
                 }
@@ -196,11 +184,9 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
         }
     }
     n_union = spk_warp_sum_u64(n_union);
-    n_fold = spk_warp_sum_u64(n_fold);
     n_keep = spk_warp_sum_u64(n_keep);
     if (lane == 0) {
         if (n_union) atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)n_union);
-        if (n_fold) atomicAdd((unsigned long long*)&a.counters[1], (unsigned long long)n_fold);
         if (n_keep) atomicAdd((unsigned long long*)&a.counters[2], (unsigned long long)n_keep);
     }
     __syncthreads();
@@ -224,8 +210,8 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
                                   const int32_t* d_grp_off, int n_groups, const int32_t* d_members, int n_members,
                                   double min_fold, int baseline, int by_count, double ratio, double min_freq,
                                   double max_freq,
-                                  uint64_t* d_out_keys, uint32_t* d_out_counts, uint64_t* d_out_tot, uint64_t cap,
-                                  uint64_t* d_fold_tots, uint64_t fold_cap, uint64_t* d_counters, void* stream) {
+                                  uint64_t* d_out_keys, uint32_t* d_out_counts, uint64_t cap,
+                                  uint64_t* d_counters, void* stream) {
     SPK_CHECK_ARG(d_keys && d_counts && d_pindex && d_counters, "null pointer");
     SPK_CHECK_ARG(n_sets == 0 || (d_lengths && d_set_off && d_grp_off && d_members), "null configuration");
     SPK_CHECK_ARG(n >= 1 && n <= PM_MAX_COLS, "1 <= n <= 256 chromosomes");
@@ -234,7 +220,7 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     SPK_CHECK_ARG((n_sets >= 1 && n_groups >= 1 && n_members >= n_groups) || (n_sets == 0 && cap == 0),
                   "bad shape (n_sets == 0 with cap == 0 counts the union only)");
     SPK_CHECK_ARG(baseline < MX_MAX_GROUPS_PER_SET && baseline >= -MX_MAX_GROUPS_PER_SET, "baseline out of range");
-    SPK_CHECK_ARG(cap == 0 || (d_out_keys && d_out_counts && d_out_tot), "null output");
+    SPK_CHECK_ARG(cap == 0 || (d_out_keys && d_out_counts), "null output");
     cudaStream_t st = (cudaStream_t)stream;
     SPK_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(uint64_t), st));
     PmArgs a;
@@ -249,13 +235,10 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     a.cfg = FilterCfg{d_set_off, d_grp_off, d_members, n_sets, min_fold, baseline, by_count, ratio, min_freq, max_freq,
                       nullptr, 0, 0};
     a.n_groups = n_groups;
-    a.union_only = (cap == 0 && !d_fold_tots && n_sets == 0) ? 1 : 0;
+    a.union_only = (cap == 0 && n_sets == 0) ? 1 : 0;
     a.out_keys = d_out_keys;
     a.out_counts = d_out_counts;
-    a.out_tot = d_out_tot;
     a.cap = cap;
-    a.fold_tots = d_fold_tots;
-    a.fold_cap = d_fold_tots ? fold_cap : 0;
     a.counters = d_counters;
     a.tslots = pm_table_slots(n);
     size_t smem = (size_t)a.tslots * (8 + 4 * (size_t)n) + (size_t)(2 * n + 2) * 4 + (size_t)a.tslots * 2;

@@ -344,7 +344,7 @@ def pmatrix_union_size(dumps):
                          [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
     counters = _zeros(8, torch.int64)
     call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), len(dumps), dumps[0].pbits, 1, 0, None,
-         None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, None, 0, None, 0, _p(counters), _stream())
+         None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, 0, _p(counters), _stream())
     n_union, _, _, n_over = (int(x) for x in counters[:4].cpu().tolist())
     if n_over:
         raise OverflowError("partition table overflow in spk_pmatrix_filter")
@@ -383,30 +383,26 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
                          [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
     counters = _zeros(8, torch.int64)
     total = sum(len(d) for d in dumps)
-    cap = max(total // (64 * nparts), 1 << 16)          # survivors are a few % of the union; grown on demand
-    fold_cap = 0
+    cap = max(total // (16 * nparts), 1 << 16)          # candidates are a few % of the union; grown on demand
     while True:
-        okeys, otot = _empty(cap, torch.int64), _empty(cap, torch.int64)
+        okeys = _empty(cap, torch.int64)
         ocnt = _empty(cap * n, torch.int32).view(cap, n)
-        ftot = _empty(fold_cap, torch.int64) if fold_cap else None
         call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), n, pbits, nparts, part, _p(d_len),
-             _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), len(members), float(min_fold), int(baseline),
-             int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt), _p(otot),
-             cap, _p(ftot), fold_cap, _p(counters), st)
-        n_union, n_fold, n_keep, n_over = (int(x) for x in counters[:4].cpu().tolist())
+             _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), len(members), float(min_fold),
+             int(baseline), int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt),
+             cap, _p(counters), st)
+        n_union, _, n_cand, n_over = (int(x) for x in counters[:4].cpu().tolist())
         if n_over:
             raise OverflowError("partition table overflow in spk_pmatrix_filter")
-        if n_keep <= cap and (not want_fold_tots or n_fold <= fold_cap):
+        if n_cand <= cap:
             break
-        cap = max(cap, n_keep)
-        fold_cap = n_fold if want_fold_tots else 0
-    cm = CountMatrix(ocnt[:n_keep], okeys[:n_keep], lengths, k, labels)
+        del okeys, ocnt
+        cap = n_cand
+    # the compact candidate matrix goes through the ordinary filter kernels (full occupancy); rows rejected
+    # by the pre-screen all fail the fold test, so its counters are those of the whole union
+    cm = CountMatrix(ocnt[:n_cand], okeys[:n_cand], lengths, k, labels)
     dm = filter_matrix(cm, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio, min_freq=min_freq,
-                       max_freq=max_freq, by_count=by_count)       # sort by k-mer + normalise (every row passes again)
-    assert len(dm) == n_keep
-    dm.n_fold_pass = n_fold
-    if want_fold_tots:
-        dm.fold_tots = ftot[:n_fold].cpu().numpy() if n_fold else np.zeros(0, np.int64)
+                       max_freq=max_freq, by_count=by_count, want_fold_tots=want_fold_tots)
     return dm, n_union
 
 
