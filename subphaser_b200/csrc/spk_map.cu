@@ -342,8 +342,9 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
 
         // bucket lookups in batches of QB independent 16/32-byte loads (issued before any is consumed)
         uint32_t hm = 0;              // bit j: position j hit
+        uint32_t rare = 0;            // bit j: position j needs the out-of-line path (stash probe / hit flag)
         uint64_t sgp[2] = {0, 0};     // subgenome id of hit j, 8 bits each
-        constexpr int QB = S16 ? 8 : 4;
+        constexpr int QB = 4;
 #pragma unroll
         for (int j0 = 0; j0 < SPK_KMERS_PER_THREAD; j0 += QB) {
             QtBucket<S16> bk[QB];
@@ -361,25 +362,43 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                 const int j = j0 + jj;
                 int at = 0;
                 bool over;
-                int sg = bk[jj].match(qv[jj], (uint32_t)S, at, over);
+                const int sg = bk[jj].match(qv[jj], (uint32_t)S, at, over);
                 const bool okj = (okmask >> j) & 1u;
-                if (okj && ((sg < 0 && over) || (sg >= 0 && a.hit_flags))) {   // rare / logging-only paths
-                    uint64_t where;
-                    if (sg < 0) {
-                        uint64_t sl = 0;
-                        sg = qt_stash_lookup(qa, key[j], sl);
-                        where = ((uint64_t)QT_SLOTS << qa.bbits) + sl;
-                    } else {
-                        const uint64_t h = qa.mx.fwd_light(key[j]);
-                        where = ((qa.mx.rbits >= 64) ? 0ull : (h >> qa.mx.rbits)) * QT_SLOTS + at;
-                    }
-                    if (sg >= 0 && a.hit_flags && !a.hit_flags[where]) a.hit_flags[where] = 1;
-                }
                 if (okj && sg >= 0) {
                     hm |= 1u << j;
                     sgp[j >> 3] |= (uint64_t)sg << (8 * (j & 7));
                 }
+                if (okj && ((sg < 0 && over) || (sg >= 0 && a.hit_flags != nullptr))) rare |= 1u << j;
             }
+        }
+        // out-of-line (not unrolled): the bucket overflowed at build time and the key may sit in the stash, or the
+        // caller wants to know WHICH table entries were hit (the "mapped k-mers" log line of Seqs.py:109-117).
+        // The k-mer is recomputed from the tile instead of indexing key[] dynamically (no local memory).
+        while (rare) {
+            const int j = __ffs(rare) - 1;
+            rare &= rare - 1;
+            const uint64_t kj = spk_kmer_at(sm.packed[buf], tid * SPK_KMERS_PER_THREAD + j, kp);
+            const uint64_t h = qa.mx.fwd_light(kj);
+            const uint64_t b = (qa.mx.rbits >= 64) ? 0ull : (h >> qa.mx.rbits);
+            uint64_t where = 0;
+            int sg = -1;
+            if ((hm >> j) & 1u) {                       // bucket hit: find the slot again (flag bookkeeping only)
+                QtBucket<S16> bq;
+                bq.load(qa.buckets, (uint32_t)b);
+                int at = 0;
+                bool over;
+                sg = bq.match((uint32_t)((h & rmask) << qa.sgbits), (uint32_t)S, at, over);
+                where = b * QT_SLOTS + at;
+            } else {
+                uint64_t sl = 0;
+                sg = qt_stash_lookup(qa, kj, sl);
+                where = ((uint64_t)QT_SLOTS << qa.bbits) + sl;
+                if (sg >= 0) {
+                    hm |= 1u << j;
+                    sgp[j >> 3] |= (uint64_t)sg << (8 * (j & 7));
+                }
+            }
+            if (sg >= 0 && a.hit_flags && !a.hit_flags[where]) a.hit_flags[where] = 1;
         }
         n_hit += __popc(hm);
 
@@ -424,17 +443,16 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                     }
             }
         } else {
-#pragma unroll
-            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
-                if ((hm >> j) & 1u) {
-                    const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
-                    const uint64_t line = bin + chk;
-                    const uint64_t rel = line - line0;
-                    if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
-                    else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
-                }
-                if (++brem == a.bin_size) { brem = 0; bin++; }
-                if (a.chunk_size && ++crem == a.chunk_size) { crem = 0; chk++; }
+            // a bin / chunk border inside the warp's 512 positions (or S > 4): per-hit adds, line by division
+            uint32_t m = hm;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
+                const uint64_t line = line_of(pos0 + j, k, a.bin_size, a.chunk_size);
+                const uint64_t rel = line - line0;
+                if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
+                else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
             }
         }
         __syncthreads();
@@ -578,12 +596,15 @@ extern "C" int spk_qtable_plan(uint64_t n_keys, int k, int S, int* slot_bits, in
     SPK_CHECK_ARG(slot_bits && bucket_bits, "null pointer");
     SPK_CHECK_ARG(k >= 1 && k <= 32 && S >= 1 && S <= MP_MAX_S, "bad k or S");
     const int sgbits = qt_sgbits(S);
-    int bn = 4;                                        // mean occupancy <= 3.5 of 7 entry slots
-    while (bn < 40 && (double)n_keys / (double)(1ull << bn) > 3.5) bn++;
+    // mean occupancy <= 1.75 of 7 entry slots: a bucket overflows (-> stash probe, a divergent dependent load for
+    // every later lookup of that bucket) with probability 3e-4; at 3.5 it was 1.6 % of the buckets, i.e. ~40 %
+    // of the warp-wide lookups had a lane in the slow path
+    int bn = 4;
+    while (bn < 40 && (double)n_keys / (double)(1ull << bn) > 1.75) bn++;
     if (bn > 2 * k) bn = 2 * k;
     int b16 = bn;
     if (2 * k + sgbits - 16 > b16) b16 = 2 * k + sgbits - 16;
-    if (b16 <= 2 * k && b16 <= 21) {                   // <= 32 MB
+    if (b16 <= 2 * k && b16 <= 22) {                   // <= 64 MB
         *slot_bits = 16;
         *bucket_bits = b16;
         return SPK_OK;

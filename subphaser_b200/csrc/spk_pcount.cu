@@ -741,6 +741,191 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
     }
 }
 
+// ---- phase 2, 32-bit remainders (rbits <= 31: every practical k / chromosome size) --------------------------
+// Same contract as k_part_count<false>, leaner instruction stream: keys and counts live in separate 32-bit
+// arrays, an insert is `old = CAS(key[s], EMPTY, r); if (old == EMPTY || old == r) count[s]++` — the same
+// straight-line code for a new key and for a hit (the 64-bit-slot version diverged on that, and about half of
+// the k-mers of a chromosome are new keys) — and there is no occupied-slot list: the dump is two vectorised
+// (128-bit) sweeps over the 8192 slots, one to size the partition's dump, one to write and clear.
+constexpr uint32_t PC_EMPTY32 = 0xffffffffu;
+
+__global__ void __launch_bounds__(PC_THREADS, 3)
+k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
+               CountOut o) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint32_t* s_key = (uint32_t*)s_raw;
+    uint32_t* s_cnt = s_key + PC_SLOTS;
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint64_t s_red[4][PC_THREADS / 32];
+    __shared__ uint32_t s_wtot[PC_THREADS / 32];
+    __shared__ uint64_t s_base;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    uint64_t distinct = 0, nge = 0, sumge = 0, sumall = 0, n_fail = 0;
+    uint32_t h1 = 0, h2 = 0;
+    if (o.histo) s_hist[tid] = 0;
+    constexpr uint32_t TMASK = PC_SLOTS - 1;
+    constexpr int SWEEP = PC_SLOTS / (PC_THREADS * 4);   // uint4 loads per thread per sweep (8)
+    for (uint32_t i = tid; i < PC_SLOTS; i += PC_THREADS) {
+        s_key[i] = PC_EMPTY32;
+        s_cnt[i] = 0;
+    }
+    __syncthreads();
+
+    auto insert = [&](uint32_t r) {
+        uint32_t s = r & TMASK;        // r = low bits of the mixer output: already uniform
+        uint32_t probes = 0;
+        while (true) {
+            const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
+            if (old == PC_EMPTY32 || old == r) {
+                atomicAdd(&s_cnt[s], 1u);
+                break;
+            }
+            s = (s + 1) & TMASK;
+            if (++probes >= PC_SLOTS) {
+                n_fail++;
+                break;
+            }
+        }
+    };
+
+    constexpr int PC_PF = 16;
+    const uint64_t G = gridDim.x;
+    uint64_t p = blockIdx.x;
+    uint32_t beg = 0, end = 0, nbeg = 0, nend = 0;
+    if (p < P) { beg = pstart[p]; end = pstart[p + 1]; }
+    if (p + G < P) { nbeg = pstart[p + G]; nend = pstart[p + G + 1]; }
+    uint32_t cur[PC_PF];
+#pragma unroll
+    for (int u = 0; u < PC_PF; u++) {
+        const uint32_t i = beg + u * PC_THREADS + tid;
+        cur[u] = i < end ? __ldcs(buf + i) : 0;
+    }
+    for (; p < P; p += G) {
+        uint32_t nxt[PC_PF];
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++) {
+            const uint32_t i = nbeg + u * PC_THREADS + tid;
+            nxt[u] = i < nend ? __ldcs(buf + i) : 0;
+        }
+        uint32_t nnbeg = 0, nnend = 0;
+        if (p + 2 * G < P) { nnbeg = pstart[p + 2 * G]; nnend = pstart[p + 2 * G + 1]; }
+        // ---- insert ----
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++)
+            if (beg + u * PC_THREADS + tid < end) insert(cur[u]);
+        for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
+            uint32_t t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = base + u * PC_THREADS + tid;
+                t[u] = i < end ? __ldcs(buf + i) : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (base + u * PC_THREADS + tid < end) insert(t[u]);
+        }
+        __syncthreads();
+        // ---- sweep 1: entries this thread will dump, distinct keys ----
+        uint32_t myk = 0, myocc = 0;
+#pragma unroll
+        for (int i = 0; i < SWEEP; i++) {
+            const uint4 c = *reinterpret_cast<const uint4*>(s_cnt + (i * PC_THREADS + tid) * 4);
+            myk += (c.x >= o.lower) + (c.y >= o.lower) + (c.z >= o.lower) + (c.w >= o.lower);
+            myocc += (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
+        }
+        distinct += myocc;
+        uint32_t incl = myk;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < PC_THREADS / 32; w++) {
+            const uint32_t t = s_wtot[w];
+            before += (w < warp) ? t : 0u;
+            total += t;
+        }
+        if (tid == 0) {
+            const uint64_t base = total ? atomicAdd((unsigned long long*)o.cursor, (unsigned long long)total) : 0ull;
+            s_base = base;
+            if (o.pindex) {
+                o.pindex[2 * p] = (uint32_t)base;
+                o.pindex[2 * p + 1] = total;
+            }
+            sumall += end - beg;
+        }
+        __syncthreads();
+        // ---- sweep 2: histogram, write the dump, clear ----
+        uint64_t at = s_base + before + (incl - myk);
+#pragma unroll
+        for (int i = 0; i < SWEEP; i++) {
+            const uint32_t idx = (i * PC_THREADS + tid) * 4;
+            const uint4 c = *reinterpret_cast<const uint4*>(s_cnt + idx);
+            if ((c.x | c.y | c.z | c.w) == 0) continue;
+            const uint4 kk = *reinterpret_cast<const uint4*>(s_key + idx);
+            const uint32_t cs[4] = {c.x, c.y, c.z, c.w}, ks[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t cnt = cs[e];
+                if (cnt == 0) continue;
+                if (o.histo) {
+                    const uint32_t b = cnt < o.histo_len - 1 ? cnt : o.histo_len - 1;
+                    if (b == 1) h1++;
+                    else if (b == 2) h2++;
+                    else if (b < 256) atomicAdd(&s_hist[b], 1u);
+                    else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
+                }
+                if (cnt >= o.lower) {
+                    nge++;
+                    sumge += cnt;
+                    if (at < o.cap) {
+                        o.keys[at] = mx.inv((p << mx.rbits) | (uint64_t)ks[e]);
+                        o.counts[at] = cnt;
+                    }
+                    at++;
+                }
+            }
+            *reinterpret_cast<uint4*>(s_key + idx) = make_uint4(PC_EMPTY32, PC_EMPTY32, PC_EMPTY32, PC_EMPTY32);
+            *reinterpret_cast<uint4*>(s_cnt + idx) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++) cur[u] = nxt[u];
+        beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
+    }
+    // ---- per-CTA totals ----
+    if (o.histo) {
+        h1 = spk_warp_sum_u32(h1);
+        h2 = spk_warp_sum_u32(h2);
+        if (lane == 0) {
+            if (h1) atomicAdd(&s_hist[1], h1);
+            if (h2) atomicAdd(&s_hist[2], h2);
+        }
+        __syncthreads();
+        if ((uint32_t)tid < o.histo_len && s_hist[tid])
+            atomicAdd((unsigned long long*)&o.histo[tid], (unsigned long long)s_hist[tid]);
+    }
+    uint64_t v[4] = {distinct, nge, sumge, sumall};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        v[q] = spk_warp_sum_u64(v[q]);
+        if (lane == 0) s_red[q][warp] = v[q];
+    }
+    n_fail = spk_warp_sum_u64(n_fail);
+    if (lane == 0 && n_fail) atomicAdd((unsigned long long*)&o.stats[1], (unsigned long long)n_fail);
+    __syncthreads();
+    if (tid < 4) {
+        uint64_t t = 0;
+        for (int w = 0; w < PC_THREADS / 32; w++) t += s_red[tid][w];
+        if (t) atomicAdd((unsigned long long*)&o.stats[4 + tid], (unsigned long long)t);
+    }
+}
+
 template <bool ENT64>
 int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lower, char* ws, uint64_t* d_keys,
              uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo, uint32_t histo_len,
@@ -815,7 +1000,17 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
     }
     CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower, d_pindex};
     const unsigned cgrid = (unsigned)min((uint64_t)sms * (ENT64 ? 2 : 3), pl.P);
-    k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
+    const char* v1 = getenv("SPK_PCOUNT_DUMP");        // "list": the 64-bit-slot kernel with the occupied-slot list
+    if (!ENT64 && pl.mx.rbits <= 31 && lower >= 1 && !(v1 && v1[0] == 'l')) {
+        static bool attr32 = false;
+        if (!attr32) {
+            SPK_CUDA(cudaFuncSetAttribute(k_part_count32, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8));
+            attr32 = true;
+        }
+        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o);
+    } else {
+        k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
+    }
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
