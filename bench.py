@@ -244,7 +244,7 @@ def main():
     value = n_kmers * args.steps / secs
     n_windows = res["n_windows"]
 
-    # roofline of the dominant kernel (k_count_canonical), live CUDA-event time on the launching stream
+    # roofline of the dominant kernel family (the partitioned counter), live CUDA-event time on the launching stream
     count_s = stage_ms.get("count", 0.0) / 1e3
     cs = torch.tensor([count_s, float(res["n_kmers_local"] * args.steps)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -259,7 +259,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm",
-                "kernel": "spk_pcount_canonical = k_part_pass<hist> + k_scatter_l1 + k_scatter_l2 + k_part_count "
+                "kernel": "spk_pcount_canonical_ex = k_hist1 + k_scatter_l1 + k_scatter_l2 + k_part_count32 "
                           "(one call per chromosome)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -310,8 +310,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(args, plan, cfg), "kmers_per_step": n_kmers,
-                       "windows_per_step": n_windows, "l2_policy": "inputs larger than L2 (5.3 GB packed sequence, "
-                       "multi-GB hash table per chromosome)", "parallelism": "chromosomes sharded over %d GPU(s), LPT" % world},
+                       "windows_per_step": n_windows, "l2_policy": "inputs larger than L2 (14.4 GB FASTA, 5.3 GB packed "
+                       "sequence, 2 x 2.7 GB partition streams per chromosome)",
+                       "parallelism": "chromosomes sharded over %d GPU(s), LPT" % world},
             "windows_per_s": n_windows * args.steps / win_s if win_s > 0 else None,
             "stage_ms_per_step": {k_: v / args.steps for k_, v in sorted(stage_ms.items())},
             "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],

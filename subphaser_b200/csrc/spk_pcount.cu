@@ -742,12 +742,33 @@ k_part_count(const void* __restrict__ buf, const uint32_t* __restrict__ pstart, 
 }
 
 // ---- phase 2, 32-bit remainders (rbits <= 31: every practical k / chromosome size) --------------------------
-// Same contract as k_part_count<false>, leaner instruction stream: keys and counts live in separate 32-bit
-// arrays, an insert is `old = CAS(key[s], EMPTY, r); if (old == EMPTY || old == r) count[s]++` — the same
-// straight-line code for a new key and for a hit (the 64-bit-slot version diverged on that, and about half of
-// the k-mers of a chromosome are new keys) — and there is no occupied-slot list: the dump is two vectorised
-// (128-bit) sweeps over the 8192 slots, one to size the partition's dump, one to write and clear.
+// Same contract as k_part_count<false>, leaner instruction stream (the 64-bit-slot kernel spent ~5 warp
+// instructions per k-mer, half of them in divergent probe loops, and stalled on instruction fetch):
+//  * keys and counts are separate 32-bit arrays; the FIRST probe of every entry is straight-line code —
+//    `old = CAS(key[s], EMPTY, r); if (old == EMPTY || old == r) c = count[s]++` — identical for a new key and
+//    a hit, no loop, no divergence; the ~20 % of entries whose home slot holds another key go to a
+//    shared-memory retry queue and are probed afterwards by all lanes together;
+//  * distinct keys and dump size are counted where they happen (old == EMPTY; the add that makes a count
+//    reach lower_count), so there is no sizing pass: one reservation per partition, then ONE 128-bit sweep
+//    over the 8192 slots that histograms, writes the kept entries (contiguous per partition) and clears.
 constexpr uint32_t PC_EMPTY32 = 0xffffffffu;
+constexpr int PC_RETRY = 2048;          // retry-queue capacity (entries beyond it probe inline)
+
+// full linear probing from the slot after home (out of line: rare in the first-probe loop, dense in the drain)
+// -> bit 0: created the key, bit 1: its count reached `lower`, bit 2: table full
+__device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cnt, uint32_t r, uint32_t lower) {
+    constexpr uint32_t TMASK = PC_SLOTS - 1;
+    uint32_t s = ((r & TMASK) + 1) & TMASK;
+    for (uint32_t probes = 1; probes < PC_SLOTS; probes++) {
+        const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
+        if (old == PC_EMPTY32 || old == r) {
+            const uint32_t c = atomicAdd(&s_cnt[s], 1u);
+            return ((old == PC_EMPTY32) ? 1u : 0u) | ((c + 1 == lower) ? 2u : 0u);
+        }
+        s = (s + 1) & TMASK;
+    }
+    return 4u;
+}
 
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
@@ -755,9 +776,10 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint32_t* s_key = (uint32_t*)s_raw;
     uint32_t* s_cnt = s_key + PC_SLOTS;
+    uint32_t* s_q = s_cnt + PC_SLOTS;                    // [PC_RETRY]
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_red[4][PC_THREADS / 32];
-    __shared__ uint32_t s_wtot[PC_THREADS / 32];
+    __shared__ uint32_t s_nq, s_nkeep, s_ndist, s_wr;
     __shared__ uint64_t s_base;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -770,22 +792,39 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         s_key[i] = PC_EMPTY32;
         s_cnt[i] = 0;
     }
+    if (tid == 0) {
+        s_nq = 0;
+        s_nkeep = 0;
+        s_ndist = 0;
+        s_wr = 0;
+    }
     __syncthreads();
+    const uint32_t lower = o.lower;
+    uint32_t my_new = 0, my_keep = 0;    // per partition: keys created / counts that reached `lower` by this thread
 
+    // first probe only; false: the home slot belongs to another key
+    auto try_home = [&](uint32_t r) -> bool {
+        const uint32_t s = r & TMASK;                    // r = low bits of the mixer output: already uniform
+        const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
+        if (old == PC_EMPTY32 || old == r) {
+            const uint32_t c = atomicAdd(&s_cnt[s], 1u);
+            my_new += (old == PC_EMPTY32) ? 1u : 0u;
+            my_keep += (c + 1 == lower) ? 1u : 0u;
+            return true;
+        }
+        return false;
+    };
+    auto probe_rest = [&](uint32_t r) {
+        const uint32_t f = pc32_probe_rest(s_key, s_cnt, r, lower);
+        my_new += f & 1u;
+        my_keep += (f >> 1) & 1u;
+        n_fail += (f >> 2) & 1u;
+    };
     auto insert = [&](uint32_t r) {
-        uint32_t s = r & TMASK;        // r = low bits of the mixer output: already uniform
-        uint32_t probes = 0;
-        while (true) {
-            const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
-            if (old == PC_EMPTY32 || old == r) {
-                atomicAdd(&s_cnt[s], 1u);
-                break;
-            }
-            s = (s + 1) & TMASK;
-            if (++probes >= PC_SLOTS) {
-                n_fail++;
-                break;
-            }
+        if (!try_home(r)) {
+            const uint32_t qi = atomicAdd(&s_nq, 1u);
+            if (qi < PC_RETRY) s_q[qi] = r;
+            else probe_rest(r);
         }
     };
 
@@ -810,10 +849,23 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         }
         uint32_t nnbeg = 0, nnend = 0;
         if (p + 2 * G < P) { nnbeg = pstart[p + 2 * G]; nnend = pstart[p + 2 * G + 1]; }
-        // ---- insert ----
+        // ---- insert, first probes (straight-line); failures are queued with one reservation per thread ----
+        uint32_t failm = 0;
 #pragma unroll
         for (int u = 0; u < PC_PF; u++)
-            if (beg + u * PC_THREADS + tid < end) insert(cur[u]);
+            if (beg + u * PC_THREADS + tid < end && !try_home(cur[u])) failm |= 1u << u;
+        if (failm) {
+            uint32_t qi = atomicAdd(&s_nq, (uint32_t)__popc(failm));
+            if (qi + __popc(failm) <= PC_RETRY) {
+#pragma unroll
+                for (int u = 0; u < PC_PF; u++)
+                    if ((failm >> u) & 1u) s_q[qi++] = cur[u];
+            } else {                                        // queue full (heavily colliding partition): probe inline
+#pragma unroll
+                for (int u = 0; u < PC_PF; u++)
+                    if ((failm >> u) & 1u) probe_rest(cur[u]);
+            }
+        }
         for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
             uint32_t t[4];
 #pragma unroll
@@ -826,72 +878,97 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
                 if (base + u * PC_THREADS + tid < end) insert(t[u]);
         }
         __syncthreads();
-        // ---- sweep 1: entries this thread will dump, distinct keys ----
-        uint32_t myk = 0, myocc = 0;
-#pragma unroll
-        for (int i = 0; i < SWEEP; i++) {
-            const uint4 c = *reinterpret_cast<const uint4*>(s_cnt + (i * PC_THREADS + tid) * 4);
-            myk += (c.x >= o.lower) + (c.y >= o.lower) + (c.z >= o.lower) + (c.w >= o.lower);
-            myocc += (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
+        // ---- insert, queued entries: all lanes probe together ----
+        const uint32_t nq = min(s_nq, (uint32_t)PC_RETRY);
+        for (uint32_t i = tid; i < nq; i += PC_THREADS) probe_rest(s_q[i]);
+        // ---- partition totals -> one reservation ----
+        my_new = spk_warp_sum_u32(my_new);
+        my_keep = spk_warp_sum_u32(my_keep);
+        if (lane == 0) {
+            if (my_new) atomicAdd(&s_ndist, my_new);
+            if (my_keep) atomicAdd(&s_nkeep, my_keep);
         }
-        distinct += myocc;
-        uint32_t incl = myk;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        if (lane == 31) s_wtot[warp] = incl;
+        my_new = my_keep = 0;
         __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < PC_THREADS / 32; w++) {
-            const uint32_t t = s_wtot[w];
-            before += (w < warp) ? t : 0u;
-            total += t;
-        }
         if (tid == 0) {
+            const uint32_t total = s_nkeep;
             const uint64_t base = total ? atomicAdd((unsigned long long*)o.cursor, (unsigned long long)total) : 0ull;
             s_base = base;
             if (o.pindex) {
                 o.pindex[2 * p] = (uint32_t)base;
                 o.pindex[2 * p + 1] = total;
             }
+            distinct += s_ndist;
             sumall += end - beg;
         }
         __syncthreads();
-        // ---- sweep 2: histogram, write the dump, clear ----
-        uint64_t at = s_base + before + (incl - myk);
-#pragma unroll
+        // ---- sweep: histogram, write the dump, clear ----
+        const uint64_t pbase = s_base;
+#pragma unroll 1
         for (int i = 0; i < SWEEP; i++) {
             const uint32_t idx = (i * PC_THREADS + tid) * 4;
             const uint4 c = *reinterpret_cast<const uint4*>(s_cnt + idx);
-            if ((c.x | c.y | c.z | c.w) == 0) continue;
+            const bool any = (c.x | c.y | c.z | c.w) != 0;
+            if (__ballot_sync(0xffffffffu, any) == 0) continue;          // warp-uniform: 128 empty slots
+            if (!any) continue;
             const uint4 kk = *reinterpret_cast<const uint4*>(s_key + idx);
+            *reinterpret_cast<uint4*>(s_key + idx) = make_uint4(PC_EMPTY32, PC_EMPTY32, PC_EMPTY32, PC_EMPTY32);
+            *reinterpret_cast<uint4*>(s_cnt + idx) = make_uint4(0u, 0u, 0u, 0u);
             const uint32_t cs[4] = {c.x, c.y, c.z, c.w}, ks[4] = {kk.x, kk.y, kk.z, kk.w};
+            if (o.histo) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const uint32_t cnt = cs[e];
-                if (cnt == 0) continue;
-                if (o.histo) {
+                for (int e = 0; e < 4; e++) {
+                    const uint32_t cnt = cs[e];
+                    if (cnt == 0) continue;
                     const uint32_t b = cnt < o.histo_len - 1 ? cnt : o.histo_len - 1;
                     if (b == 1) h1++;
                     else if (b == 2) h2++;
                     else if (b < 256) atomicAdd(&s_hist[b], 1u);
                     else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
                 }
-                if (cnt >= o.lower) {
-                    nge++;
-                    sumge += cnt;
-                    if (at < o.cap) {
-                        o.keys[at] = mx.inv((p << mx.rbits) | (uint64_t)ks[e]);
-                        o.counts[at] = cnt;
+            }
+            // kept entries are rare (a few per cent of the distinct keys): per-thread reservation in smem
+            const uint32_t km = (c.x >= lower ? 1u : 0u) | (c.y >= lower ? 2u : 0u) | (c.z >= lower ? 4u : 0u) |
+                                (c.w >= lower ? 8u : 0u);                 // lower >= 1: implies occupied
+            if (km) {
+                uint32_t pos = atomicAdd(&s_wr, (uint32_t)__popc(km));
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if ((km >> e) & 1u) {
+                        if (pos < PC_RETRY / 2) {            // staged (the retry queue is free by now): written below by all lanes
+                            s_q[2 * pos] = ks[e];
+                            s_q[2 * pos + 1] = cs[e];
+                        } else {
+                            nge++;
+                            sumge += cs[e];
+                            if (pbase + pos < o.cap) {
+                                o.keys[pbase + pos] = mx.inv((p << mx.rbits) | (uint64_t)ks[e]);
+                                o.counts[pbase + pos] = cs[e];
+                            }
+                        }
+                        pos++;
                     }
-                    at++;
+            }
+        }
+        __syncthreads();
+        {   // kept entries: f^-1 and the global stores with every lane busy (a lane-at-a-time version cost a third of the kernel)
+            const uint32_t nst = min(s_wr, (uint32_t)(PC_RETRY / 2));
+            for (uint32_t i = tid; i < nst; i += PC_THREADS) {
+                const uint32_t r = s_q[2 * i], cnt = s_q[2 * i + 1];
+                nge++;
+                sumge += cnt;
+                if (pbase + i < o.cap) {
+                    o.keys[pbase + i] = mx.inv((p << mx.rbits) | (uint64_t)r);
+                    o.counts[pbase + i] = cnt;
                 }
             }
-            *reinterpret_cast<uint4*>(s_key + idx) = make_uint4(PC_EMPTY32, PC_EMPTY32, PC_EMPTY32, PC_EMPTY32);
-            *reinterpret_cast<uint4*>(s_cnt + idx) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_nq = 0;
+            s_nkeep = 0;
+            s_ndist = 0;
+            s_wr = 0;
         }
         __syncthreads();
 #pragma unroll
@@ -1004,10 +1081,10 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
     if (!ENT64 && pl.mx.rbits <= 31 && lower >= 1 && !(v1 && v1[0] == 'l')) {
         static bool attr32 = false;
         if (!attr32) {
-            SPK_CUDA(cudaFuncSetAttribute(k_part_count32, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8));
+            SPK_CUDA(cudaFuncSetAttribute(k_part_count32, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8 + PC_RETRY * 4));
             attr32 = true;
         }
-        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o);
+        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o);
     } else {
         k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
     }

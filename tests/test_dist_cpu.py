@@ -43,6 +43,15 @@ def _worker(rank, world, port, q):
     ok = total == sum(100 * (r + 1) for r in range(world))
     for i in range(n):
         ok &= bool(torch.equal(out[i][0], full[i][0]) and torch.equal(out[i][1], full[i][1]) and out[i][2] == full[i][2])
+    # partition indices of the dumps travel with them (same partition bits on every rank)
+    pbits = 3
+    pidx_full = {i: torch.arange(2 << pbits, dtype=torch.int32) + 100 * i for i in range(n)}
+    pidx, pb = hotpath.exchange_pindex({i: pidx_full[i] for i in range(n) if owner[i] == rank}, n, owner, dist, dev, pbits)
+    ok &= pb == pbits and all(bool(torch.equal(pidx[i], pidx_full[i])) for i in range(n))
+    # ranks that disagree on the partition bits (or lack an index) fall back to the plain union on every rank
+    pidx2, pb2 = hotpath.exchange_pindex({i: pidx_full[i] for i in range(n) if owner[i] == rank}, n, owner, dist, dev,
+                                         pbits + rank)
+    ok &= pb2 == 0 and pidx2 == {}
     wins = {i: torch.full((i + 1, 3), i, dtype=torch.int64) for i in range(n) if owner[i] == rank}
     allw = hotpath.exchange_windows(wins, n, 3, owner, dist, dev)
     for i in range(n):
