@@ -179,6 +179,8 @@ def main():
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pg = dist
     engine.require_cuda()
@@ -314,7 +316,8 @@ def main():
                        "sequence, 2 x 2.7 GB partition streams per chromosome)",
                        "parallelism": "chromosomes sharded over %d GPU(s), LPT" % world},
             "windows_per_s": n_windows * args.steps / win_s if win_s > 0 else None,
-            "stage_ms_per_step": {k_: v / args.steps for k_, v in sorted(stage_ms.items())},
+            "stage_ms_per_step": {k_: v / args.steps for k_, v in sorted(stage_ms.items()) if not k_.startswith("_")},
+            "loop_ms_per_step": {k_[1:]: v / args.steps for k_, v in sorted(stage_ms.items()) if k_.startswith("_")},
             "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],
                         "n_windows": n_windows, "labels": res["labels_full"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

@@ -185,6 +185,7 @@ int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, const uint3
  * test, so fold-pass and kept counts of the compact matrix are those of the whole union.
  * d_keys / d_counts / d_pindex: device arrays of n device pointers.  nparts/part: only partitions
  * p % nparts == part (multi-GPU row sharding).  n_sets == 0 with cap == 0: count the union rows only.
+ * total_entries: sum of the dump sizes (sizes the shared-memory table so an average partition takes one round).
  * d_counters (uint64[8], overwritten): [0] union rows (= len(d_mat)), [2] candidate rows, [3] table overflows
  * (must be 0; otherwise use the plain path), [4] rows written. */
 int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_counts,
@@ -192,7 +193,8 @@ int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_c
                        const uint64_t* d_lengths, const int32_t* d_set_off, int n_sets, const int32_t* d_grp_off,
                        int n_groups, const int32_t* d_members, int n_members, double min_fold, int baseline,
                        int by_count, double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
-                       uint32_t* d_out_counts, uint64_t cap, uint64_t* d_counters, void* stream);
+                       uint32_t* d_out_counts, uint64_t cap, uint64_t total_entries, uint64_t* d_counters,
+                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).

@@ -184,9 +184,9 @@ class Cluster:
             return {chr: 0 for chr in self.chrs}
         if self._resample_idx is not None:
             idx = np.asarray(self._resample_idx, dtype=np.int32)
-        else:   # sklearn.utils.resample(replace=True): random_state.randint(0, M, size=n_samples)
-            idx = np.random.RandomState(self.seed).randint(0, M, size=(replicates, replicates)).astype(np.int32)
-        d_idx = torch.from_numpy(np.ascontiguousarray(idx)).to(engine._dev())
+            d_idx = torch.from_numpy(np.ascontiguousarray(idx)).to(engine._dev())
+        else:   # sklearn.utils.resample(replace=True): randint(0, M, size=n_samples) per replicate
+            d_idx = engine.resample_indices(M, replicates, self.seed)
         G = engine.gram_batched(self._Z, d_idx)
         labels, _ = engine.kmeans_gram(G, self.n_clusters, order=self._name_order(), n_init=10,
                                        max_iter=300, seed=self.seed + 1)

@@ -17,8 +17,8 @@
 
 namespace {
 
-constexpr int PM_THREADS = 256;
-constexpr int PM_MAX_COLS = 256;
+constexpr int PM_THREADS = 512;
+constexpr int PM_MAX_COLS = 512;
 constexpr int PM_B = 4;              // dump entries in flight per thread
 
 struct PmArgs {
@@ -41,7 +41,7 @@ struct PmArgs {
 
 __device__ __forceinline__ uint32_t pm_hash(uint64_t key) { return (uint32_t)(spk_hash64(key) >> 32); }
 
-__global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
+__global__ void __launch_bounds__(PM_THREADS, 1) k_pmatrix_filter(PmArgs a) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const int n = a.n;
     const uint32_t TS = a.tslots, TM = TS - 1;
@@ -194,11 +194,13 @@ __global__ void __launch_bounds__(PM_THREADS, 2) k_pmatrix_filter(PmArgs a) {
     (void)lengths;
 }
 
-uint32_t pm_table_slots(int n) {
-    // largest power of two whose table (8-byte key + n 4-byte counters per slot) stays under ~100 KB,
-    // so that two CTAs share an SM
-    uint32_t ts = 4096;
-    while (ts > 256 && (size_t)ts * (8 + 4 * (size_t)n) > 100 * 1024) ts >>= 1;
+uint32_t pm_table_slots(int n, double mean_entries) {
+    // smallest power of two that takes an average partition in ONE round (entries <= 7/8 of the slots), capped
+    // by shared memory: a slot is an 8-byte key + n 4-byte counters and the table must stay under ~190 KB
+    // (one 512-thread CTA per SM)
+    uint32_t ts = 256;
+    while (ts < 8192 && (double)ts * 0.875 < mean_entries * 1.05) ts <<= 1;
+    while (ts > 256 && (size_t)ts * (8 + 4 * (size_t)n) > 190 * 1024) ts >>= 1;
     return ts;
 }
 
@@ -211,10 +213,10 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
                                   double min_fold, int baseline, int by_count, double ratio, double min_freq,
                                   double max_freq,
                                   uint64_t* d_out_keys, uint32_t* d_out_counts, uint64_t cap,
-                                  uint64_t* d_counters, void* stream) {
+                                  uint64_t total_entries, uint64_t* d_counters, void* stream) {
     SPK_CHECK_ARG(d_keys && d_counts && d_pindex && d_counters, "null pointer");
     SPK_CHECK_ARG(n_sets == 0 || (d_lengths && d_set_off && d_grp_off && d_members), "null configuration");
-    SPK_CHECK_ARG(n >= 1 && n <= PM_MAX_COLS, "1 <= n <= 256 chromosomes");
+    SPK_CHECK_ARG(n >= 1 && n <= PM_MAX_COLS, "1 <= n <= 512 chromosomes");
     SPK_CHECK_ARG(pbits >= 0 && pbits <= 30, "bad pbits");
     SPK_CHECK_ARG(nparts >= 1 && part < nparts, "bad partition");
     SPK_CHECK_ARG((n_sets >= 1 && n_groups >= 1 && n_members >= n_groups) || (n_sets == 0 && cap == 0),
@@ -240,11 +242,11 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     a.out_counts = d_out_counts;
     a.cap = cap;
     a.counters = d_counters;
-    a.tslots = pm_table_slots(n);
+    a.tslots = pm_table_slots(n, (double)total_entries / (double)(1ull << pbits));
     size_t smem = (size_t)a.tslots * (8 + 4 * (size_t)n) + (size_t)(2 * n + 2) * 4 + (size_t)a.tslots * 2;
     smem = (smem + 7) / 8 * 8;
     if (!a.union_only) smem += spk_filter_stage_bytes(n_sets, n_groups, n_members, n);
-    SPK_CHECK_ARG(smem <= 200 * 1024, "homoeolog configuration too large");
+    SPK_CHECK_ARG(smem <= 220 * 1024, "homoeolog configuration too large");
     static size_t smem_set = 0;
     if (smem > smem_set) {
         SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -252,7 +254,7 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     }
     const uint64_t mine = (a.P + nparts - 1 - part) / nparts;
     if (mine == 0) return SPK_OK;
-    const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 2, mine);
+    const unsigned grid = (unsigned)min((uint64_t)spk_num_sms(), mine);
     k_pmatrix_filter<<<grid, PM_THREADS, smem, st>>>(a);
     SPK_LAUNCH_CHECK();
     return SPK_OK;

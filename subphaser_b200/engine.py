@@ -331,6 +331,9 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
     return DiffMatrix(keys, norm, otot, cm.k, labels, n_fold, fold_tots)
 
 
+_PM_CAP = {}
+
+
 def can_pmatrix(dumps):
     """True when every dump carries a partition index with the same partition bits."""
     return (len(dumps) > 0 and len(dumps) <= 256 and all(d.pindex is not None and d.pbits > 0 for d in dumps)
@@ -344,7 +347,8 @@ def pmatrix_union_size(dumps):
                          [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
     counters = _zeros(8, torch.int64)
     call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), len(dumps), dumps[0].pbits, 1, 0, None,
-         None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, 0, _p(counters), _stream())
+         None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, 0, sum(len(d) for d in dumps),
+         _p(counters), _stream())
     n_union, _, _, n_over = (int(x) for x in counters[:4].cpu().tolist())
     if n_over:
         raise OverflowError("partition table overflow in spk_pmatrix_filter")
@@ -384,20 +388,22 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
     counters = _zeros(8, torch.int64)
     total = sum(len(d) for d in dumps)
     cap = max(total // (16 * nparts), 1 << 16)          # candidates are a few % of the union; grown on demand
+    cap = max(cap, _PM_CAP.get((n, total // 1024), 0))   # what an earlier pass over the same dumps needed
     while True:
         okeys = _empty(cap, torch.int64)
         ocnt = _empty(cap * n, torch.int32).view(cap, n)
         call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), n, pbits, nparts, part, _p(d_len),
              _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), len(members), float(min_fold),
              int(baseline), int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt),
-             cap, _p(counters), st)
+             cap, total, _p(counters), st)
         n_union, _, n_cand, n_over = (int(x) for x in counters[:4].cpu().tolist())
         if n_over:
             raise OverflowError("partition table overflow in spk_pmatrix_filter")
         if n_cand <= cap:
             break
         del okeys, ocnt
-        cap = n_cand
+        cap = n_cand + n_cand // 16
+        _PM_CAP[(n, total // 1024)] = cap
     # the compact candidate matrix goes through the ordinary filter kernels (full occupancy); rows rejected
     # by the pre-screen all fail the fold test, so its counters are those of the whole union
     cm = CountMatrix(ocnt[:n_cand], okeys[:n_cand], lengths, k, labels)
@@ -424,6 +430,16 @@ def argsort_keys(keys, key_bits):
 # ----------------------------------------------------------------------------------------------------
 # K5-K8: cluster statistics
 # ----------------------------------------------------------------------------------------------------
+def resample_indices(M, R, seed):
+    """The bootstrap's resampling plan (sklearn.utils.resample(replace=True, n_samples=R), R times): int32 [R, R]
+    indices into the M k-mers, drawn on the device (the reference is unseeded, Cluster.py:90; drawing 10^6
+    numbers on the host and copying them cost more than the whole clustering)."""
+    require_cuda()
+    g = torch.Generator(device=_dev())
+    g.manual_seed(int(seed))
+    return torch.randint(0, int(M), (int(R), int(R)), generator=g, device=_dev(), dtype=torch.int32)
+
+
 def zscore_rows(X):
     """X float64 [M, n] device -> Z (Cluster.normalize_data on data.T, Cluster.py:76-80)."""
     require_cuda()

@@ -28,30 +28,46 @@ def lpt_assign(lengths, world):
     return owner
 
 
+def _gather_concat(parts, sizes, owner, n, dist, dev, dtype):
+    """parts: {chromosome index: 1-D tensor} owned by this rank; sizes[i]: its length on every rank.
+    One all_gather of the per-rank concatenation (padded to the longest) -> {i: view} for every chromosome."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    per_rank = [[i for i in range(n) if owner[i] == r] for r in range(world)]
+    tot = [sum(sizes[i] for i in per_rank[r]) for r in range(world)]
+    width = max(max(tot), 1)
+    send = torch.zeros(width, dtype=dtype, device=dev)
+    off = 0
+    for i in per_rank[rank]:
+        if sizes[i]:
+            send[off:off + sizes[i]] = parts[i]
+        off += sizes[i]
+    recv = torch.empty(world, width, dtype=dtype, device=dev)
+    dist.all_gather(list(recv.unbind(0)), send)
+    out = {}
+    for r in range(world):
+        off = 0
+        for i in per_rank[r]:
+            out[i] = recv[r, off:off + sizes[i]]
+            off += sizes[i]
+    return out
+
+
 def exchange_dumps(local, n, owner, dist, dev, n_kmers_local=0):
     """The one exchange step of the path: after it every rank holds every chromosome's dump.
     local: {chromosome index: (keys int64 tensor, counts int32 tensor, length)} for the chromosomes this
-    rank owns.  Sizes / lengths / k-mer totals travel in one all_reduce, the dumps by broadcast from
-    their owner.  Works on any backend (NCCL on device tensors; gloo on CPU tensors in the tests)."""
-    rank = dist.get_rank()
+    rank owns.  Sizes / lengths / k-mer totals travel in one all_reduce, the dumps in two all_gathers of the
+    per-rank concatenations (keys, counts) — 3 collectives instead of 2 per chromosome.  Works on any
+    backend (NCCL on device tensors; gloo on CPU tensors in the tests)."""
     meta = torch.zeros(n + 1, 2, dtype=torch.int64, device=dev)
     for i, (kk, cc, length) in local.items():
         meta[i, 0], meta[i, 1] = int(kk.numel()), int(length)
     meta[n, 0] = int(n_kmers_local)
     dist.all_reduce(meta)
     meta_h = meta.cpu().tolist()
-    out = {}
-    for i in range(n):
-        cnt, length = int(meta_h[i][0]), int(meta_h[i][1])
-        if owner[i] == rank:
-            kk, cc, _ = local[i]
-        else:
-            kk = torch.empty(cnt, dtype=torch.int64, device=dev)
-            cc = torch.empty(cnt, dtype=torch.int32, device=dev)
-        if cnt:
-            dist.broadcast(kk, src=owner[i])
-            dist.broadcast(cc, src=owner[i])
-        out[i] = (kk, cc, length)
+    sizes = [int(meta_h[i][0]) for i in range(n)]
+    keys = _gather_concat({i: v[0] for i, v in local.items()}, sizes, owner, n, dist, dev, torch.int64)
+    counts = _gather_concat({i: v[1] for i, v in local.items()}, sizes, owner, n, dist, dev, torch.int32)
+    out = {i: (keys[i], counts[i], int(meta_h[i][1])) for i in range(n)}
     return out, int(meta_h[n][0])
 
 
@@ -59,18 +75,13 @@ def exchange_pindex(local, n, owner, dist, dev, pbits_local):
     """Partition indices of the dumps (int32 [2 << pbits] each) -> present on every rank.  All ranks must use
     the same partition bits (the table is sized for the largest chromosome of the genome); returns ({}, 0)
     when any rank has none."""
-    rank = dist.get_rank()
     ok = all(v is not None for v in local.values())
     meta = torch.tensor([int(pbits_local) if ok else -1, -(int(pbits_local) if ok else -1)], dtype=torch.int64, device=dev)
     dist.all_reduce(meta, op=dist.ReduceOp.MAX)
     pmax, pmin = int(meta[0].item()), -int(meta[1].item())
     if pmax != pmin or pmax <= 0:
         return {}, 0
-    out = {}
-    for i in range(n):
-        t = local[i] if owner[i] == rank else torch.empty(2 << pmax, dtype=torch.int32, device=dev)
-        dist.broadcast(t, src=owner[i])
-        out[i] = t
+    out = _gather_concat(local, [2 << pmax] * n, owner, n, dist, dev, torch.int32)
     return out, pmax
 
 
@@ -129,6 +140,25 @@ def exchange_windows(win_counts, n, nsg, owner, dist, dev):
 
 
 _PINNED = {}
+_SCRATCH = {}
+
+
+def _scratch_table(max_bytes, k, lower_count, genome_max):
+    """The multi-GB count scratch (partition streams, dump buffers) is kept between calls: re-allocating it
+    every pass makes the caching allocator split and re-grow its largest blocks (cudaMalloc/cudaFree of GBs,
+    each a device-wide synchronisation — up to 50 ms of a 500-ms pass, varying from run to run)."""
+    key = (int(k), int(lower_count), int(genome_max))
+    tab = _SCRATCH.get("table")
+    if tab is None or tab[0] != key or tab[1].max_bases < max_bytes:
+        _SCRATCH.pop("table", None)
+        tab = (key, engine.CountTable(max_bytes, k, lower_count, genome_max_bases=genome_max))
+        _SCRATCH["table"] = tab
+    return tab[1]
+
+
+def release_scratch():
+    _SCRATCH.clear()
+    _PINNED.clear()
 
 
 def _to_host_pinned(name, t):
@@ -191,7 +221,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
 
     # ---- K1-K3 per chromosome -----------------------------------------------------------------------
     max_bytes = max([chrom_inputs[i][1] for i in mine] + [1])
-    table = engine.CountTable(max_bytes, k, lower_count, genome_max_bases=max([c[1] for c in chrom_inputs] + [1]))
+    table = _scratch_table(max_bytes, k, lower_count, max([c[1] for c in chrom_inputs] + [1]))
     seqs, dumps = {}, {}
     n_kmers = 0
     # host inputs: the H2D copy of chromosome j+1 runs on a side stream while chromosome j is counted
@@ -209,6 +239,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         return d, ev
 
     pending = start_copy(mine[0]) if (host_inputs and mine) else None
+    e_loop = t.start("_loop_pack_count")      # coarse brackets ("_..."): stage sums vs. whole-loop time = host gaps
     for pos, i in enumerate(mine):
         buf, nbytes = chrom_inputs[i]
         if host_inputs:
@@ -228,7 +259,8 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         dump = engine.count_packed(seq, k, lower_count, table=table, timer=t)
         seqs[i], dumps[i] = seq, dump
         n_kmers += dump.n_valid_kmers
-    del table
+    t.stop(e_loop)
+    del table          # stays alive in _SCRATCH for the next call
 
     # ---- exchange: every rank needs every dump (exact merge of the global k-mer table) -------------
     if world > 1:
@@ -283,8 +315,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     R = int(replicates)
     d_bs = None
     if R > 0:
-        idx = np.random.RandomState(seed).randint(0, M, size=(R, R)).astype(np.int32)
-        d_idx = torch.from_numpy(idx).to(dev)
+        d_idx = engine.resample_indices(M, R, seed)
         Gb = engine.gram_batched(Z, d_idx)
         lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
         ari, vm = engine.cluster_scores(lab_full_h, lab_b)
@@ -304,6 +335,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     sig = engine.SigTable(sig_keys, sig_vals, k, track_hits=False, S=nsg)
     t.stop(e)
     win_counts = {}
+    e_loop = t.start("_loop_map_stack")
     for i in mine:
         e = t.start("map")
         lines, nh = engine.map_bins(seqs[i], sig, nsg, bin_size, chunk_size)
@@ -319,6 +351,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
                       int(window_size), L, engine._p(out), nwin, engine._stream())
         win_counts[i] = out[:nwin]
         t.stop(e)
+    t.stop(e_loop)
     if keep_seqs is not None:
         keep_seqs.update(seqs)
 
