@@ -5,6 +5,7 @@
 // The reference dict holds each specific k-mer and its reverse complement (Cluster.py:174-175), so a
 // forward-strand lookup hits exactly when the CANONICAL k-mer is in the matrix; the table here stores
 // canonical keys only (half the size, stays L2-resident).
+#include <stdlib.h>
 #include "spk_common.cuh"
 #include "spk_tile.cuh"
 #include "spk_mixer.cuh"
@@ -600,7 +601,12 @@ extern "C" int spk_qtable_plan(uint64_t n_keys, int k, int S, int* slot_bits, in
     // every later lookup of that bucket) with probability 3e-4; at 3.5 it was 1.6 % of the buckets, i.e. ~40 %
     // of the warp-wide lookups had a lane in the slow path
     int bn = 4;
-    while (bn < 40 && (double)n_keys / (double)(1ull << bn) > 1.75) bn++;
+    double mean = 1.75;
+    if (const char* e = getenv("SPK_QT_MEAN")) {       // test hook: crowd the buckets to exercise the stash path
+        const double v = atof(e);
+        if (v > 0.0) mean = v;
+    }
+    while (bn < 40 && (double)n_keys / (double)(1ull << bn) > mean) bn++;
     if (bn > 2 * k) bn = 2 * k;
     int b16 = bn;
     if (2 * k + sgbits - 16 > b16) b16 = 2 * k + sgbits - 16;

@@ -234,8 +234,9 @@ __device__ __forceinline__ ScatterSmem carve_scatter(uint8_t* base, int nb) {
 inline size_t scatter_smem_bytes(int nb) { return (size_t)nb * 12 + (size_t)SC_CHUNK * 6; }
 
 // exclusive scan of cnt[nb] into off[nb] by a 256-thread CTA (nb a multiple of 256 or smaller); returns total
+template <int T = SPK_TILE_THREADS>
 __device__ __forceinline__ uint32_t bins_scan(const uint32_t* cnt, uint32_t* off, int nb, uint32_t* s_warp) {
-    const int per = (nb + SPK_TILE_THREADS - 1) / SPK_TILE_THREADS;
+    const int per = (nb + T - 1) / T;
     const int b0 = threadIdx.x * per;
     uint32_t sum = 0;
     for (int q = 0; q < per; q++)
@@ -249,7 +250,7 @@ __device__ __forceinline__ uint32_t bins_scan(const uint32_t* cnt, uint32_t* off
     if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
     __syncthreads();
     uint32_t prefix = 0, total = 0;
-    for (int w = 0; w < SPK_TILE_THREADS / 32; w++) {
+    for (int w = 0; w < T / 32; w++) {
         if (w < (int)(threadIdx.x >> 5)) prefix += s_warp[w];
         total += s_warp[w];
     }
@@ -264,8 +265,9 @@ __device__ __forceinline__ uint32_t bins_scan(const uint32_t* cnt, uint32_t* off
 }
 
 // reserve one global run per non-empty bin and turn cnt into the running cursor
+template <int T = SPK_TILE_THREADS>
 __device__ __forceinline__ void bins_reserve(ScatterSmem& s, int nb, uint32_t* __restrict__ gcursor) {
-    for (int b = threadIdx.x; b < nb; b += SPK_TILE_THREADS) {
+    for (int b = threadIdx.x; b < nb; b += T) {
         const uint32_t c = s.cnt[b];
         if (c) s.gbase[b] = atomicAdd(&gcursor[b], c) - s.off[b];
         s.cnt[b] = s.off[b];
@@ -427,14 +429,16 @@ k_scatter_prepare(const uint32_t* __restrict__ pstart, int b1, int b2, uint32_t*
     if (threadIdx.x == 0) ustart[nb] = s_carry;
 }
 
-__global__ void __launch_bounds__(SPK_TILE_THREADS, 2)
+constexpr int SC2_THREADS = 512;     // level 2 is latency-bound on its chunk loads: twice the warps of level 1
+
+__global__ void __launch_bounds__(SC2_THREADS, 2)
 k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pstart,
              const uint32_t* __restrict__ ustart, int b1, int b2, int rbits, uint32_t* __restrict__ cursor,
              uint32_t* __restrict__ buf) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     const int nb = 1 << b2;
     ScatterSmem sc = carve_scatter(s_raw, nb);
-    __shared__ uint32_t s_warp[SPK_TILE_THREADS / 32];
+    __shared__ uint32_t s_warp[SC2_THREADS / 32];
     __shared__ uint32_t s_unit[3];   // bucket, begin, end
     const int tid = threadIdx.x;
     const int nb1 = 1 << b1;
@@ -454,33 +458,33 @@ k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pst
             s_unit[1] = beg;
             s_unit[2] = min(beg + (uint32_t)SC_CHUNK, be);
         }
-        for (int b = tid; b < nb; b += SPK_TILE_THREADS) sc.cnt[b] = 0;
+        for (int b = tid; b < nb; b += SC2_THREADS) sc.cnt[b] = 0;
         __syncthreads();
         const uint32_t bucket = s_unit[0], beg = s_unit[1], end = s_unit[2];
-        for (uint32_t base = beg; base < end; base += 8 * SPK_TILE_THREADS) {
-            uint32_t v[8];
+        for (uint32_t base = beg; base < end; base += 4 * SC2_THREADS) {
+            uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const uint32_t i = base + u * SPK_TILE_THREADS + tid;
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = base + u * SC2_THREADS + tid;
                 v[u] = i < end ? __ldg(buf1 + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (base + u * SPK_TILE_THREADS + tid < end) atomicAdd(&sc.cnt[v[u] >> rbits], 1u);
+            for (int u = 0; u < 4; u++)
+                if (base + u * SC2_THREADS + tid < end) atomicAdd(&sc.cnt[v[u] >> rbits], 1u);
         }
         __syncthreads();
-        const uint32_t n_e = bins_scan(sc.cnt, sc.off, nb, s_warp);
-        bins_reserve(sc, nb, cursor + ((uint64_t)bucket << b2));
-        for (uint32_t base = beg; base < end; base += 8 * SPK_TILE_THREADS) {
-            uint32_t v[8];
+        const uint32_t n_e = bins_scan<SC2_THREADS>(sc.cnt, sc.off, nb, s_warp);
+        bins_reserve<SC2_THREADS>(sc, nb, cursor + ((uint64_t)bucket << b2));
+        for (uint32_t base = beg; base < end; base += 4 * SC2_THREADS) {
+            uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const uint32_t i = base + u * SPK_TILE_THREADS + tid;
+            for (int u = 0; u < 4; u++) {
+                const uint32_t i = base + u * SC2_THREADS + tid;
                 v[u] = i < end ? __ldg(buf1 + i) : 0u;     // second read of the chunk: L1/L2 hit
             }
 #pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (base + u * SPK_TILE_THREADS + tid < end) {
+            for (int u = 0; u < 4; u++)
+                if (base + u * SC2_THREADS + tid < end) {
                     const uint32_t sub = v[u] >> rbits;
                     const uint32_t p = atomicAdd(&sc.cnt[sub], 1u);
                     sc.sorted[p] = v[u] & rmask;
@@ -488,7 +492,7 @@ k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pst
                 }
         }
         __syncthreads();
-        for (uint32_t i = tid; i < n_e; i += SPK_TILE_THREADS) buf[sc.gbase[sc.bin[i]] + i] = sc.sorted[i];
+        for (uint32_t i = tid; i < n_e; i += SC2_THREADS) buf[sc.gbase[sc.bin[i]] + i] = sc.sorted[i];
         __syncthreads();
     }
 }
@@ -1052,7 +1056,7 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         SPK_LAUNCH_CHECK();
         k_scatter_prepare<<<1, 1024, 0, st>>>(pstart, pl.b1, pl.b2, cur1, ustart);
         SPK_LAUNCH_CHECK();
-        k_scatter_l2<<<(unsigned)(sms * 2), SPK_TILE_THREADS, smem2, st>>>(buf1, pstart, ustart, pl.b1, pl.b2,
+        k_scatter_l2<<<(unsigned)(sms * 2), SC2_THREADS, smem2, st>>>(buf1, pstart, ustart, pl.b1, pl.b2,
                                                                            pl.mx.rbits, cursor, (uint32_t*)buf);
         SPK_LAUNCH_CHECK();
     } else {

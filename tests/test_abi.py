@@ -33,6 +33,33 @@ def test_binding_covers_header(spk_built):
     assert lib.spk_map_num_lines(25_000_000, 15, 10000, 10_000_000) == 2502
 
 
+def test_host_side_planners(spk_built):
+    """Pure host functions of the ABI (no device work): partition bits of the counter, layout of the K9 table."""
+    from subphaser_b200 import _lib
+    lib = _lib.load()
+    # counter: <= 4096 k-mers per partition on average, never more partition bits than 2k or 22
+    assert lib.spk_pcount_pbits(300_000_000, 17) == 17
+    assert lib.spk_pcount_pbits(865_000_000, 17) == 18
+    assert lib.spk_pcount_pbits(10_000, 17) == 2
+    assert lib.spk_pcount_pbits(10**9, 5) == 10                       # tiny k: at most 4^k words
+    assert lib.spk_pcount_pbits(2**32, 17) == -1                      # >= 2^32 bases: global-table path
+    for nb in (1, 4096, 10**6, 10**9):
+        p = lib.spk_pcount_pbits(nb, 21)
+        assert 2 <= p <= 22 and (nb >> p) <= 4096
+        assert lib.spk_pcount_workspace_bytes_ex(nb, 21, p) == lib.spk_pcount_workspace_bytes(nb, 21) > 0
+        assert lib.spk_pcount_workspace_bytes_ex(nb, 21, 1) == 0      # fewer bits than the automatic choice: refused
+    # K9 bucketed quotient table: 16-bit slots whenever remainder + subgenome id fit, mean load <= 1.75
+    sb, bb = ctypes.c_int(), ctypes.c_int()
+    assert lib.spk_qtable_plan(3_600_000, 17, 3, ctypes.byref(sb), ctypes.byref(bb)) == 0
+    assert (sb.value, bb.value) == (16, 22) or (sb.value, bb.value) == (16, 21)
+    assert 2 * 17 - bb.value + 2 <= 16 and 3_600_000 / (1 << bb.value) <= 1.75
+    assert lib.spk_qtable_plan(1000, 15, 2, ctypes.byref(sb), ctypes.byref(bb)) == 0 and sb.value == 16
+    assert 2 * 15 - bb.value + 2 <= 16
+    assert lib.spk_qtable_plan(3_600_000, 21, 3, ctypes.byref(sb), ctypes.byref(bb)) == 0 and sb.value == 32
+    assert lib.spk_qtable_plan(1000, 32, 3, ctypes.byref(sb), ctypes.byref(bb)) != 0   # 64-bit keys: open-addressed table
+    assert lib.spk_map_num_lines(0, 17, 10000, 0) == 0
+
+
 def test_sass_has_bulk_copy(spk_built):
     """The sequence tiles are staged with the TMA engine: cp.async.bulk shows up as UBLKCP in SASS."""
     import shutil

@@ -410,9 +410,10 @@ def test_stack_lines_kernel_matches_reference_stack(tmp_path):
             assert [int(w) * ws_i for w in np.nonzero(nz)[0]] == [c[1] for c in st["coords"]]
 
 
-@pytest.mark.parametrize("k", [17, 29, 31])
+@pytest.mark.parametrize("k", [9, 17, 21, 29, 31])
 def test_map_bins_vs_oracle_mapper(k):
-    """K9 against oracle/kmer_count.c:orc_map_bins, including k > 28 (separate value array)."""
+    """K9 against oracle/kmer_count.c:orc_map_bins: 16-bit (k=9,17) and 32-bit (k=21) bucketed quotient tables,
+    the open-addressed table for wide k, including k > 28 (separate value array)."""
     import torch
     import spk_testutil as util
     from oracle import kmers
@@ -425,13 +426,20 @@ def test_map_bins_vs_oracle_mapper(k):
     pick = rng.choice(len(keys_all), size=min(4000, len(keys_all)), replace=False)
     keys = np.sort(keys_all[pick])
     sgs = rng.integers(0, 3, len(keys)).astype(np.uint8)
-    for bin_size, chunk in ((1000, 7000), (10000, 0), (333, 50000)):
+    for bin_size, chunk, qt_mean in ((1000, 7000, None), (10000, 0, "8"), (333, 50000, None)):
         L = len(codes)
         n_lines = (L - 1) // bin_size + ((L - 1 + k - 1) // chunk if chunk else 0) + 1
         want, hits = kmers.map_bins(codes, k, keys, sgs, 3, bin_size, chunk, n_lines)
         d, n = engine.to_device_bytes(fa)
         ps = engine.pack_fasta(d, n)
-        sig = engine.SigTable(torch.from_numpy(keys.view(np.int64).copy()).cuda(), torch.from_numpy(sgs).cuda(), k)
+        if qt_mean:      # ~8 keys per 7-entry bucket: a third of the keys overflow into the stash
+            os.environ["SPK_QT_MEAN"] = qt_mean
+        try:
+            sig = engine.SigTable(torch.from_numpy(keys.view(np.int64).copy()).cuda(), torch.from_numpy(sgs).cuda(), k)
+        finally:
+            os.environ.pop("SPK_QT_MEAN", None)
+        if qt_mean and k == 9:   # (wider k: the remainder width, not the load, fixes the bucket count)
+            assert sig.bucket and int((sig.skeys != -1).sum().item()) > 0          # the stash is really in use
         got, nh = engine.map_bins(ps, sig, 3, bin_size, chunk)
         assert nh == hits
         np.testing.assert_array_equal(got.cpu().numpy().view(np.uint32), want)
