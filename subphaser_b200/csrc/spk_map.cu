@@ -314,8 +314,6 @@ __global__ void __launch_bounds__(SPK_TILE_THREADS, 3)
 k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_bases, int k,
              MapArgs a, QtArgs qa) {
     __shared__ SpkTileSmem sm;
-    __shared__ uint32_t s_cnt[MP_SMEM_LINES * MP_MAX_S];
-    __shared__ uint64_t s_line0;
     const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
     const int tid = threadIdx.x;
     const SpkKmerParams kp = spk_kmer_params(k);
@@ -326,13 +324,24 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
 
     uint64_t tile = blockIdx.x;
     if (tid == 0 && tile < n_tiles) spk_tile_issue(sm, packed, valid, tile, 0);
+    // (bin, chunk) cursors of this thread's first position: divided once, then advanced by the constant
+    // grid stride (64-bit divisions per tile were ~10 % of the kernel's instructions)
+    uint64_t pos0 = tile * SPK_TILE_BASES + (uint64_t)tid * SPK_KMERS_PER_THREAD;
+    uint64_t bin = pos0 / a.bin_size;
+    uint64_t brem = pos0 - bin * a.bin_size;
+    uint64_t chk = 0, crem = 0;
+    if (a.chunk_size) {
+        chk = (pos0 + (uint64_t)(k - 1)) / a.chunk_size;
+        crem = (pos0 + (uint64_t)(k - 1)) - chk * a.chunk_size;
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * SPK_TILE_BASES;
+    const uint64_t dbin = stride / a.bin_size, dbrem = stride - dbin * a.bin_size;
+    const uint64_t dchk = a.chunk_size ? stride / a.chunk_size : 0, dcrem = a.chunk_size ? stride - dchk * a.chunk_size : 0;
 
     for (uint32_t it = 0; tile < n_tiles; it++, tile += gridDim.x) {
         const int buf = it & 1;
         const uint32_t parity = (it >> 1) & 1;
-        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) s_cnt[i] = 0;
-        if (tid == 0) s_line0 = line_of(tile * SPK_TILE_BASES, k, a.bin_size, a.chunk_size);
-        __syncthreads();  // buffer buf^1 free, counters cleared, line0 visible
+        __syncthreads();  // every warp is done with buffer buf^1 (the only CTA-wide barrier per tile)
         if (tid == 0 && tile + gridDim.x < n_tiles)
             spk_tile_issue(sm, packed, valid, tile + gridDim.x, buf ^ 1);
         spk_mbar_wait(&sm.bar[buf], parity);
@@ -403,24 +412,16 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
         }
         n_hit += __popc(hm);
 
-        // line bookkeeping for this thread's 16 consecutive positions
-        const uint64_t pos0 = tile * SPK_TILE_BASES + (uint64_t)tid * SPK_KMERS_PER_THREAD;
-        uint64_t bin = pos0 / a.bin_size;
-        uint64_t brem = pos0 - bin * a.bin_size;
-        uint64_t chk = 0, crem = 0;
-        if (a.chunk_size) {
-            chk = (pos0 + (uint64_t)(k - 1)) / a.chunk_size;
-            crem = (pos0 + (uint64_t)(k - 1)) - chk * a.chunk_size;
-        }
-        const uint64_t line0 = s_line0;
-        // fast path: the whole warp (512 positions) falls on one line -> warp-reduce the per-subgenome
-        // hit counts and let one lane add them (the slow path would serialise ~hits same-address atomics)
+        // fast path: the whole warp (512 positions) falls on one line -> warp-reduce the per-subgenome hit
+        // counts and let one lane add them to the line's counters (S REDs per warp and tile; nothing is staged
+        // in shared memory, so the tile loop needs no second barrier)
         const bool one_line = (brem + SPK_KMERS_PER_THREAD <= a.bin_size) &&
                               (!a.chunk_size || crem + SPK_KMERS_PER_THREAD <= a.chunk_size);
-        const uint64_t rel_t = bin + chk - line0;
-        const uint32_t rel32 = rel_t < 0xffffffffull ? (uint32_t)rel_t : 0xffffffffu;
-        const uint32_t rel_first = __shfl_sync(0xffffffffu, rel32, 0);
-        const bool warp_one_line = __all_sync(0xffffffffu, one_line && rel32 == rel_first) && S <= 4;
+        const uint64_t line_t = bin + chk;
+        const uint32_t lo_t = (uint32_t)line_t, hi_t = (uint32_t)(line_t >> 32);
+        const uint32_t lo_first = __shfl_sync(0xffffffffu, lo_t, 0), hi_first = __shfl_sync(0xffffffffu, hi_t, 0);
+        const bool warp_one_line =
+            __all_sync(0xffffffffu, one_line && lo_t == lo_first && hi_t == hi_first) && S <= 4;
         if (warp_one_line) {
             uint32_t c01 = 0, c23 = 0;   // four 16-bit counters (<= 16 per thread, <= 512 per warp)
 #pragma unroll
@@ -433,15 +434,11 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
             }
             c01 = __reduce_add_sync(0xffffffffu, c01);
             c23 = __reduce_add_sync(0xffffffffu, c23);
-            if ((tid & 31) == 0) {
+            if ((tid & 31) == 0 && line_t < a.n_lines) {
                 const uint32_t c[4] = {c01 & 0xffffu, c01 >> 16, c23 & 0xffffu, c23 >> 16};
-                const uint64_t line = line0 + rel_first;
 #pragma unroll
                 for (int s = 0; s < 4; s++)
-                    if (c[s] && s < S) {
-                        if (rel_first < MP_SMEM_LINES) atomicAdd(&s_cnt[rel_first * MP_MAX_S + s], c[s]);
-                        else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + s], c[s]);
-                    }
+                    if (c[s] && s < S) atomicAdd(&a.line_counts[line_t * a.S + s], c[s]);
             }
         } else {
             // a bin / chunk border inside the warp's 512 positions (or S > 4): per-hit adds, line by division
@@ -451,19 +448,18 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                 m &= m - 1;
                 const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
                 const uint64_t line = line_of(pos0 + j, k, a.bin_size, a.chunk_size);
-                const uint64_t rel = line - line0;
-                if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
-                else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
+                if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
             }
         }
-        __syncthreads();
-        for (int i = tid; i < MP_SMEM_LINES * MP_MAX_S; i += SPK_TILE_THREADS) {
-            const uint32_t c = s_cnt[i];
-            if (c) {
-                const uint64_t line = line0 + i / MP_MAX_S;
-                const int sg = i % MP_MAX_S;
-                if (line < a.n_lines && sg < a.S) atomicAdd(&a.line_counts[line * a.S + sg], c);
-            }
+        // advance the cursors to this thread's first position in the CTA's next tile
+        pos0 += stride;
+        bin += dbin;
+        brem += dbrem;
+        if (brem >= a.bin_size) { brem -= a.bin_size; bin++; }
+        if (a.chunk_size) {
+            chk += dchk;
+            crem += dcrem;
+            if (crem >= a.chunk_size) { crem -= a.chunk_size; chk++; }
         }
     }
     n_hit = spk_warp_sum_u64(n_hit);
