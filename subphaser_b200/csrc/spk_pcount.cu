@@ -281,7 +281,8 @@ __device__ __forceinline__ void bins_reserve(ScatterSmem& s, int nb, uint32_t* _
 // traversal (L2-atomic bound, as long as level 1 itself) is gone.
 __global__ void __launch_bounds__(SPK_TILE_THREADS, 4)
 k_hist1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k, Mixer mx,
-        int b1, uint32_t* __restrict__ bsize, uint64_t* __restrict__ stats) {
+        int b1, uint32_t* __restrict__ bsize, uint64_t* __restrict__ stats, uint32_t* __restrict__ psize,
+        int red_split) {
     __shared__ SpkTileSmem sm;
     __shared__ uint32_t s_bins[SC_MAX_BINS];
     const int tid = threadIdx.x;
@@ -304,7 +305,13 @@ k_hist1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, u
         n_valid += __popc(okmask);
 #pragma unroll
         for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
-            if ((okmask >> j) & 1u) atomicAdd(&s_bins[mx.fwd(key[j]) >> sh1], 1u);
+            if ((okmask >> j) & 1u) {
+                const uint64_t h = mx.fwd(key[j]);
+                atomicAdd(&s_bins[h >> sh1], 1u);
+                // this kernel is ALU-bound with the L2 atomic units idle, level 1 is co-limited by them: the
+                // P-bin partition histogram is split between the two (k-mers j < red_split of every thread here)
+                if (j < red_split) atomicAdd(&psize[h >> mx.rbits], 1u);
+            }
     }
     __syncthreads();
     for (int b = tid; b < nb; b += SPK_TILE_THREADS)
@@ -334,7 +341,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(const uint32_t* __restrict
 __global__ void __launch_bounds__(SPK_TILE_THREADS, 2)
 k_scatter_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k,
              Mixer mx, int b1, uint32_t* __restrict__ cur1, uint32_t* __restrict__ buf1,
-             uint32_t* __restrict__ psize) {
+             uint32_t* __restrict__ psize, int red_split) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     constexpr int PKW = (SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) / 4;   // 1028
     constexpr int VDW = (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) / 4;     // 516
@@ -390,7 +397,7 @@ k_scatter_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                 if ((okmask >> j) & 1u) {
                     const uint64_t h = mx.fwd(key[j]);
                     const uint32_t b = (uint32_t)(h >> sh1);
-                    atomicAdd(&psize[h >> mx.rbits], 1u);          // final-partition histogram (RED to L2)
+                    if (j >= red_split) atomicAdd(&psize[h >> mx.rbits], 1u);   // final-partition histogram (RED to L2)
                     const uint32_t p = atomicAdd(&sc.cnt[b], 1u);
                     sc.sorted[p] = (uint32_t)(h & m1);
                     sc.bin[p] = (uint16_t)b;
@@ -1030,7 +1037,10 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         uint32_t* bsize = ustart;                      // bucket sizes live in ustart until k_scatter_prepare
         const int nb1 = 1 << pl.b1;
         SPK_CUDA(cudaMemsetAsync(bsize, 0, (size_t)nb1 * 4, st));
-        k_hist1<<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, bsize, d_stats);
+        int red_split = 6;                             // of 16: share of the partition-histogram REDs issued by k_hist1
+        if (const char* e = getenv("SPK_PCOUNT_SPLIT")) red_split = atoi(e);
+        k_hist1<<<pass_grid, SPK_TILE_THREADS, 0, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, bsize, d_stats, psize,
+                                                        red_split);
         SPK_LAUNCH_CHECK();
         k_bucket_scan<<<1, 1024, 0, st>>>(bsize, nb1, cur1);
         SPK_LAUNCH_CHECK();
@@ -1046,7 +1056,7 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         }
         const uint64_t n_super = (pl.n_tiles + SC_TILES - 1) / SC_TILES;
         k_scatter_l1<<<(unsigned)min((uint64_t)sms * 2, n_super), SPK_TILE_THREADS, smem1, st>>>(
-            pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1, psize);
+            pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1, psize, red_split);
         SPK_LAUNCH_CHECK();
         k_scan_seg_totals<<<(unsigned)nseg, 1024, 0, st>>>(psize, pl.P, segs);
         SPK_LAUNCH_CHECK();
