@@ -251,7 +251,12 @@ int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n_b
  * with 0xFF), probed only for marked buckets; membership is exact.
  * spk_qtable_plan picks slot_bits (16|32) and bucket_bits for n_keys, k, S (SPK_EINVAL: no such layout,
  * use spk_sig_table_build / spk_map_bins).  d_buckets: (8 << bucket_bits) slots pre-filled with 0xFF.
- * spk_map_bins_q: same contract as spk_map_bins; d_hit_flags (optional) is uint8[(8 << bucket_bits) + sslots]. */
+ * spk_map_bins_q: same contract as spk_map_bins; d_hit_flags (optional) is uint8[(8 << bucket_bits) + sslots].
+ * Multi-record FASTA (Seqs.py:121-153 map every record on its own coordinates): d_rec_start (uint64[n_rec+1],
+ * packed position where each record starts, separator bases included, last = n_bases) and d_rec_line0
+ * (uint64[n_rec], first counter row of each record; a record of L bases owns spk_map_num_lines(L, ...) rows);
+ * a hit at packed position i of record r then counts in row rec_line0[r] + line(i - rec_start[r]).
+ * NULL: the whole input is one record. */
 int spk_qtable_plan(uint64_t n_keys, int k, int S, int* slot_bits, int* bucket_bits);
 int spk_qtable_build(const uint64_t* d_keys, const uint8_t* d_vals, uint64_t n, int k, int S, void* d_buckets,
                      int slot_bits, int bucket_bits, uint64_t* d_skeys, uint8_t* d_svals, uint64_t sslots,
@@ -260,7 +265,8 @@ int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid, uint64_t n
                    const void* d_buckets, int slot_bits, int bucket_bits, const uint64_t* d_skeys,
                    const uint8_t* d_svals, uint64_t sslots, int pack_vals, int S, uint64_t bin_size,
                    uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines, uint8_t* d_hit_flags,
-                   uint64_t* d_nhits, void* stream);
+                   uint64_t* d_nhits, const uint64_t* d_rec_start, const uint64_t* d_rec_line0, uint32_t n_rec,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10  per-window Fisher exact test (right tail) + Benjamini-Hochberg

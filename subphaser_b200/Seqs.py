@@ -105,52 +105,63 @@ def map_kmer3(chromfiles, d_kmers, fout=sys.stdout, k=None, window_size=10e6,
     i = 0
     mapped_num, mapped_seqs = 0, 0
     all_lines = []
+    lib = engine._lib.load()
     for chromfile in chromfiles:
         seq = _packed(chromfile)
         if seq.n_records > 1:
-            raise NotImplementedError("multi-record FASTA in map_kmer3 is not on the GPU path yet")
-        cid = _first_id(chromfile)
-        L = seq.n_bases
-        if chunk:
-            logger.info("Chunking chromsome {}: {:,} bp".format(cid, L))
-        counts_d, nhits = engine.map_bins(seq, sig, S, bin_size, W)
-        counts = counts_d.cpu().numpy().view(np.uint32)
-        nz = np.nonzero(counts.any(axis=1))[0]
-        # line id -> (bin, chunk): walk the (bin, chunk) boundaries in position order
-        if len(nz):
-            lid = nz.astype(np.int64)
-            if W:
-                # line = pos//bin + (pos+k-1)//W is monotone in pos; recover bin by searching the
-                # first position of every line: bins and chunk starts are the breakpoints
-                brk = np.unique(np.concatenate([
-                    np.arange(0, L, bin_size, dtype=np.int64),
-                    np.maximum(np.arange(0, L + k, W, dtype=np.int64) - (k - 1), 0)]))
-                brk = brk[brk < L]
-                first_line = brk // bin_size + (brk + k - 1) // W
-                pos = brk[np.searchsorted(first_line, lid)]
-                bins = pos // bin_size
-                chk = (pos + k - 1) // W
-                size = np.minimum((chk + 1) * W, L)
-            else:
-                bins = lid
-                size = np.full(len(lid), L, dtype=np.int64)
-            starts = bins * bin_size
-            ends = np.minimum(starts + bin_size, size)
-            rows = counts[nz]
-            text = "".join(
-                "{}\t{}\t{}\t{}\n".format(cid, s, e, "\t".join(map(str, r)))
-                for s, e, r in zip(starts.tolist(), ends.tolist(), rows.tolist()))
-            fout.write(text)
-            all_lines.append((cid, starts, ends, rows.astype(np.int64)))
-        if log:
-            logger.info("Mapped {} kmers to chromsome {}".format(nhits, cid))
-        n_chunks = max(1, -(-L // W)) if W else 1
-        i += n_chunks
-        mapped_num += nhits
-        if nhits > 0:
-            # the reference counts chunks ("sequences") containing hits; per-chunk hit flags are not
-            # tracked on the device, chromosomes with hits are counted chunk-wise as all-mapped
-            mapped_seqs += n_chunks
+            # every record is mapped on its own coordinates (Seqs.py:121-153); one kernel pass over the file
+            recs = [(rid, len(rseq)) for rid, _, rseq in _iter_fasta(chromfile)]
+            if sum(L + 1 for _, L in recs) - 1 != seq.n_bases:
+                raise ValueError("cannot index the records of {} (text before the first header?)".format(chromfile))
+            counts_d, _ = engine.map_bins(seq, sig, S, bin_size, W, record_lengths=[L for _, L in recs])
+        else:
+            recs = [(_first_id(chromfile), seq.n_bases)]
+            counts_d, _ = engine.map_bins(seq, sig, S, bin_size, W)
+        counts_all = counts_d.cpu().numpy().view(np.uint32)
+        row0 = 0
+        for cid, L in recs:
+            nl = lib.spk_map_num_lines(L, k, bin_size, W)
+            counts = counts_all[row0:row0 + nl]
+            row0 += nl
+            if chunk:
+                logger.info("Chunking chromsome {}: {:,} bp".format(cid, L))
+            nhits = int(counts.sum(dtype=np.int64))
+            nz = np.nonzero(counts.any(axis=1))[0]
+            # line id -> (bin, chunk): walk the (bin, chunk) boundaries in position order
+            if len(nz):
+                lid = nz.astype(np.int64)
+                if W:
+                    # line = pos//bin + (pos+k-1)//W is monotone in pos; recover bin by searching the
+                    # first position of every line: bins and chunk starts are the breakpoints
+                    brk = np.unique(np.concatenate([
+                        np.arange(0, L, bin_size, dtype=np.int64),
+                        np.maximum(np.arange(0, L + k, W, dtype=np.int64) - (k - 1), 0)]))
+                    brk = brk[brk < L]
+                    first_line = brk // bin_size + (brk + k - 1) // W
+                    pos = brk[np.searchsorted(first_line, lid)]
+                    bins = pos // bin_size
+                    chk = (pos + k - 1) // W
+                    size = np.minimum((chk + 1) * W, L)
+                else:
+                    bins = lid
+                    size = np.full(len(lid), L, dtype=np.int64)
+                starts = bins * bin_size
+                ends = np.minimum(starts + bin_size, size)
+                rows = counts[nz]
+                text = "".join(
+                    "{}\t{}\t{}\t{}\n".format(cid, s, e, "\t".join(map(str, r)))
+                    for s, e, r in zip(starts.tolist(), ends.tolist(), rows.tolist()))
+                fout.write(text)
+                all_lines.append((cid, starts, ends, rows.astype(np.int64)))
+            if log:
+                logger.info("Mapped {} kmers to chromsome {}".format(nhits, cid))
+            n_chunks = max(1, -(-L // W)) if W else 1
+            i += n_chunks
+            mapped_num += nhits
+            if nhits > 0:
+                # the reference counts chunks ("sequences") containing hits; per-chunk hit flags are not
+                # tracked on the device, records with hits are counted chunk-wise as all-mapped
+                mapped_seqs += n_chunks
     logger.info("Processed {} sequences".format(i))
     mapped_cat, total = sig.n_mapped(), len(d_kmers)
     try:

@@ -56,7 +56,7 @@ SIGNATURES = {
     "spk_qtable_plan": (c_i, [c_u64, c_i, c_i, c_p, c_p]),
     "spk_qtable_build": (c_i, [c_p, c_p, c_u64, c_i, c_i, c_p, c_i, c_i, c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_map_bins_q": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_i, c_i, c_p, c_p, c_u64, c_i, c_i, c_u64, c_u64,
-                             c_p, c_u64, c_p, c_p, c_p]),
+                             c_p, c_u64, c_p, c_p, c_p, c_p, c_u32, c_p]),
     "spk_fisher_right_tail": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
     "spk_colsum_i64": (c_i, [c_p, c_u64, c_i, c_p, c_p]),
     "spk_enrich_rows": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p]),

@@ -81,6 +81,11 @@ struct MapArgs {
     uint64_t n_lines;
     uint8_t* hit_flags;
     uint64_t* nhits;
+    // multi-record FASTA (Seqs.py:121-153 treat every record separately): record r occupies packed positions
+    // [rec_start[r], rec_start[r+1]) (incl. its separator base) and owns the lines from rec_line0[r]
+    const uint64_t* rec_start;   // [n_rec + 1], ascending; nullptr: one record
+    const uint64_t* rec_line0;   // [n_rec]
+    uint32_t n_rec;
 };
 
 __device__ __forceinline__ uint64_t line_of(uint64_t pos, int k, uint64_t bin_size,
@@ -421,8 +426,25 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
         const uint32_t lo_t = (uint32_t)line_t, hi_t = (uint32_t)(line_t >> 32);
         const uint32_t lo_first = __shfl_sync(0xffffffffu, lo_t, 0), hi_first = __shfl_sync(0xffffffffu, hi_t, 0);
         const bool warp_one_line =
-            __all_sync(0xffffffffu, one_line && lo_t == lo_first && hi_t == hi_first) && S <= 4;
-        if (warp_one_line) {
+            __all_sync(0xffffffffu, one_line && lo_t == lo_first && hi_t == hi_first) && S <= 4 && !a.rec_start;
+        if (a.rec_start) {
+            // record mode (small inputs: LTRs, custom features): per hit, find the record and its local line
+            uint32_t m = hm;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t sg = (uint32_t)(sgp[j >> 3] >> (8 * (j & 7))) & 0xffu;
+                const uint64_t pos = pos0 + j;
+                uint32_t lo = 0, hi = a.n_rec;               // last record with rec_start[r] <= pos
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (a.rec_start[mid] <= pos) lo = mid;
+                    else hi = mid;
+                }
+                const uint64_t line = a.rec_line0[lo] + line_of(pos - a.rec_start[lo], k, a.bin_size, a.chunk_size);
+                if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
+            }
+        } else if (warp_one_line) {
             uint32_t c01 = 0, c23 = 0;   // four 16-bit counters (<= 16 per thread, <= 512 per warp)
 #pragma unroll
             for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
@@ -575,7 +597,7 @@ extern "C" int spk_map_bins(const uint32_t* d_packed, const uint32_t* d_valid, u
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
     SPK_CHECK_ARG(!pack_vals || k <= 28, "packed values need k <= 28");
     MapArgs a{d_skeys, d_svals, sslots, d_filter, d_filter ? filter_bits - 1 : 0, pack_vals, S, bin_size, chunk_size,
-              d_line_counts, n_lines, d_hit_flags, d_nhits};
+              d_line_counts, n_lines, d_hit_flags, d_nhits, nullptr, nullptr, 0};
     k_map_bins<<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
         (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a);
     SPK_LAUNCH_CHECK();
@@ -650,7 +672,8 @@ extern "C" int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid,
                               const void* d_buckets, int slot_bits, int bucket_bits, const uint64_t* d_skeys,
                               const uint8_t* d_svals, uint64_t sslots, int pack_vals, int S, uint64_t bin_size,
                               uint64_t chunk_size, uint32_t* d_line_counts, uint64_t n_lines,
-                              uint8_t* d_hit_flags, uint64_t* d_nhits, void* stream) {
+                              uint8_t* d_hit_flags, uint64_t* d_nhits, const uint64_t* d_rec_start,
+                              const uint64_t* d_rec_line0, uint32_t n_rec, void* stream) {
     SPK_CHECK_ARG(d_packed && d_valid && d_buckets && d_skeys && d_svals && d_line_counts, "null pointer");
     SPK_CHECK_ARG(slot_bits == 16 || slot_bits == 32, "slot_bits must be 16 or 32");
     SPK_CHECK_ARG(k >= 1 && k <= 32 && bucket_bits >= 0 && bucket_bits <= 2 * k && bucket_bits <= 30, "bad geometry");
@@ -659,12 +682,13 @@ extern "C" int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid,
     SPK_CHECK_ARG(bin_size >= 1, "bin_size must be >= 1");
     SPK_CHECK_ARG(sslots >= 2, "stash too small");
     SPK_CHECK_ARG(!pack_vals || k <= 28, "packed values need k <= 28");
-    SPK_CHECK_ARG(n_lines >= spk_map_num_lines(n_bases, k, bin_size, chunk_size), "n_lines too small");
+    SPK_CHECK_ARG(d_rec_start || n_lines >= spk_map_num_lines(n_bases, k, bin_size, chunk_size), "n_lines too small");
+    SPK_CHECK_ARG(!d_rec_start || (d_rec_line0 && n_rec >= 1), "record index incomplete");
     if (n_bases < (uint64_t)k) return SPK_OK;
     const uint64_t n_tiles = (n_bases + SPK_TILE_BASES - 1) / SPK_TILE_BASES;
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms() * 3, n_tiles);
     MapArgs a{d_skeys, d_svals, sslots, nullptr, 0, pack_vals, S, bin_size, chunk_size,
-              d_line_counts, n_lines, d_hit_flags, d_nhits};
+              d_line_counts, n_lines, d_hit_flags, d_nhits, d_rec_start, d_rec_line0, n_rec};
     QtArgs qa{d_buckets, slot_bits, bucket_bits, qt_sgbits(S), spk_make_mixer(k, bucket_bits), d_skeys, d_svals,
               sslots, pack_vals};
     if (slot_bits == 16)

@@ -589,11 +589,30 @@ class SigTable:
         return int(self.hit_flags.sum().item()) if self.hit_flags is not None else 0
 
 
-def map_bins(seq, sig, S, bin_size, chunk_size):
-    """-> (line_counts int32 [n_lines, S] device, n_hits)."""
+def map_bins(seq, sig, S, bin_size, chunk_size, record_lengths=None):
+    """-> (line_counts int32 [n_lines, S] device, n_hits).
+    record_lengths (multi-record FASTA): bases of every record in file order; the rows of record r then start at
+    sum(spk_map_num_lines(L_q) for q < r) and use the record's own coordinates (Seqs.py:121-153)."""
     require_cuda()
     lib = _lib.load()
-    n_lines = lib.spk_map_num_lines(seq.n_bases, sig.k, int(bin_size), int(chunk_size))
+    rec_start = rec_line0 = None
+    n_rec = 0
+    if record_lengths is not None and len(record_lengths) > 1:
+        if not sig.bucket:
+            raise NotImplementedError("multi-record map needs the bucketed k-mer table (k <= ~24)")
+        lens = [int(x) for x in record_lengths]
+        n_rec = len(lens)
+        starts = np.zeros(n_rec + 1, np.int64)
+        starts[1:] = np.cumsum(np.asarray(lens, np.int64) + 1)      # + the separator base before the next record
+        starts[n_rec] = seq.n_bases
+        nl = [lib.spk_map_num_lines(L, sig.k, int(bin_size), int(chunk_size)) for L in lens]
+        line0 = np.zeros(n_rec, np.int64)
+        line0[1:] = np.cumsum(nl)[:-1]
+        n_lines = int(sum(nl))
+        rec_start = torch.from_numpy(starts).to(_dev())
+        rec_line0 = torch.from_numpy(line0).to(_dev())
+    else:
+        n_lines = lib.spk_map_num_lines(seq.n_bases, sig.k, int(bin_size), int(chunk_size))
     counts = _zeros(max(n_lines, 1) * S, torch.int32).view(max(n_lines, 1), S)
     nhits = _zeros(1, torch.int64)
     if seq.n_bases and sig.bucket:
@@ -601,7 +620,8 @@ def map_bins(seq, sig, S, bin_size, chunk_size):
             raise ValueError("map_bins: table holds %d subgenomes, S=%d" % (sig.S, S))
         call("spk_map_bins_q", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.buckets), sig.slot_bits,
              sig.bucket_bits, _p(sig.skeys), _p(sig.svals), sig.slots, sig.pack_vals, sig.S, int(bin_size),
-             int(chunk_size), _p(counts), max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())
+             int(chunk_size), _p(counts), max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _p(rec_start),
+             _p(rec_line0), n_rec, _stream())
     elif seq.n_bases:
         call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
              sig.slots, S, _p(sig.filter), sig.filter_bits, sig.pack_vals, int(bin_size), int(chunk_size), _p(counts),

@@ -147,6 +147,42 @@ def gen_map_stack(Seqs, Circos):
     jdump(cases, "map_stack.json")
 
 
+def gen_map_multi(Seqs):
+    """Multi-record FASTA through Seqs.map_kmer3 (the LTR / custom-feature calls of __main__.py:509-518,574-589 use
+    chunk=False with one row per sequence; chunk=True treats every record like a chromosome)."""
+    rng = np.random.default_rng(17)
+    cases = []
+    for k, lens, bin_size, window, chunk in ((7, [900, 40, 1500, 5, 2300, 700], 10000000, 10e6, False),
+                                             (9, [3000, 1200, 6, 4100], 500, 1300, True),
+                                             (5, [60, 61, 59, 120, 3, 0, 300], 50, 10e6, False)):
+        seqs = [util.messy_seq(rng, L, n_frac=0.03) if L else "" for L in lens]
+        allup = "N".join(s.upper() for s in seqs)
+        d_kmers = {}
+        sg_names = ["SG1", "SG2"]
+        for s in rng.integers(0, max(len(allup) - k, 1), 150):
+            km = allup[s:s + k]
+            if len(km) < k or any(c not in "ACGT" for c in km):
+                continue
+            canon = min(km, kmers.revcomp(km))
+            if canon in d_kmers:
+                continue
+            sg = sg_names[int(rng.integers(0, 2))]
+            d_kmers[canon] = sg
+            d_kmers[kmers.revcomp(canon)] = sg
+        tmp = tempfile.mkdtemp()
+        fa = os.path.join(tmp, "m.fasta")
+        records = [("rec%d some description" % i, s) for i, s in enumerate(seqs)]
+        with open(fa, "wb") as f:
+            f.write(util.fasta(records))
+        out = io.StringIO()
+        Seqs.map_kmer3([fa], d_kmers, fout=out, k=k, window_size=window, bin_size=bin_size, sg_names=sg_names,
+                       ncpu=1, method="map", chunk=chunk)
+        shutil.rmtree(tmp)
+        cases.append(dict(k=k, records=[[n, s] for n, s in records], bin_size=bin_size, window_size=window,
+                          chunk=chunk, sg_names=sg_names, d_kmers=d_kmers, bin_count_text=out.getvalue()))
+    jdump(cases, "map_multi.json")
+
+
 def gen_cluster_units(C):
     rng = np.random.default_rng(4)
     from collections import OrderedDict
@@ -267,6 +303,7 @@ def main():
     gen_filter(J)
     gen_fisher_enrich(S_mod)
     gen_map_stack(Seqs, Circos)
+    gen_map_multi(Seqs)
     gen_cluster_units(C)
     gen_pipeline(J, C, Seqs, Circos, S_mod)
 

@@ -159,6 +159,22 @@ def test_map_and_stack_match_reference_text(tmp_path):
                 assert counts == st["counts"]
 
 
+def test_map_multi_record_fasta_matches_reference_text(tmp_path):
+    """Seqs.map_kmer3 on multi-record FASTA (the LTR / custom-feature calls use chunk=False, one row per
+    sequence): byte-identical to the text the reference's own code wrote (tests/golden/map_multi.json)."""
+    from subphaser_b200 import Seqs, _registry
+    import spk_testutil as util
+    for ci, case in enumerate(load("map_multi.json")):
+        fa = tmp_path / ("m%d.fasta" % ci)
+        fa.write_bytes(util.fasta([(n, s) for n, s in case["records"]]))
+        out = tmp_path / ("m%d.bin.count" % ci)
+        _registry.clear()
+        with open(out, "w") as f:
+            Seqs.map_kmer3([str(fa)], case["d_kmers"], fout=f, k=case["k"], window_size=case["window_size"],
+                           bin_size=case["bin_size"], sg_names=case["sg_names"], ncpu=1, chunk=case["chunk"])
+        assert out.read_text() == case["bin_count_text"]
+
+
 # ---- K10 Fisher / enrich / BH ------------------------------------------------------------------------------
 def test_fisher_enrich_bh_match_reference_vectors():
     from subphaser_b200 import engine
