@@ -21,6 +21,7 @@ struct PackWs {
     int64_t* tile_last_nl;   // [ntiles]  global position of last '\n' in tile (or -1); scanned in place
     uint64_t* tile_off;      // [ntiles+1] kept bases before tile (after scan)
     uint32_t* tile_kept;     // [ntiles]
+    uint32_t* tile_skip;     // [ntiles] pass A: number of '\n' + '\r' bytes; bit 31: the tile contains a '>'
     uint64_t* totals;        // [4] scratch: valid count, records
 };
 
@@ -37,6 +38,8 @@ __host__ PackWs carve_ws(void* ws, size_t nbytes, size_t* total) {
     w.tile_off = (uint64_t*)(p + off);
     off += align_up((ntiles + 1) * 8, 256);
     w.tile_kept = (uint32_t*)(p + off);
+    off += align_up(ntiles * 4, 256);
+    w.tile_skip = (uint32_t*)(p + off);
     off += align_up(ntiles * 4, 256);
     w.totals = (uint64_t*)(p + off);
     off += 256;
@@ -81,13 +84,24 @@ __device__ __forceinline__ int last_newline16(const uint4& v) {
 }
 
 // ---- pass A -------------------------------------------------------------------------------------
+// 0x80 in every byte of y that is zero (exact: no borrow between bytes)
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) {
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c) { return zero_bytes(w ^ (c * 0x01010101u)); }
+
+// Per tile: position of the last '\n' (for the line-start carry), and — so that the kept-base count of an
+// ordinary tile needs no second look at its bytes — the number of '\n' / '\r' bytes and whether it has a '>'.
 __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t* __restrict__ in,
                                                                    size_t nbytes, size_t ntiles,
-                                                                   int64_t* __restrict__ tile_last_nl) {
+                                                                   int64_t* __restrict__ tile_last_nl,
+                                                                   uint32_t* __restrict__ tile_skip) {
     __shared__ int s_max[PK_THREADS / 32];
+    __shared__ uint32_t s_skip[PK_THREADS / 32];
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t pos = tile * PK_TILE + (size_t)threadIdx.x * PK_BYTES_PER_THREAD;
         int last = -1;
+        uint32_t skip = 0;       // low bits: count, bit 31: '>' seen
         if (pos < nbytes) {
             const uint4 v = load_tile_bytes(in, nbytes, pos);
             const int l = last_newline16(v);
@@ -98,15 +112,36 @@ __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t*
                 while (ll >= 0 && ((word_of(v, ll >> 2) >> (8 * (ll & 3))) & 0xffu) != 0x0au) ll--;
                 if (ll >= 0) last = threadIdx.x * 16 + ll;
             }
+            uint32_t gt = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const uint32_t x = word_of(v, w);
+                skip += __popc(eq_bytes(x, '\n') | eq_bytes(x, '\r'));
+                gt |= eq_bytes(x, '>');
+            }
+            if (pos + 16 > nbytes) skip -= (uint32_t)(pos + 16 - nbytes);   // the '\n' padding past the end
+            if (gt) skip |= 0x80000000u;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-        if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = last;
+        uint32_t cnt = skip & 0x7fffffffu, flag = skip >> 31;
+        cnt = spk_warp_sum_u32(cnt);
+        flag = __any_sync(0xffffffffu, flag) ? 1u : 0u;
+        if ((threadIdx.x & 31) == 0) {
+            s_max[threadIdx.x >> 5] = last;
+            s_skip[threadIdx.x >> 5] = cnt | (flag << 31);
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int m = -1;
-            for (int w = 0; w < PK_THREADS / 32; w++) m = max(m, s_max[w]);
+            uint32_t c = 0, f = 0;
+            for (int w = 0; w < PK_THREADS / 32; w++) {
+                m = max(m, s_max[w]);
+                c += s_skip[w] & 0x7fffffffu;
+                f |= s_skip[w] >> 31;
+            }
             tile_last_nl[tile] = (m < 0) ? -1 : (int64_t)(tile * PK_TILE + m);
+            tile_skip[tile] = c | (f << 31);
         }
         __syncthreads();
     }
@@ -230,12 +265,6 @@ __device__ __forceinline__ void classify16(const uint4& v, size_t pos, size_t nb
 }
 
 // ---- SWAR fast path --------------------------------------------------------------------------------------
-// 0x80 in every byte of y that is zero (exact: no borrow between bytes)
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t y) {
-    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c) { return zero_bytes(w ^ (c * 0x01010101u)); }
-
 // Same result as classify16 for 16 in-range bytes that are not inside a header line and contain no '>':
 // four bytes per 32-bit operation instead of a 16-step byte loop (the byte loop made K1 ALU-bound).
 // Returns false when the bytes need the general path.
@@ -313,6 +342,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restrict__ in, size_t nbytes,
                                                           size_t ntiles,
                                                           const int64_t* __restrict__ tile_carry_nl,
+                                                          const uint32_t* __restrict__ tile_skip,
                                                           uint32_t* __restrict__ tile_kept,
                                                           const uint64_t* __restrict__ tile_off,
                                                           uint32_t* __restrict__ packed,
@@ -332,6 +362,20 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
             // is the line that straddles into this tile a header?  (one byte read per tile)
             const size_t ls = (size_t)(carry + 1);
             s_carry_hdr = (ls < tbase) ? (in[ls] == '>') : 0;
+        }
+        if (!EMIT) {
+            // an ordinary tile (no '>' in it, not entered inside a header line) keeps every byte that is not a
+            // line break: pass A already counted those, so the tile's bytes are not read a second time here
+            __syncthreads();
+            const uint32_t sk = tile_skip[tile];
+            if (!(sk >> 31) && !s_carry_hdr) {
+                if (threadIdx.x == 0) {
+                    const size_t nb = (nbytes - tbase < (size_t)PK_TILE) ? nbytes - tbase : (size_t)PK_TILE;
+                    tile_kept[tile] = (uint32_t)nb - (sk & 0x7fffffffu);
+                }
+                __syncthreads();   // s_carry_hdr is rewritten by the next iteration
+                continue;
+            }
         }
         uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
         int my_last = -1;
@@ -362,9 +406,9 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
             uint32_t tot;
             block_excl_sum((uint32_t)kept, s_w32, &tot);
             if (threadIdx.x == 0) tile_kept[tile] = tot;
-            my_valid += nvalid;
             my_hdr += headers;
         } else {
+            my_valid += nvalid;
             // Stage the tile's output words in shared memory (OR of <= 4 words per thread), then write whole
             // words with coalesced plain stores; only the two words a tile may share with its neighbours
             // go through a global atomicOr (the outputs are zero-initialised).
@@ -408,13 +452,11 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
         }
         __syncthreads();   // s_carry_hdr is rewritten by the next iteration
     }
-    if (!EMIT) {
-        my_valid = spk_warp_sum_u64(my_valid);
-        my_hdr = spk_warp_sum_u64(my_hdr);
-        if ((threadIdx.x & 31) == 0) {
-            if (my_valid) atomicAdd((unsigned long long*)&totals[0], (unsigned long long)my_valid);
-            if (my_hdr) atomicAdd((unsigned long long*)&totals[1], (unsigned long long)my_hdr);
-        }
+    my_valid = spk_warp_sum_u64(my_valid);     // valid bases: counted where they are emitted (pass C)
+    my_hdr = spk_warp_sum_u64(my_hdr);         // records: only tiles with a '>' reach the classifier in pass B
+    if ((threadIdx.x & 31) == 0) {
+        if (my_valid) atomicAdd((unsigned long long*)&totals[0], (unsigned long long)my_valid);
+        if (my_hdr) atomicAdd((unsigned long long*)&totals[1], (unsigned long long)my_hdr);
     }
 }
 
@@ -464,20 +506,20 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
     SPK_CUDA(cudaMemsetAsync(d_valid, 0, spk_valid_words(cap_bases) * 4, st));
     if (ntiles > 0) {
         const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
-        k_tile_last_newline<<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl);
+        k_tile_last_newline<<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip);
         SPK_LAUNCH_CHECK();
         k_scan_max_excl<<<1, 1024, 0, st>>>(w.tile_last_nl, ntiles);
         SPK_LAUNCH_CHECK();
-        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_kept,
-                                                       nullptr, nullptr, nullptr, w.totals);
+        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip,
+                                                       w.tile_kept, nullptr, nullptr, nullptr, w.totals);
         SPK_LAUNCH_CHECK();
     }
     k_scan_sum_excl<<<1, 1024, 0, st>>>(w.tile_kept, w.tile_off, ntiles);
     SPK_LAUNCH_CHECK();
     if (ntiles > 0) {
         const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
-        k_classify<true><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, nullptr,
-                                                      w.tile_off, d_packed, d_valid, nullptr);
+        k_classify<true><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip, nullptr,
+                                                      w.tile_off, d_packed, d_valid, w.totals);
         SPK_LAUNCH_CHECK();
     }
     k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, d_info);
