@@ -159,8 +159,9 @@ def host_sample(plan, sample_bases):
 
 def workload_name(args, plan, cfg):
     g = sum(c["length"] for c in plan.chroms)
-    return "%s wheat-shaped synthetic: %d chromosomes, %.3g bp, k=%d, %d subgenomes, %d-bp windows%s" % (
-        args.config, len(plan.chroms), g, cfg["k"], len(plan.sg_letters), cfg["window"],
+    shape = {"C1": "Arabidopsis-shaped", "C2": "peanut-shaped", "C5": "hexaploid"}.get(args.config, "wheat-shaped")
+    return "%s %s synthetic: %d chromosomes, %.3g bp, k=%d, %d subgenomes, %d-bp windows%s" % (
+        args.config, shape, len(plan.chroms), g, cfg["k"], len(plan.sg_letters), cfg["window"],
         "" if args.scale == 1.0 else " (scale %g)" % args.scale)
 
 

@@ -22,6 +22,10 @@ CONFIGS = {
     "C1": dict(sg="AB", lengths=None, k=15, window=1_000_000),      # Arabidopsis-shaped, filled below
     "C2": dict(sg="AB", lengths=[127_000_000] * 20, k=15, window=1_000_000),
     "C3": dict(sg="ABD", lengths=[m * 1_000_000 for m in WHEAT_MB], k=17, window=1_000_000),
+    # C4 (bootstrap K-Means + PCA on the chrom x k-mer matrix) is the clustering stage of the C3 run
+    "C4": dict(sg="ABD", lengths=[m * 1_000_000 for m in WHEAT_MB], k=17, window=1_000_000),
+    # synthetic hexaploid, 21 x 2.38 Gb (chromosomes longer than 2^31 bp), k=21, 100-kb windows
+    "C5": dict(sg="ABD", lengths=[2_380_000_000] * 21, k=21, window=100_000),
 }
 CONFIGS["C1"]["lengths"] = [int(x) for x in np.linspace(14e6, 26e6, 13)] + [20_000_000]   # 14 chr, 2 SG
 
@@ -132,7 +136,7 @@ def synth_chromosome(plan, chrom, line_width=60, d_library=None):
 def plan_for(config, seed=None, scale=1.0):
     """GenomePlan of one of the BASELINE.json configs; `scale` shrinks every chromosome (tests)."""
     cfg = CONFIGS[config]
-    seeds = {"C1": 101, "C2": 202, "C3": 303}
+    seeds = {"C1": 101, "C2": 202, "C3": 303, "C4": 303, "C5": 505}
     lengths = [max(int(L * scale), 1000) for L in cfg["lengths"]]
     if config == "C1":
         lengths = lengths[:14]

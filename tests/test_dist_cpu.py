@@ -18,7 +18,8 @@ def test_lpt_assignment_balances_wheat():
         owner = hotpath.lpt_assign(lengths, world)
         assert len(owner) == 21 and set(owner) == set(range(world))
         load = [sum(l for l, o in zip(lengths, owner) if o == r) for r in range(world)]
-        assert max(load) / (sum(load) / world) < 1.15          # 1.135 at 8 ranks
+        # greedy LPT gives 1.135 at 8 ranks; the local search brings it to 1.08 (and ~1.00 at 2 / 4)
+        assert max(load) / (sum(load) / world) < {1: 1.0001, 2: 1.005, 4: 1.01, 8: 1.09}[world]
     assert hotpath.lpt_assign(lengths, 8) == hotpath.lpt_assign(lengths, 8)   # deterministic on every rank
 
 
