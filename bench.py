@@ -180,8 +180,8 @@ def main():
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")           # these levels print a version banner on stdout: keep it to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         pg = dist
     engine.require_cuda()
