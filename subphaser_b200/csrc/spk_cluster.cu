@@ -584,7 +584,6 @@ k_pca_gram(const double* __restrict__ G, int n, int ncomp, double* __restrict__ 
     }
 }
 
-inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 inline unsigned row_grid(uint64_t M, int threads) {
     const uint64_t blocks = (M + threads - 1) / threads;
     const uint64_t cap = (uint64_t)spk_num_sms() * 16;

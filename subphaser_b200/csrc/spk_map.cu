@@ -4,7 +4,9 @@
 // position i, `sg = d_kmers[seq[i:i+k]]`; on a hit `d_bin[(i+offset)//bin_size][sg] += 1`.
 // The reference dict holds each specific k-mer and its reverse complement (Cluster.py:174-175), so a
 // forward-strand lookup hits exactly when the CANONICAL k-mer is in the matrix; the table here stores
-// canonical keys only (half the size, stays L2-resident).
+// canonical keys only (half the size, stays L2-resident).  Shipped layout: the bucketed quotient table below
+// (k_qt_build / k_map_bins_q, one 16/32-byte load per position); k_sig_build / k_map_bins (open addressing +
+// one-hash bitmap) remain for keys wider than the quotient slots.
 #include <stdlib.h>
 #include "spk_common.cuh"
 #include "spk_tile.cuh"
@@ -12,7 +14,6 @@
 
 namespace {
 
-constexpr int MP_BATCH = 8;
 constexpr int MP_SMEM_LINES = 16;
 constexpr int MP_MAX_S = 32;
 

@@ -6,14 +6,19 @@
 // split into P = 2^pbits hash partitions small enough that one partition's table fits in the shared
 // memory of a CTA; HBM only sees streaming traffic:
 //
-//   phase 0  k_part_pass<hist>     recompute k-mers tile by tile (TMA-staged), RED partition sizes
-//            k_scan_*              exclusive scan of the P sizes -> partition extents, cursors
-//   phase 1  k_part_pass<scatter>  same traversal, append the 32-bit remainder r to its partition
-//   phase 2  k_part_count          one CTA per partition: stream r, insert into an smem table
-//                                  (CAS on new keys, 32-bit add on hits), then scan the table:
-//                                  stats, histogram, dump of count >= L
+//   k_hist1         one traversal (TMA-staged tiles): bucket histogram (top b1 bits) privatised in smem
+//   k_scatter_l1    4-tile super-tiles -> 2^b1 buckets: smem histogram, scan, one global reservation per
+//                   bucket, counting-sort in smem, coalesced runs; REDs the P-bin partition histogram
+//   k_scan_*        exclusive scan of the P sizes -> partition extents, cursors
+//   k_scatter_l2    16384-entry chunks of a bucket -> its 2^b2 final partitions (same smem-staged scheme),
+//                   writing the 32-bit remainder r
+//   k_part_count32  one partition per CTA iteration: stream r (software-pipelined through registers),
+//                   CAS+add into a 32-bit smem table, one reservation per partition, one sweep that
+//                   writes the partition's dump contiguously (pindex) and clears the table
+//   (inputs below 16.7 M bases or remainders wider than 32 bits: k_part_pass<hist|scatter> one-level
+//    scatter with cursor atomics; remainders wider than 31 bits: k_part_count<ENT64> with 64-bit slots)
 //
-// DRAM traffic per k-mer: 2 x 0.375 B (sequence, read twice) + 4 B write + 4 B read.
+// DRAM traffic per k-mer: 2 x 0.375 B (sequence, read twice) + 2 x (4 B write + 4 B read) = 16.75 B.
 // Partitioning uses a bijective mixer f on the 2k-bit canonical word: partition = top pbits of f(u),
 // remainder r = the rest; the dump applies f^-1, so keys are exact and the result is bit-identical to
 // the v1 kernel / the jellyfish semantics (only the dump ORDER differs, which is arbitrary anyway).
