@@ -788,11 +788,11 @@ __device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cn
 
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
-               CountOut o) {
+               CountOut o, uint32_t retry_cap) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint32_t* s_key = (uint32_t*)s_raw;
     uint32_t* s_cnt = s_key + PC_SLOTS;
-    uint32_t* s_q = s_cnt + PC_SLOTS;                    // [PC_RETRY]
+    uint32_t* s_q = s_cnt + PC_SLOTS;                    // [PC_RETRY]; retry_cap <= PC_RETRY entries are used as queue
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_red[4][PC_THREADS / 32];
     __shared__ uint32_t s_nq, s_nkeep, s_ndist, s_wr;
@@ -839,7 +839,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     auto insert = [&](uint32_t r) {
         if (!try_home(r)) {
             const uint32_t qi = atomicAdd(&s_nq, 1u);
-            if (qi < PC_RETRY) s_q[qi] = r;
+            if (qi < retry_cap) s_q[qi] = r;
             else probe_rest(r);
         }
     };
@@ -872,14 +872,18 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
             if (beg + u * PC_THREADS + tid < end && !try_home(cur[u])) failm |= 1u << u;
         if (failm) {
             uint32_t qi = atomicAdd(&s_nq, (uint32_t)__popc(failm));
-            if (qi + __popc(failm) <= PC_RETRY) {
+            if (qi + __popc(failm) <= retry_cap) {
 #pragma unroll
                 for (int u = 0; u < PC_PF; u++)
                     if ((failm >> u) & 1u) s_q[qi++] = cur[u];
-            } else {                                        // queue full (heavily colliding partition): probe inline
-#pragma unroll
+            } else {                                        // queue (nearly) full — a heavily colliding partition:
+#pragma unroll                                              // fill what is left of the reservation, probe the rest inline
                 for (int u = 0; u < PC_PF; u++)
-                    if ((failm >> u) & 1u) probe_rest(cur[u]);
+                    if ((failm >> u) & 1u) {
+                        if (qi < retry_cap) s_q[qi] = cur[u];     // every slot below min(s_nq, retry_cap) must be written
+                        else probe_rest(cur[u]);
+                        qi++;
+                    }
             }
         }
         for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
@@ -895,7 +899,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         }
         __syncthreads();
         // ---- insert, queued entries: all lanes probe together ----
-        const uint32_t nq = min(s_nq, (uint32_t)PC_RETRY);
+        const uint32_t nq = min(s_nq, retry_cap);
         for (uint32_t i = tid; i < nq; i += PC_THREADS) probe_rest(s_q[i]);
         // ---- partition totals -> one reservation ----
         my_new = spk_warp_sum_u32(my_new);
@@ -1103,7 +1107,13 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
             SPK_CUDA(cudaFuncSetAttribute(k_part_count32, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8 + PC_RETRY * 4));
             attr32 = true;
         }
-        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o);
+        uint32_t retry_cap = PC_RETRY;
+        if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
+            const long v = atol(e);
+            if (v >= 0 && v < PC_RETRY) retry_cap = (uint32_t)v;
+        }
+        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o,
+                                                                              retry_cap);
     } else {
         k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
     }

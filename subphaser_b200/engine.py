@@ -336,7 +336,8 @@ _PM_CAP = {}
 
 def can_pmatrix(dumps):
     """True when every dump carries a partition index with the same partition bits."""
-    return (len(dumps) > 0 and len(dumps) <= 256 and all(d.pindex is not None and d.pbits > 0 for d in dumps)
+    # (<= 128 columns: a shared-memory table slot is an 8-byte key + 4 bytes per chromosome)
+    return (len(dumps) > 0 and len(dumps) <= 128 and all(d.pindex is not None and d.pbits > 0 for d in dumps)
             and len({d.pbits for d in dumps}) == 1 and os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain")
 
 

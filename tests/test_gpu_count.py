@@ -122,3 +122,19 @@ def test_two_level_scatter_path(k):
     assert len(seq) > 9_000_000
     _check(util.fasta([("big", seq)]), k, 1)
     _check(util.fasta([("big", seq)]), k, 3)
+
+
+def test_retry_queue_overflow_paths(monkeypatch):
+    """k_part_count32 queues the entries whose home slot is taken and probes them later; with the queue capped
+    at a few entries (test hook) every partition overflows it, so the inline-probe and the straddling-
+    reservation paths must give the same counts."""
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    rng = np.random.default_rng(5)
+    seq = util.messy_seq(rng, 400_000, repeat_unit="ACGTTGCA")
+    fa = util.fasta([("c", seq)])
+    for cap in ("0", "7", "100"):
+        monkeypatch.setenv("SPK_PCOUNT_RETRY_CAP", cap)
+        _check(fa, 17, 1)
+        _check(fa, 15, 2)
+    monkeypatch.delenv("SPK_PCOUNT_RETRY_CAP")
