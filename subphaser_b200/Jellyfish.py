@@ -192,9 +192,14 @@ class JellyfishDumps:
         for dumpfile in self.dumpfiles:
             logger.info("Loading " + dumpfile)
             dumps.append(load_dump(dumpfile))
+        cm = None
         if engine.can_pmatrix(dumps):      # dumps counted with common partition bits: no union table at all
             cm = engine.LazyUnion(dumps, self.labels)
-        else:
+            try:
+                len(cm)                    # `__main__.py:417` asks for it right away: one union-only pass
+            except OverflowError:          # a hash partition did not fit the shared-memory table
+                cm = None
+        if cm is None:
             cm = engine.build_matrix(dumps, self.labels)
         self.lengths = list(cm.lengths)
         return cm
@@ -229,11 +234,16 @@ class JellyfishDumps:
             if len(sg) > 32:
                 raise ValueError("more than 32 groups in one homoeologous set is not supported")
         if isinstance(d_mat, engine.LazyUnion):
-            dm, n_all = engine.pmatrix_filter(d_mat.dumps, sgs, list(self.labels), min_fold=min_fold,
-                                              baseline=baseline, ratio=ratio, min_freq=min_freq, max_freq=max_freq,
-                                              by_count=by_count, want_fold_tots=outfig is not None,
-                                              lengths=list(lengths))
-            d_mat._len = n_all
+            try:
+                dm, n_all = engine.pmatrix_filter(d_mat.dumps, sgs, list(self.labels), min_fold=min_fold,
+                                                  baseline=baseline, ratio=ratio, min_freq=min_freq,
+                                                  max_freq=max_freq, by_count=by_count,
+                                                  want_fold_tots=outfig is not None, lengths=list(lengths))
+                d_mat._len = n_all
+            except OverflowError:      # a hash partition did not fit the shared-memory table: plain union
+                d_mat = engine.build_matrix(d_mat.dumps, self.labels)
+        if isinstance(d_mat, engine.LazyUnion):
+            pass
         elif isinstance(d_mat, engine.CountMatrix):
             if list(lengths) != list(d_mat.lengths):
                 d_mat = engine.CountMatrix(d_mat.matrix, d_mat.row_keys, lengths, d_mat.k, d_mat.labels)

@@ -309,13 +309,24 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     dump_list = [dumps[i] for i in range(n)]
 
     # ---- K3b/K4 matrix + filter: rows are independent -> each rank builds the rows of its share ----------
-    if engine.can_pmatrix(dump_list):
+    dm = None
+    use_p = engine.can_pmatrix(dump_list)
+    if use_p:
         # partitioned union + filter in shared memory (rank r: partitions p % world == r)
         e = t.start("matrix")
-        dm, n_union = engine.pmatrix_filter(dump_list, sgs, labels, min_fold=min_fold, baseline=baseline, ratio=ratio,
-                                            min_freq=min_freq, max_freq=max_freq, nparts=world, part=rank)
+        try:
+            dm, n_union = engine.pmatrix_filter(dump_list, sgs, labels, min_fold=min_fold, baseline=baseline,
+                                                ratio=ratio, min_freq=min_freq, max_freq=max_freq, nparts=world,
+                                                part=rank)
+        except OverflowError:          # a partition did not fit the shared-memory table (adversarial skew)
+            dm = None
         t.stop(e)
-    else:
+    if world > 1 and use_p:            # every rank must take the same path: the row shards differ between them
+        ok = torch.tensor([0 if dm is None else 1], dtype=torch.int64, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            dm = None
+    if dm is None:
         e = t.start("matrix")
         cm = engine.build_matrix(dump_list, labels, nparts=world, part=rank)
         t.stop(e)
