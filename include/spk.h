@@ -195,6 +195,12 @@ int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_c
                        int by_count, double ratio, double min_freq, double max_freq, uint64_t* d_out_keys,
                        uint32_t* d_out_counts, uint64_t cap, uint64_t total_entries, uint64_t* d_counters,
                        void* stream);
+/* spk_dump_regroup: move the contiguous run of every hash partition of a dump (d_pindex, uint32[2 << pbits])
+ * to d_new_start[p] (uint32[1 << pbits]) in d_out_keys / d_out_counts — the multi-GPU exchange regroups a dump by
+ * destination rank (partition class p mod world) before the all-to-all. */
+int spk_dump_regroup(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_pindex,
+                     const uint32_t* d_new_start, int pbits, uint64_t* d_out_keys, uint32_t* d_out_counts,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).

@@ -36,6 +36,7 @@ SIGNATURES = {
                                       c_i, c_p, c_p]),
     "spk_pmatrix_filter": (c_i, [c_p, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_d, c_i, c_i,
                                  c_d, c_d, c_d, c_p, c_p, c_u64, c_u64, c_p, c_p]),
+    "spk_dump_regroup": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]),
     "spk_table_scan_blocks": (c_i, []),
     "spk_table_stats": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u32, c_p]),
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),

@@ -194,6 +194,24 @@ __global__ void __launch_bounds__(PM_THREADS, 1) k_pmatrix_filter(PmArgs a) {
     (void)lengths;
 }
 
+// Regroup a partition-indexed dump: partition p's run [pindex[2p], +pindex[2p+1]) moves to new_start[p].
+// One warp per partition (runs are a few dozen entries); used by the multi-GPU exchange to make every
+// destination rank's partition class contiguous before the all-to-all.
+__global__ void __launch_bounds__(256)
+k_dump_regroup(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+               const uint32_t* __restrict__ pindex, const uint32_t* __restrict__ new_start, uint64_t P,
+               uint64_t* __restrict__ okeys, uint32_t* __restrict__ ocounts) {
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += nw) {
+        const uint32_t s = pindex[2 * p], c = pindex[2 * p + 1], d = new_start[p];
+        for (uint32_t i = lane; i < c; i += 32) {
+            okeys[d + i] = keys[s + i];
+            ocounts[d + i] = counts[s + i];
+        }
+    }
+}
+
 uint32_t pm_table_slots(int n, double mean_entries) {
     // smallest power of two that takes an average partition in ONE round (entries <= 7/8 of the slots), capped
     // by shared memory: a slot is an 8-byte key + n 4-byte counters and the table must stay under ~190 KB
@@ -256,6 +274,20 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     if (mine == 0) return SPK_OK;
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms(), mine);
     k_pmatrix_filter<<<grid, PM_THREADS, smem, st>>>(a);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_dump_regroup(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_pindex,
+                                const uint32_t* d_new_start, int pbits, uint64_t* d_out_keys, uint32_t* d_out_counts,
+                                void* stream) {
+    SPK_CHECK_ARG(d_pindex && d_new_start, "null pointer");
+    SPK_CHECK_ARG(pbits >= 0 && pbits <= 30, "bad pbits");
+    SPK_CHECK_ARG((d_keys && d_counts && d_out_keys && d_out_counts) || true, "null pointer");
+    const uint64_t P = 1ull << pbits;
+    const unsigned grid = (unsigned)min((P * 32 + 255) / 256, (uint64_t)spk_num_sms() * 16);
+    k_dump_regroup<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_counts, d_pindex, d_new_start, P, d_out_keys,
+                                                           d_out_counts);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -9,6 +9,7 @@ one exchange step is the merge of the per-chromosome dumps into the global k-mer
 broadcast from their owners over NVLink (exact, variable-size) and `lengths` are all-reduced; the
 per-window counts are all-gathered before the genome-wide Fisher step.
 """
+import os
 import time
 
 import numpy as np
@@ -120,6 +121,124 @@ def exchange_pindex(local, n, owner, dist, dev, pbits_local):
         return {}, 0
     out = _gather_concat(local, [2 << pmax] * n, owner, n, dist, dev, torch.int32)
     return out, pmax
+
+
+def _all_to_all(send, in_splits, out_splits, dist, dev):
+    """Ragged all-to-all of a 1-D tensor; NCCL does it in one collective, other backends (gloo in the CPU
+    tests) get it as one broadcast per source rank."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    recv = torch.empty(int(sum(out_splits)), dtype=send.dtype, device=dev)
+    try:
+        dist.all_to_all_single(recv, send, [int(x) for x in out_splits], [int(x) for x in in_splits])
+        return recv
+    except (RuntimeError, NotImplementedError, AttributeError):
+        pass
+    sizes = torch.zeros(world, world, dtype=torch.int64, device=dev)
+    sizes[rank] = torch.tensor([int(x) for x in in_splits], dtype=torch.int64, device=dev)
+    dist.all_reduce(sizes)
+    sizes_h = sizes.cpu().tolist()
+    off_out = 0
+    for src in range(world):
+        tot = int(sum(sizes_h[src]))
+        buf = send if src == rank else torch.empty(tot, dtype=send.dtype, device=dev)
+        if tot:
+            dist.broadcast(buf, src=src)
+        a = int(sum(sizes_h[src][:rank]))
+        m = int(sizes_h[src][rank])
+        recv[off_out:off_out + m] = buf[a:a + m]
+        off_out += m
+    return recv
+
+
+def exchange_dumps_by_class(local, pindex_local, pbits, n, owner, dist, dev, n_kmers_local=0):
+    """The exchange step with 1/world of the volume: rank r builds the union rows of the hash partitions
+    p = r (mod world) only, so it needs just that class of every other chromosome's dump.  Every owned dump is
+    regrouped class-major (its partitions are contiguous runs located by pindex), the classes travel in three
+    ragged all-to-alls (keys, counts, per-partition sizes), and the receiver rebuilds a full-size partition
+    index for the slice it got.  -> ({i: (keys, counts, length, pindex)} for the chromosomes of OTHER ranks,
+    total k-mers)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    P = 1 << int(pbits)
+    mine = [i for i in range(n) if owner[i] == rank]
+    part = torch.arange(P, device=dev)
+    perm = torch.argsort(part % world, stable=True)                 # class-major, partitions ascending inside
+    ncls = [len(range(c, P, world)) for c in range(world)]          # partitions per class
+    cls_poff = [0]
+    for c in range(world):
+        cls_poff.append(cls_poff[-1] + ncls[c])
+    meta = torch.zeros(n + 1, world + 1, dtype=torch.int64, device=dev)
+    regrouped = {}
+    for i in mine:
+        kk, cc, length = local[i]
+        pidx = pindex_local[i].to(torch.int64)
+        start_p, cnt_p = pidx[0::2][perm], pidx[1::2][perm]
+        new_start = torch.cumsum(cnt_p, 0) - cnt_p
+        total = int(kk.numel())
+        csum = torch.cumsum(cnt_p, 0)
+        ends = torch.stack([csum[cls_poff[c + 1] - 1] if ncls[c] else csum.new_zeros(()) for c in range(world)])
+        tot_c = ends - torch.cat([ends.new_zeros(1), ends[:-1]])
+        meta[i, :world] = tot_c
+        meta[i, world] = int(length)
+        if kk.is_cuda:      # one warp per partition run (spk_dump_regroup); the index math above is 2^pbits elements
+            ns = torch.empty(P, dtype=torch.int32, device=dev)
+            ns[perm] = new_start.to(torch.int32)
+            rk_, rc_ = torch.empty_like(kk), torch.empty_like(cc)
+            _lib.call("spk_dump_regroup", engine._p(kk), engine._p(cc), engine._p(pindex_local[i]), engine._p(ns),
+                      int(pbits), engine._p(rk_), engine._p(rc_), engine._stream())
+        else:               # CPU tensors (gloo tests): the same permutation with torch indexing
+            src = (torch.repeat_interleave(start_p - new_start, cnt_p, output_size=total) +
+                   torch.arange(total, device=dev))
+            rk_, rc_ = kk[src], cc[src]
+        regrouped[i] = (rk_, rc_, cnt_p.to(torch.int32))
+    meta[n, 0] = int(n_kmers_local)
+    dist.all_reduce(meta)
+    meta_h = meta.cpu().tolist()
+    tot = [[int(x) for x in meta_h[i][:world]] for i in range(n)]
+    # send order: for every destination class, my chromosomes in index order
+    cls_off = {i: [0] for i in mine}
+    for i in mine:
+        for c in range(world):
+            cls_off[i].append(cls_off[i][-1] + tot[i][c])
+
+    def pack(which, per_class_len=None):
+        pieces, splits = [], []
+        for d in range(world):
+            m = 0
+            for i in mine:
+                if per_class_len is None:
+                    a, b = cls_off[i][d], cls_off[i][d + 1]
+                else:
+                    a, b = cls_poff[d], cls_poff[d + 1]
+                pieces.append(regrouped[i][which][a:b])
+                m += b - a
+            splits.append(m)
+        dtype = {0: torch.int64, 1: torch.int32, 2: torch.int32}[which]
+        return (torch.cat(pieces) if pieces else torch.empty(0, dtype=dtype, device=dev)), splits
+
+    owned_by = [[i for i in range(n) if owner[i] == s] for s in range(world)]
+    out_e = [sum(tot[i][rank] for i in owned_by[s]) for s in range(world)]
+    out_p = [ncls[rank] * len(owned_by[s]) for s in range(world)]
+    send_k, in_e = pack(0)
+    send_c, _ = pack(1)
+    send_p, in_p = pack(2, per_class_len=True)
+    rk = _all_to_all(send_k, in_e, out_e, dist, dev)
+    rc = _all_to_all(send_c, in_e, out_e, dist, dev)
+    rp = _all_to_all(send_p, in_p, out_p, dist, dev)
+    out = {}
+    oe = op = 0
+    my_parts = torch.arange(rank, P, world, device=dev)
+    for s in range(world):
+        for i in owned_by[s]:
+            m = tot[i][rank]
+            if s != rank:
+                pc = rp[op:op + ncls[rank]].to(torch.int64)
+                pidx = torch.zeros(2 * P, dtype=torch.int32, device=dev)
+                pidx[2 * my_parts] = (torch.cumsum(pc, 0) - pc).to(torch.int32)
+                pidx[2 * my_parts + 1] = pc.to(torch.int32)
+                out[i] = (rk[oe:oe + m], rc[oe:oe + m], int(meta_h[i][world]), pidx)
+            oe += m
+            op += ncls[rank]
+    return out, int(meta_h[n][0])
 
 
 def exchange_rows(dm, n_union_local, dist, dev):
@@ -291,21 +410,39 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         e2 = t.start("_x_wait")                      # time until the slowest rank has finished counting
         dist.barrier()
         t.stop(e2)
-        e2 = t.start("_x_dumps")
         local = {i: (dumps[i].keys, dumps[i].counts, dumps[i].length) for i in mine}
-        everything, n_kmers_total = exchange_dumps(local, n, owner, dist, dev, n_kmers)
-        t.stop(e2)
-        e2 = t.start("_x_pindex")
-        pidx, pbits = exchange_pindex({i: dumps[i].pindex for i in mine}, n, owner, dist, dev,
-                                      dumps[mine[0]].pbits if mine else 0)
-        t.stop(e2)
-        for i in range(n):
-            if owner[i] != rank:
-                kk, cc, length = everything[i]
-                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx.get(i), pbits)
+        # same partition bits everywhere (the table is sized for the largest chromosome of the genome)?
+        pb = torch.tensor([dumps[i].pbits if dumps[i].pindex is not None else -1 for i in mine] or [-2],
+                          dtype=torch.int64, device=dev)
+        pmeta = torch.stack([pb.max(), -pb.min()])
+        dist.all_reduce(pmeta, op=dist.ReduceOp.MAX)
+        pb_max, pb_min = int(pmeta[0].item()), -int(pmeta[1].item())
+        by_class = (pb_max == pb_min and pb_max > 0 and n <= 128 and
+                    os.environ.get("SPK_EXCHANGE", "class") == "class" and
+                    os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain")
+        e2 = t.start("_x_dumps")
+        if by_class:
+            # each rank only needs the partition class it will merge: 1/world of every foreign dump
+            got, n_kmers_total = exchange_dumps_by_class(local, {i: dumps[i].pindex for i in mine}, pb_max, n, owner,
+                                                         dist, dev, n_kmers)
+            for i, (kk, cc, length, pidx) in got.items():
+                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx, pb_max)
+            t.stop(e2)
+        else:
+            everything, n_kmers_total = exchange_dumps(local, n, owner, dist, dev, n_kmers)
+            t.stop(e2)
+            e2 = t.start("_x_pindex")
+            pidx, pbits = exchange_pindex({i: dumps[i].pindex for i in mine}, n, owner, dist, dev,
+                                          dumps[mine[0]].pbits if mine else 0)
+            t.stop(e2)
+            for i in range(n):
+                if owner[i] != rank:
+                    kk, cc, length = everything[i]
+                    dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx.get(i), pbits)
         t.stop(e)
     else:
         n_kmers_total = n_kmers
+        by_class = False
     dump_list = [dumps[i] for i in range(n)]
 
     # ---- K3b/K4 matrix + filter: rows are independent -> each rank builds the rows of its share ----------
@@ -327,6 +464,9 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         if int(ok.item()) == 0:
             dm = None
     if dm is None:
+        if world > 1 and by_class:
+            raise OverflowError("a hash partition overflowed the shared-memory union table and the ranks hold only "
+                                "their partition class of the dumps: rerun with SPK_EXCHANGE=gather")
         e = t.start("matrix")
         cm = engine.build_matrix(dump_list, labels, nparts=world, part=rank)
         t.stop(e)

@@ -53,6 +53,41 @@ def _worker(rank, world, port, q):
     pidx2, pb2 = hotpath.exchange_pindex({i: pidx_full[i] for i in range(n) if owner[i] == rank}, n, owner, dist, dev,
                                          pbits + rank)
     ok &= pb2 == 0 and pidx2 == {}
+    # class-wise exchange: a rank receives only the hash partitions p = rank (mod world) of the foreign dumps
+    pb = 4
+    P = 1 << pb
+    dumps_full, pidx_all = {}, {}
+    for i in range(n):
+        gi = torch.Generator().manual_seed(100 + i)
+        cnt = torch.randint(0, 6, (P,), generator=gi)
+        if i == 3:
+            cnt[:] = 0
+        order = torch.randperm(P, generator=gi)                     # partitions lie in arbitrary order in the dump
+        start = torch.zeros(P, dtype=torch.int64)
+        start[order] = torch.cumsum(cnt[order], 0) - cnt[order]
+        tot = int(cnt.sum())
+        kk = torch.randint(0, 2**40, (tot,), generator=gi, dtype=torch.int64)
+        cc = torch.randint(3, 100, (tot,), generator=gi, dtype=torch.int32)
+        pi = torch.zeros(2 * P, dtype=torch.int32)
+        pi[0::2] = start.to(torch.int32)
+        pi[1::2] = cnt.to(torch.int32)
+        dumps_full[i] = (kk, cc, 2000 + i)
+        pidx_all[i] = pi
+    got, total2 = hotpath.exchange_dumps_by_class({i: dumps_full[i] for i in range(n) if owner[i] == rank},
+                                                  {i: pidx_all[i] for i in range(n) if owner[i] == rank}, pb, n, owner,
+                                                  dist, dev, n_kmers_local=7 * (rank + 1))
+    ok &= total2 == sum(7 * (r + 1) for r in range(world))
+    ok &= sorted(got) == [i for i in range(n) if owner[i] != rank]
+    for i, (kk, cc, length, pi) in got.items():
+        fk, fc, fl = dumps_full[i]
+        ok &= length == fl
+        for p_ in range(P):
+            a, m = int(pi[2 * p_]), int(pi[2 * p_ + 1])
+            if p_ % world != rank:
+                ok &= m == 0
+                continue
+            fa, fm = int(pidx_all[i][2 * p_]), int(pidx_all[i][2 * p_ + 1])
+            ok &= m == fm and bool(torch.equal(kk[a:a + m], fk[fa:fa + fm]) and torch.equal(cc[a:a + m], fc[fa:fa + fm]))
     wins = {i: torch.full((i + 1, 3), i, dtype=torch.int64) for i in range(n) if owner[i] == rank}
     allw = hotpath.exchange_windows(wins, n, 3, owner, dist, dev)
     for i in range(n):
@@ -74,3 +109,62 @@ def test_exchange_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _worker_class(rank, world, port, q):
+    """class-wise exchange only, for world sizes that do not divide the partition count evenly"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from subphaser_b200 import hotpath
+    n, pb = 7, 5
+    P = 1 << pb
+    owner = hotpath.lpt_assign([70, 60, 50, 40, 30, 20, 10], world)
+    dev = torch.device("cpu")
+    full, pidx_all = {}, {}
+    for i in range(n):
+        gi = torch.Generator().manual_seed(500 + i)
+        cnt = torch.randint(0, 9, (P,), generator=gi)
+        order = torch.randperm(P, generator=gi)
+        start = torch.zeros(P, dtype=torch.int64)
+        start[order] = torch.cumsum(cnt[order], 0) - cnt[order]
+        tot = int(cnt.sum())
+        full[i] = (torch.randint(0, 2**40, (tot,), generator=gi, dtype=torch.int64),
+                   torch.randint(3, 100, (tot,), generator=gi, dtype=torch.int32), 3000 + i)
+        pi = torch.zeros(2 * P, dtype=torch.int32)
+        pi[0::2] = start.to(torch.int32)
+        pi[1::2] = cnt.to(torch.int32)
+        pidx_all[i] = pi
+    mine = [i for i in range(n) if owner[i] == rank]
+    got, total = hotpath.exchange_dumps_by_class({i: full[i] for i in mine}, {i: pidx_all[i] for i in mine}, pb, n,
+                                                 owner, dist, dev, n_kmers_local=rank + 1)
+    ok = total == world * (world + 1) // 2 and sorted(got) == [i for i in range(n) if owner[i] != rank]
+    for i, (kk, cc, length, pi) in got.items():
+        fk, fc, fl = full[i]
+        ok &= length == fl and int(pi[1::2].sum()) == int(kk.numel()) == int(cc.numel())
+        for p_ in range(P):
+            a, m = int(pi[2 * p_]), int(pi[2 * p_ + 1])
+            fa, fm = int(pidx_all[i][2 * p_]), int(pidx_all[i][2 * p_ + 1])
+            if p_ % world != rank:
+                ok &= m == 0
+            else:
+                ok &= m == fm and bool(torch.equal(kk[a:a + m], fk[fa:fa + fm]) and torch.equal(cc[a:a + m], fc[fa:fa + fm]))
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [3, 4])
+def test_class_exchange_more_ranks_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_class, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(r, True) for r in range(world)]
