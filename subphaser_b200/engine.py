@@ -1,7 +1,7 @@
 """Device-side engine: thin Python orchestration of the libspk kernels.
 
 torch is used for three things only: allocating device/pinned buffers, naming the current CUDA stream
-and (in parallel.py) bootstrapping NCCL.  All arithmetic happens in libspk.so.  Nothing here falls back
+and (in hotpath.py / bench.py) bootstrapping NCCL through torch.distributed.  All arithmetic happens in libspk.so.  Nothing here falls back
 to the CPU: without a CUDA device every entry point raises.
 """
 import ctypes

@@ -12,7 +12,7 @@ MODE = ["partitioned"]
 
 @pytest.fixture(params=["partitioned", "global"], autouse=True)
 def count_mode(request):
-    """every test runs against both counters: v2 (L2-resident partitions) and v1 (global table)"""
+    """every test runs against both counters: partitioned (shared-memory tables) and v1 (global table)"""
     MODE[0] = request.param
     yield
 

@@ -22,7 +22,7 @@ for mode in modes:
         dump = engine.count_packed(seq, k, 3, table=tab)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        print("%s G=%s MB=%s: %.1f ms  %.2f G kmers/s  (valid %d distinct %d dumped %d)" % (
-            mode, os.environ.get("SPK_PCOUNT_G", "4"), os.environ.get("SPK_PCOUNT_TABLE_MB", "16"), ms,
+        print("%s split=%s: %.1f ms  %.2f G kmers/s  (valid %d distinct %d dumped %d)" % (
+            mode, os.environ.get("SPK_PCOUNT_SPLIT", "6"), ms,
             dump.n_valid_kmers / ms / 1e6, dump.n_valid_kmers, dump.n_distinct, len(dump)))
     del tab
