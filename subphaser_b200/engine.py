@@ -388,7 +388,9 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
                          [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
     counters = _zeros(8, torch.int64)
     total = sum(len(d) for d in dumps)
-    cap = max(total // (16 * nparts), 1 << 16)          # candidates are a few % of the union; grown on demand
+    # candidates are a few % of the union; grown on demand.  (On several ranks `total` counts the foreign dumps by
+    # their partition class only, so the share per rank is estimated more generously.)
+    cap = max(total // (16 * nparts) if nparts == 1 else total // (4 * nparts), 1 << 16)
     cap = max(cap, _PM_CAP.get((n, total // 1024), 0))   # what an earlier pass over the same dumps needed
     while True:
         okeys = _empty(cap, torch.int64)
