@@ -40,12 +40,25 @@ struct PcPlan {
     Mixer mx;
     uint64_t n_tiles;
     int two_level, b1, b2;        // two-level scatter: 2^b1 buckets x 2^b2 sub-partitions (b1 + b2 = pbits)
+    int v3;                       // descriptor pipeline (k_v3_*): no histogram passes, no global atomics
+    uint32_t n_st;                // v3: super-tiles (16384 bases)
     size_t off_buf, off_buf1, off_psize, off_pstart, off_cursor, off_segs, off_cur1, off_ustart, off_out, total;
+    size_t off_desc, off_off2, off_chunks, off_btot, off_cb;     // v3
 };
 
 constexpr int SC_TILES = 4;                         // tiles per super-tile of the two-level scatter
 constexpr int SC_CHUNK = SC_TILES * SPK_TILE_BASES; // 16384 entries staged in shared memory at a time
 constexpr int SC_MAX_BINS = 2048;
+constexpr int V3_THREADS = 1024;
+constexpr int V3_CH = SC_CHUNK;                      // 16384: entries of a level-1 super-tile
+// Level-2 chunk: 12288 entries (12 per thread).  With 2^9 sub-partitions a run then averages 24 entries, so that a
+// run longer than the 32 entries one warp-wide load of the counter covers is rare (~5 %; at 16384 it is 45 % of the
+// runs, and every such run costs the counter an un-prefetched dependent load).
+constexpr int V3_E2 = 12;
+constexpr int V3_CH2 = V3_THREADS * V3_E2;
+constexpr int V3_ST1 = SC_CHUNK + 3 * 1024;          // slots of a level-1 super-tile: 16384 entries + <= 3 padding slots per bucket
+static_assert(V3_THREADS * SPK_KMERS_PER_THREAD == V3_CH && SC_TILES * SPK_TILE_THREADS == V3_THREADS, "v3 geometry");
+static_assert(V3_E2 % 4 == 0 && V3_CH2 <= 65535, "v3 chunk geometry");
 
 inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -80,7 +93,42 @@ int make_plan(uint64_t n_bases, int k, int pbits_req, PcPlan* pl) {
     const char* e2 = getenv("SPK_PCOUNT_TWO_LEVEL");
     pl->two_level = (!pl->ent64 && pbits >= 12 && 2 * k - pl->b1 <= 32 && (1 << pl->b1) <= SC_MAX_BINS &&
                      !(e2 && e2[0] == '0')) ? 1 : 0;
+    // v3 descriptor pipeline: 2^9 sub-partitions per bucket (runs of ~32 entries per chunk for the counter),
+    // 2^(pbits-9) buckets (runs of >= 16 entries per super-tile for level 2), 32-bit entries and offsets
+    const char* e3 = getenv("SPK_PCOUNT_PIPE");
+    pl->v3 = 0;
+    pl->n_st = (uint32_t)((pl->n_tiles + SC_TILES - 1) / SC_TILES);
+    if (!pl->ent64 && pbits >= 15 && pbits <= 19 && 2 * k - pbits <= 31 && 2 * k - (pbits - 9) <= 31 &&
+        n_bases < 3400000000ull && !(e3 && e3[0] == 'v' && e3[1] == '2')) {
+        pl->v3 = 1;
+        pl->two_level = 0;
+        pl->b2 = 9;
+        pl->b1 = pbits - 9;
+    }
     size_t off = 0;
+    if (pl->v3) {
+        const size_t nb1 = (size_t)1 << pl->b1, nb2 = (size_t)1 << pl->b2;
+        const size_t max_chunks = ((size_t)pl->n_st * V3_ST1 + V3_CH2 - 1) / V3_CH2 + nb1 + 1;   // (slots: entries + padding)
+        pl->off_buf = off;                                   // chunk-sorted stream (level-2 output)
+        off += al256(max_chunks * V3_CH2 * 4);
+        pl->off_buf1 = off;                                  // super-tile-sorted stream (level-1 output)
+        off += al256(((size_t)pl->n_st + 1) * V3_ST1 * 4);
+        pl->off_desc = off;
+        off += al256(nb1 * (size_t)pl->n_st * 4);
+        pl->off_off2 = off;
+        off += al256(max_chunks * (nb2 + 1) * 2);
+        pl->off_chunks = off;
+        off += al256(max_chunks * 16);
+        pl->off_btot = off;
+        off += al256(nb1 * 4);
+        pl->off_cb = off;
+        off += al256((nb1 + 1) * 4);
+        pl->off_psize = pl->off_pstart = pl->off_cursor = pl->off_segs = pl->off_cur1 = pl->off_ustart = 0;
+        pl->off_out = off;
+        off += 256;
+        pl->total = off;
+        return SPK_OK;
+    }
     pl->off_buf = off;
     off += al256((size_t)(n_bases + 64) * (pl->ent64 ? 8 : 4));
     pl->off_buf1 = off;
@@ -509,6 +557,330 @@ k_scatter_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ pst
     }
 }
 
+
+// ---- v3: descriptor pipeline -----------------------------------------------------------------------------------
+// The two-level scatter above needs the bucket sizes before level 1 can write (k_hist1: a whole extra traversal)
+// and the P partition sizes before level 2 can write (one RED to L2 per k-mer, the hidden limiter of level 1),
+// and both levels generate every k-mer twice (histogram pass, placement pass).  v3 removes all three:
+//   k_v3_l1      one traversal, 1024 threads x 16 k-mers held in registers: rank = smem atomicAdd on the bucket
+//                counter, block scan, placement into a smem buffer, ONE bulk (TMA) store of the locally sorted
+//                super-tile at a fixed stride.  Every bucket's run starts on a 16-byte boundary and is padded to
+//                a multiple of 4 entries with a sentinel, so that level 2 can copy it with 16-byte cp.async.  The
+//                per-(bucket, super-tile) run descriptors (start | slots) go to descT[bucket][super-tile].
+//                No global reservation, no histogram pass, no recompute.
+//   k_v3_plan / k_v3_chunks   bucket totals -> chunk table: bucket b's virtual stream (its runs in super-tile
+//                order) is cut into 12288-slot chunks; every chunk records the run it starts in.
+//   k_v3_l2      one chunk at a time: gather its runs (cp.async 16 B, 8 lanes per run), rank by sub-partition in
+//                registers, scan, place, bulk store of the chunk sorted by sub-partition + the u16 offsets of the
+//                2^b2 sub-partitions inside the chunk.  No partition histogram, no global atomics.
+//   k_part_count32<true>   partition (b, sub) = one short run per chunk of bucket b, gathered (warp per run,
+//                software-pipelined one partition ahead through registers) into the same smem table.
+// Everything is a deterministic function of the input (no atomic decides an output position).
+
+constexpr uint32_t V3_SENT = 0xffffffffu;            // padding slot (entries are < 2^31: see make_plan)
+
+__device__ __forceinline__ void spk_bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(spk_smem_u32(ssrc)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void spk_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void spk_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void spk_cp_async16(uint32_t sdst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void spk_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// exclusive scan over the 1024 threads of a CTA (two barriers, ~30 instructions per thread); s_warp: 32 words
+__device__ __forceinline__ uint32_t v3_scan(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    const uint32_t wt = s_warp[lane];
+    uint32_t wi = wt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+    }
+    total = __shfl_sync(0xffffffffu, wi, 31);
+    const uint32_t prefix = __shfl_sync(0xffffffffu, wi - wt, warp);
+    __syncthreads();
+    return prefix + incl - v;
+}
+
+struct V3Chunk {          // one 12288-slot chunk of a bucket's virtual stream
+    uint32_t st0;         // super-tile whose run contains the chunk's first slot
+    uint32_t skip;        // slots of that run that belong to the previous chunk
+    uint32_t bucket;
+    uint32_t n;           // slots in the chunk (12288 except the last chunk of a bucket)
+};
+
+__global__ void __launch_bounds__(V3_THREADS, 1)
+k_v3_l1(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid, uint64_t n_tiles, int k, Mixer mx,
+        int b1, uint32_t* __restrict__ buf1, uint32_t* __restrict__ descT, uint32_t n_st,
+        uint32_t* __restrict__ btot, uint64_t* __restrict__ stats) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr int PKW = (SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) / 4;   // 1028
+    constexpr int VDW = (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) / 4;     // 516
+    uint32_t* sorted = (uint32_t*)s_raw;                 // [V3_ST1]
+    uint32_t* pk0 = sorted + V3_ST1;                     // [2][PKW]
+    uint32_t* vd0 = pk0 + 2 * PKW;                       // [2][VDW]
+    uint64_t* bar = (uint64_t*)(vd0 + 2 * VDW);          // [2]   (8-byte aligned: V3_ST1, 2*PKW + 2*VDW are even)
+    uint32_t* cnt = (uint32_t*)(bar + 2);                // [1024]
+    uint32_t* off = cnt + V3_THREADS;                    // [1024]
+    __shared__ uint32_t s_warp[32];
+    const int nb = 1 << b1;                              // <= 1024: bucket q is scanned by thread q
+    const int tid = threadIdx.x;
+    const int tile = tid >> 8, t256 = tid & 255;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    const int sh1 = 2 * k - b1;                                    // bucket = h >> sh1
+    const uint64_t m1 = (sh1 >= 64) ? ~0ull : ((1ull << sh1) - 1);  // entry = h & m1  (<= 31 bits)
+    if (tid == 0) {
+        spk_mbar_init(&bar[0], 1);
+        spk_mbar_init(&bar[1], 1);
+        spk_fence_mbar_init();
+    }
+    cnt[tid] = 0;
+    __syncthreads();
+    auto issue = [&](uint64_t st, int buf) {
+        const uint64_t t0 = st * SC_TILES;
+        const int ntl = (int)min((uint64_t)SC_TILES, n_tiles - t0);
+        const uint32_t pb = ntl * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES;
+        const uint32_t vb = ntl * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES;
+        spk_mbar_expect_tx(&bar[buf], pb + vb);
+        spk_bulk_g2s(pk0 + buf * PKW, packed + t0 * SPK_TILE_PACKED_BYTES, pb, &bar[buf]);
+        spk_bulk_g2s(vd0 + buf * VDW, valid + t0 * SPK_TILE_VALID_BYTES, vb, &bar[buf]);
+    };
+    uint64_t n_valid = 0;
+    uint64_t st = blockIdx.x;
+    if (tid == 0 && st < n_st) issue(st, 0);
+    for (uint32_t it = 0; st < n_st; it++, st += gridDim.x) {
+        const int b = it & 1;
+        // (every thread passed the barrier that follows the placement of the previous super-tile, so nobody still
+        //  reads the tile buffer b^1 that is refilled here)
+        if (tid == 0 && st + gridDim.x < n_st) issue(st + gridDim.x, b ^ 1);
+        spk_mbar_wait(&bar[b], (it >> 1) & 1);
+        const int ntl = (int)min((uint64_t)SC_TILES, n_tiles - st * SC_TILES);
+        uint32_t e[SPK_KMERS_PER_THREAD], meta[SPK_KMERS_PER_THREAD];
+        {
+            uint64_t key[SPK_KMERS_PER_THREAD];
+            uint32_t okmask;
+            spk_kmers_from_t(pk0 + b * PKW + tile * (SPK_TILE_PACKED_BYTES / 4),
+                             vd0 + b * VDW + tile * (SPK_TILE_VALID_BYTES / 4), t256, kp, key, okmask);
+            if (tile >= ntl) okmask = 0;                    // tiles past the end were not loaded
+#pragma unroll
+            for (int j = 0; j < SPK_KMERS_PER_THREAD; j++) {
+                meta[j] = 0xffffffffu;
+                e[j] = 0;
+                if ((okmask >> j) & 1u) {
+                    const uint64_t h = mx.fwd(key[j]);
+                    const uint32_t bk = (uint32_t)(h >> sh1);
+                    e[j] = (uint32_t)(h & m1);
+                    meta[j] = (bk << 16) | atomicAdd(&cnt[bk], 1u);     // rank inside the bucket (< 16384)
+                }
+            }
+        }
+        __syncthreads();
+        // bucket q: c entries in (c + 3) & ~3 slots starting at a multiple of 4
+        const uint32_t c = cnt[tid];
+        const uint32_t slots = (c + 3u) & ~3u;
+        uint32_t n_slots;
+        const uint32_t o = v3_scan(slots, s_warp, n_slots);
+        off[tid] = o;
+        cnt[tid] = 0;
+        if (tid < nb) {
+            descT[(size_t)tid * n_st + st] = o | (slots << 16);      // start < 2^16, slots <= 16384
+            if (slots) atomicAdd(&btot[tid], slots);
+        }
+        if (tid == 0) {
+            spk_bulk_wait_read();          // the previous super-tile's bulk store has finished reading `sorted`
+        }
+        n_valid += c;
+        __syncthreads();
+        for (uint32_t i = c; i < slots; i++) sorted[o + i] = V3_SENT;
+#pragma unroll
+        for (int j = 0; j < SPK_KMERS_PER_THREAD; j++)
+            if (meta[j] != 0xffffffffu) sorted[off[meta[j] >> 16] + (meta[j] & 0xffffu)] = e[j];
+        spk_fence_proxy_async();           // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
+        __syncthreads();
+        if (tid == 0 && n_slots) spk_bulk_s2g(buf1 + (size_t)st * V3_ST1, sorted, n_slots * 4);
+    }
+    if (tid == 0) spk_bulk_wait_all();
+    n_valid = spk_warp_sum_u64(n_valid);
+    if ((tid & 31) == 0 && n_valid) atomicAdd((unsigned long long*)&stats[0], (unsigned long long)n_valid);
+}
+
+// bucket totals (slots) -> first chunk of every bucket (single CTA; nb <= 1024)
+__global__ void __launch_bounds__(1024) k_v3_plan(const uint32_t* __restrict__ btot, int nb, uint32_t* __restrict__ cb) {
+    __shared__ uint32_t s_warp[32];
+    const int b = threadIdx.x;
+    const uint32_t nc = b < nb ? (btot[b] + V3_CH2 - 1) / V3_CH2 : 0u;
+    uint32_t tot;
+    const uint32_t excl = v3_scan(nc, s_warp, tot);
+    if (b < nb) cb[b] = excl;
+    if (b == 0) cb[nb] = tot;
+}
+
+// one CTA per bucket: walk its run sizes in super-tile order, note where every chunk starts
+__global__ void __launch_bounds__(1024)
+k_v3_chunks(const uint32_t* __restrict__ descT, uint32_t n_st, const uint32_t* __restrict__ btot,
+            const uint32_t* __restrict__ cb, V3Chunk* __restrict__ chunks) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t b = blockIdx.x;
+    const uint32_t total = btot[b], g0 = cb[b];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n_st; base += 1024) {
+        const uint32_t st = base + threadIdx.x;
+        const uint32_t c = st < n_st ? (descT[(size_t)b * n_st + st] >> 16) : 0u;
+        uint32_t tot;
+        const uint32_t excl = carry + v3_scan(c, s_warp, tot);
+        // chunk boundaries inside this run (a run of up to 16384 slots can hold two)
+        for (uint32_t m = (excl + V3_CH2 - 1) / V3_CH2; c && (uint64_t)m * V3_CH2 < (uint64_t)excl + c; m++) {
+            const uint64_t at = (uint64_t)m * V3_CH2;
+            V3Chunk ch;
+            ch.st0 = st;
+            ch.skip = (uint32_t)(at - excl);
+            ch.bucket = b;
+            ch.n = (uint32_t)min((uint64_t)V3_CH2, (uint64_t)total - at);
+            chunks[g0 + m] = ch;
+        }
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(V3_THREADS, 1)
+k_v3_l2(const uint32_t* __restrict__ buf1, const uint32_t* __restrict__ descT, uint32_t n_st,
+        const V3Chunk* __restrict__ chunks, const uint32_t* __restrict__ n_chunks_p, int b2, int rbits,
+        uint32_t* __restrict__ buf2, uint16_t* __restrict__ off2) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    uint32_t* sorted = (uint32_t*)s_raw;                 // [V3_CH2]
+    uint32_t* stage = sorted + V3_CH2;                   // [V3_CH2]
+    uint32_t* r_src = stage + V3_CH2;                    // [1024] run list of one batch: first slot in buf1 / 4
+    uint32_t* r_dl = r_src + V3_THREADS;                 // [1024] dst | len << 16 (slots)
+    uint32_t* cnt = r_dl + V3_THREADS;                   // [1024]
+    uint32_t* off = cnt + V3_THREADS;                    // [1024]
+    __shared__ uint32_t s_warp[32];
+    const int nb = 1 << b2;                              // <= 1024
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_chunks = *n_chunks_p;
+    const uint32_t rmask = (rbits >= 32) ? 0xffffffffu : ((1u << rbits) - 1u);
+    const uint32_t stage_s = spk_smem_u32(stage);
+    cnt[tid] = 0;
+    __syncthreads();
+
+    // gather the runs of a chunk into `stage` (asynchronous 16-byte copies; completed by cp.async.wait_all + barrier).
+    // The chunk record and this thread's first run descriptor were loaded one iteration earlier: their latency —
+    // two dependent global loads — would otherwise be exposed to all 1024 threads of the only CTA on the SM.
+    auto gather_issue = [&](const V3Chunk ch, const uint32_t d_first) {
+        const uint32_t* drow = descT + (size_t)ch.bucket * n_st;
+        uint32_t acc = 0;
+        for (uint32_t base = ch.st0; base < n_st && acc < ch.n; base += V3_THREADS) {     // block-uniform
+            const uint32_t st = base + tid;
+            uint32_t c = 0, start = 0;
+            if (st < n_st) {
+                const uint32_t d = (base == ch.st0) ? d_first : drow[st];
+                start = d & 0xffffu;
+                c = d >> 16;
+                if (st == ch.st0) { start += ch.skip; c -= ch.skip; }
+            }
+            uint32_t tot;
+            const uint32_t dst = acc + v3_scan(c, s_warp, tot);
+            uint32_t len = 0;
+            if (c && dst < ch.n) len = min(c, ch.n - dst);
+            r_src[tid] = (uint32_t)(((uint64_t)st * V3_ST1 + start) >> 2);
+            r_dl[tid] = len ? (dst | (len << 16)) : 0u;  // len <= 12288, dst < 12288 (dst of a run past the chunk's end can be anything)
+            acc += tot;
+            // runs of the batch that contribute: [0, n_run) (the slots are consecutive, so they are a prefix... except
+            // empty runs in between, which simply have len 0)
+            const uint32_t n_run = min((uint32_t)V3_THREADS, n_st - base);
+            __syncthreads();
+            // 8 lanes per run, 16 bytes per lane and step
+            for (uint32_t r = 4 * warp + (lane >> 3); r < n_run; r += 4 * (V3_THREADS / 32)) {
+                const uint32_t dl = r_dl[r];
+                const uint32_t ln = dl >> 16, d0 = dl & 0xffffu;
+                const uint4* src = reinterpret_cast<const uint4*>(buf1) + r_src[r];
+                for (uint32_t i = (lane & 7); 4 * i < ln; i += 8) spk_cp_async16(stage_s + 4 * (d0 + 4 * i), src + i);
+            }
+            __syncthreads();
+        }
+    };
+    // (record of chunk g + 3G and first descriptor of chunk g + 2G are loaded per iteration: two independent loads)
+    auto load_rec = [&](uint32_t g, V3Chunk& ch) {
+        ch.st0 = ch.skip = ch.bucket = ch.n = 0;
+        if (g < n_chunks) ch = chunks[g];
+    };
+    auto load_desc = [&](uint32_t g, const V3Chunk& ch) -> uint32_t {
+        return (g < n_chunks && ch.st0 + tid < n_st) ? descT[(size_t)ch.bucket * n_st + ch.st0 + tid] : 0u;
+    };
+    uint32_t g = blockIdx.x;
+    const uint32_t G = gridDim.x;
+    V3Chunk cur_ch, nxt_ch, nn_ch;
+    uint32_t nxt_d;
+    load_rec(g, cur_ch);
+    load_rec(g + G, nxt_ch);
+    load_rec(g + 2 * G, nn_ch);
+    if (g < n_chunks) gather_issue(cur_ch, load_desc(g, cur_ch));
+    nxt_d = load_desc(g + G, nxt_ch);
+    for (; g < n_chunks; g += G) {
+        const uint32_t n_s = cur_ch.n;                    // slots (entries + padding)
+        const uint32_t nn_d = load_desc(g + 2 * G, nn_ch);
+        V3Chunk n3_ch;
+        load_rec(g + 3 * G, n3_ch);
+        spk_cp_async_wait_all();
+        __syncthreads();
+        uint32_t e[V3_E2], meta[V3_E2];
+#pragma unroll
+        for (int u = 0; u < V3_E2 / 4; u++) {
+            const uint32_t i0 = 4u * (u * V3_THREADS + tid);
+            uint4 v = make_uint4(V3_SENT, V3_SENT, V3_SENT, V3_SENT);
+            if (i0 < n_s) v = *reinterpret_cast<const uint4*>(stage + i0);       // n_s is a multiple of 4
+            const uint32_t vs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                meta[4 * u + q] = 0xffffffffu;
+                e[4 * u + q] = vs[q] & rmask;
+                if (vs[q] != V3_SENT) {
+                    const uint32_t sub = vs[q] >> rbits;
+                    meta[4 * u + q] = (sub << 16) | atomicAdd(&cnt[sub], 1u);
+                }
+            }
+        }
+        __syncthreads();                                  // `stage` is consumed: the next chunk may stream in
+        if (g + G < n_chunks) gather_issue(nxt_ch, nxt_d);
+        uint32_t n_e;
+        const uint32_t c = cnt[tid];
+        const uint32_t o = v3_scan(c, s_warp, n_e);
+        off[tid] = o;
+        cnt[tid] = 0;
+        uint16_t* orow = off2 + (size_t)g * (nb + 1);
+        if (tid < nb) orow[tid] = (uint16_t)o;
+        if (tid == 0) {
+            orow[nb] = (uint16_t)n_e;
+            spk_bulk_wait_read();
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < V3_E2; j++)
+            if (meta[j] != 0xffffffffu) sorted[off[meta[j] >> 16] + (meta[j] & 0xffffu)] = e[j];
+        spk_fence_proxy_async();
+        __syncthreads();
+        if (tid == 0 && n_e) spk_bulk_s2g(buf2 + (size_t)g * V3_CH2, sorted, (n_e * 4 + 15) & ~15u);
+        cur_ch = nxt_ch;
+        nxt_ch = nn_ch;
+        nxt_d = nn_d;
+        nn_ch = n3_ch;
+    }
+    if (tid == 0) spk_bulk_wait_all();
+}
+
 // ---- phase 2: one partition per CTA iteration, table in shared memory ---------------------------------------
 __device__ __forceinline__ uint32_t fmix32(uint32_t h) {
     h ^= h >> 16;
@@ -786,9 +1158,20 @@ __device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cn
     return 4u;
 }
 
+// GATHER (v3 pipeline): partition p = (bucket b, sub-partition) is not contiguous; it is one run per chunk of bucket
+// b: run r = [off2[g][sub], off2[g][sub + 1]) of chunk g = cb[b] + r.  Warp w owns the runs w, w + 8, ...; lane l
+// loads the descriptor of run w + 8 l two partitions ahead, the first 32 entries of the warp's first 16 runs are
+// loaded one partition ahead (lane i = entry i of the run), longer / later runs are read when they are inserted.
+struct GatherIn {
+    const uint32_t* cb;       // [2^b1 + 1] first chunk of every bucket
+    const uint16_t* off2;     // [(2^b2 + 1) per chunk]
+    int b2;
+};
+
+template <bool GATHER>
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
-               CountOut o, uint32_t retry_cap) {
+               CountOut o, uint32_t retry_cap, GatherIn gi) {
     extern __shared__ __align__(16) uint8_t s_raw[];
     uint32_t* s_key = (uint32_t*)s_raw;
     uint32_t* s_cnt = s_key + PC_SLOTS;
@@ -845,31 +1228,107 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     };
 
     constexpr int PC_PF = 16;
+    constexpr int NW = PC_THREADS / 32;
     const uint64_t G = gridDim.x;
     uint64_t p = blockIdx.x;
-    uint32_t beg = 0, end = 0, nbeg = 0, nend = 0;
-    if (p < P) { beg = pstart[p]; end = pstart[p + 1]; }
-    if (p + G < P) { nbeg = pstart[p + G]; nend = pstart[p + G + 1]; }
+    // contiguous input: [beg, end) of the partition stream; gathered input: this lane's run descriptor (src, len)
+    // and the number of runs (chunks of the bucket) for the current / next / next-next partition of the CTA
+    uint32_t beg = 0, end = 0, nbeg = 0, nend = 0, cnc = 0, nnc = 0;
+    // two dependent loads (chunk range of the bucket, then the run offsets): split over two loop iterations, so
+    // that neither is waited for where it is issued
+    auto range_load = [&](uint64_t pp, uint32_t& g0, uint32_t& g1) {
+        g0 = g1 = 0;
+        if (pp < P) {
+            const uint32_t b = (uint32_t)(pp >> gi.b2);
+            g0 = __ldg(gi.cb + b);
+            g1 = __ldg(gi.cb + b + 1);
+        }
+    };
+    auto desc_load = [&](uint64_t pp, uint32_t g0, uint32_t g1, uint32_t& src, uint32_t& len, uint32_t& nc) {
+        src = 0; len = 0;
+        nc = g1 - g0;
+        const uint32_t r = warp + NW * lane;
+        if (pp < P && r < nc) {
+            const uint32_t nb2 = 1u << gi.b2;
+            const uint32_t sub = (uint32_t)pp & (nb2 - 1);
+            const uint16_t* q = gi.off2 + (size_t)(g0 + r) * (nb2 + 1) + sub;
+            const uint32_t a = __ldg(q), z = __ldg(q + 1);
+            src = (g0 + r) * (uint32_t)V3_CH2 + a;
+            len = z - a;
+        }
+    };
+    uint32_t rg0 = 0, rg1 = 0;       // chunk range of the bucket of partition p + 3G
     uint32_t cur[PC_PF];
+    if constexpr (GATHER) {
+        range_load(p, rg0, rg1);
+        desc_load(p, rg0, rg1, beg, end, cnc);
+        range_load(p + G, rg0, rg1);
+        desc_load(p + G, rg0, rg1, nbeg, nend, nnc);
+        range_load(p + 2 * G, rg0, rg1);
 #pragma unroll
-    for (int u = 0; u < PC_PF; u++) {
-        const uint32_t i = beg + u * PC_THREADS + tid;
-        cur[u] = i < end ? __ldcs(buf + i) : 0;
+        for (int u = 0; u < PC_PF; u++) {
+            const uint32_t sr = __shfl_sync(0xffffffffu, beg, u), ln = __shfl_sync(0xffffffffu, end, u);
+            cur[u] = (uint32_t)lane < ln ? __ldcs(buf + sr + lane) : 0;
+        }
+    } else {
+        if (p < P) { beg = pstart[p]; end = pstart[p + 1]; }
+        if (p + G < P) { nbeg = pstart[p + G]; nend = pstart[p + G + 1]; }
+#pragma unroll
+        for (int u = 0; u < PC_PF; u++) {
+            const uint32_t i = beg + u * PC_THREADS + tid;
+            cur[u] = i < end ? __ldcs(buf + i) : 0;
+        }
     }
     for (; p < P; p += G) {
         uint32_t nxt[PC_PF];
+        uint32_t nnbeg = 0, nnend = 0, nnnc = 0;
+        if constexpr (GATHER) {
 #pragma unroll
-        for (int u = 0; u < PC_PF; u++) {
-            const uint32_t i = nbeg + u * PC_THREADS + tid;
-            nxt[u] = i < nend ? __ldcs(buf + i) : 0;
+            for (int u = 0; u < PC_PF; u++) {
+                const uint32_t sr = __shfl_sync(0xffffffffu, nbeg, u), ln = __shfl_sync(0xffffffffu, nend, u);
+                nxt[u] = (uint32_t)lane < ln ? __ldcs(buf + sr + lane) : 0;
+            }
+            desc_load(p + 2 * G, rg0, rg1, nnbeg, nnend, nnnc);
+            range_load(p + 3 * G, rg0, rg1);
+        } else {
+#pragma unroll
+            for (int u = 0; u < PC_PF; u++) {
+                const uint32_t i = nbeg + u * PC_THREADS + tid;
+                nxt[u] = i < nend ? __ldcs(buf + i) : 0;
+            }
+            if (p + 2 * G < P) { nnbeg = pstart[p + 2 * G]; nnend = pstart[p + 2 * G + 1]; }
         }
-        uint32_t nnbeg = 0, nnend = 0;
-        if (p + 2 * G < P) { nnbeg = pstart[p + 2 * G]; nnend = pstart[p + 2 * G + 1]; }
+        // gathered input: what the prefetch did not cover (entries 32.. of a run, the runs of lanes 16..31) is loaded
+        // here, before the first probes, so that its latency hides under them (first NLO such runs; the rest below)
+        constexpr int NLO = 2;
+        uint32_t lo[NLO], lov = 0, todo = 0, todo_long = 0;
+        if constexpr (GATHER) {
+            todo = __ballot_sync(0xffffffffu, end > (lane < PC_PF ? 32u : 0u));
+#pragma unroll
+            for (int q = 0; q < NLO; q++) {
+                lo[q] = 0;
+                if (todo) {                                   // warp-uniform
+                    const int u = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const uint32_t sr = __shfl_sync(0xffffffffu, beg, u), ln = __shfl_sync(0xffffffffu, end, u);
+                    const uint32_t i = (u < PC_PF ? 32u : 0u) + lane;
+                    if (i < ln) {
+                        lo[q] = __ldcs(buf + sr + i);
+                        lov |= 1u << q;
+                    }
+                    if (ln > (u < PC_PF ? 64u : 32u)) todo_long |= 1u << u;
+                }
+            }
+        }
         // ---- insert, first probes (straight-line); failures are queued with one reservation per thread ----
         uint32_t failm = 0;
 #pragma unroll
-        for (int u = 0; u < PC_PF; u++)
-            if (beg + u * PC_THREADS + tid < end && !try_home(cur[u])) failm |= 1u << u;
+        for (int u = 0; u < PC_PF; u++) {
+            bool have;
+            if constexpr (GATHER) have = (uint32_t)lane < __shfl_sync(0xffffffffu, end, u);
+            else have = beg + u * PC_THREADS + tid < end;
+            if (have && !try_home(cur[u])) failm |= 1u << u;
+        }
         if (failm) {
             uint32_t qi = atomicAdd(&s_nq, (uint32_t)__popc(failm));
             if (qi + __popc(failm) <= retry_cap) {
@@ -886,16 +1345,47 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
                     }
             }
         }
-        for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
-            uint32_t t[4];
+        if constexpr (GATHER) {
+            // what the prefetch did not cover: entries 32.. of the first 16 runs of the warp, the runs of lanes 16..31,
+            // and (a bucket with more than 256 chunks) the runs beyond the descriptor registers
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t i = base + u * PC_THREADS + tid;
-                t[u] = i < end ? __ldcs(buf + i) : 0;
+            for (int q = 0; q < NLO; q++)
+                if ((lov >> q) & 1u) insert(lo[q]);
+            while (todo | todo_long) {                        // rare: more than NLO such runs, or a run beyond 64 entries
+                const bool lg = todo == 0;
+                const uint32_t m = lg ? todo_long : todo;
+                const int u = __ffs(m) - 1;
+                if (lg) todo_long &= todo_long - 1;
+                else todo &= todo - 1;
+                const uint32_t sr = __shfl_sync(0xffffffffu, beg, u), ln = __shfl_sync(0xffffffffu, end, u);
+                for (uint32_t i = (u < PC_PF ? 32u : 0u) + (lg ? 32u : 0u) + lane; i < ln; i += 32)
+                    insert(__ldcs(buf + sr + i));
             }
+            if (cnc > 32 * NW) {
+                const uint32_t nb2 = 1u << gi.b2;
+                const uint32_t b = (uint32_t)(p >> gi.b2), sub = (uint32_t)p & (nb2 - 1);
+                const uint32_t g0 = __ldg(gi.cb + b);
+                for (uint32_t r = 32 * NW + warp; r < cnc; r += NW) {
+                    const uint16_t* q = gi.off2 + (size_t)(g0 + r) * (nb2 + 1) + sub;
+                    const uint32_t a = __ldg(q), z = __ldg(q + 1);
+                    const uint32_t sr = (g0 + r) * (uint32_t)V3_CH2 + a;
+                    for (uint32_t i = a + lane; i < z; i += 32) insert(__ldcs(buf + sr + (i - a)));
+                    if (lane == 0) sumall += z - a;
+                }
+            }
+            sumall += end;                      // this lane's run (every run is owned by exactly one lane)
+        } else {
+            for (uint32_t base = beg + PC_PF * PC_THREADS; base < end; base += 4 * PC_THREADS) {   // oversized partition
+                uint32_t t[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (base + u * PC_THREADS + tid < end) insert(t[u]);
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = base + u * PC_THREADS + tid;
+                    t[u] = i < end ? __ldcs(buf + i) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (base + u * PC_THREADS + tid < end) insert(t[u]);
+            }
         }
         __syncthreads();
         // ---- insert, queued entries: all lanes probe together ----
@@ -919,7 +1409,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
                 o.pindex[2 * p + 1] = total;
             }
             distinct += s_ndist;
-            sumall += end - beg;
+            if constexpr (!GATHER) sumall += end - beg;
         }
         __syncthreads();
         // ---- sweep: histogram, write the dump, clear ----
@@ -994,6 +1484,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
 #pragma unroll
         for (int u = 0; u < PC_PF; u++) cur[u] = nxt[u];
         beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
+        cnc = nnc; nnc = nnnc;
     }
     // ---- per-CTA totals ----
     if (o.histo) {
@@ -1028,15 +1519,54 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
              uint32_t* d_counts, uint64_t cap, uint64_t* d_stats, uint64_t* d_histo, uint32_t histo_len,
              uint32_t* d_pindex, cudaStream_t st) {
     void* buf = ws + pl.off_buf;
+    uint64_t* out_cursor = (uint64_t*)(ws + pl.off_out);
+    SPK_CUDA(cudaMemsetAsync(out_cursor, 0, 256, st));
+    if (pl.n_tiles == 0) return SPK_OK;
+    const int sms = spk_num_sms();
+    if (pl.v3 && !ENT64) {
+        uint32_t* buf1 = (uint32_t*)(ws + pl.off_buf1);
+        uint32_t* descT = (uint32_t*)(ws + pl.off_desc);
+        uint16_t* off2 = (uint16_t*)(ws + pl.off_off2);
+        V3Chunk* chunks = (V3Chunk*)(ws + pl.off_chunks);
+        uint32_t* btot = (uint32_t*)(ws + pl.off_btot);
+        uint32_t* cb = (uint32_t*)(ws + pl.off_cb);
+        const int nb1 = 1 << pl.b1, nb2 = 1 << pl.b2;
+        SPK_CUDA(cudaMemsetAsync(btot, 0, (size_t)nb1 * 4, st));
+        constexpr size_t TILE_BYTES = 2 * ((SC_TILES * SPK_TILE_PACKED_BYTES + SPK_HALO_PACKED_BYTES) +
+                                           (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES)) + 16;
+        const size_t smem1 = (size_t)V3_ST1 * 4 + TILE_BYTES + (size_t)V3_THREADS * 8;
+        const size_t smem2 = (size_t)V3_CH2 * 8 + (size_t)V3_THREADS * 16;
+        SPK_CUDA(cudaFuncSetAttribute(k_v3_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        SPK_CUDA(cudaFuncSetAttribute(k_v3_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_v3_l1<<<(unsigned)min((uint32_t)sms, pl.n_st), V3_THREADS, smem1, st>>>(pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, buf1,
+                                                                                  descT, pl.n_st, btot, d_stats);
+        SPK_LAUNCH_CHECK();
+        k_v3_plan<<<1, 1024, 0, st>>>(btot, nb1, cb);
+        SPK_LAUNCH_CHECK();
+        k_v3_chunks<<<nb1, 1024, 0, st>>>(descT, pl.n_st, btot, cb, chunks);
+        SPK_LAUNCH_CHECK();
+        k_v3_l2<<<(unsigned)min((uint32_t)sms, 2 * pl.n_st + (uint32_t)nb1 + 1u), V3_THREADS, smem2, st>>>(
+            buf1, descT, pl.n_st, chunks, cb + nb1, pl.b2, pl.mx.rbits, (uint32_t*)buf, off2);
+        SPK_LAUNCH_CHECK();
+        SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PC_SLOTS * 8 + PC_RETRY * 4));
+        uint32_t retry_cap = PC_RETRY;
+        if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
+            const long v = atol(e);
+            if (v >= 0 && v < PC_RETRY) retry_cap = (uint32_t)v;
+        }
+        CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower, d_pindex};
+        GatherIn gi{cb, off2, pl.b2};
+        k_part_count32<true><<<(unsigned)min((uint64_t)sms * 3, pl.P), PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>(
+            (const uint32_t*)buf, nullptr, pl.P, pl.mx, o, retry_cap, gi);
+        SPK_LAUNCH_CHECK();
+        return SPK_OK;
+    }
     uint32_t* psize = (uint32_t*)(ws + pl.off_psize);
     uint32_t* pstart = (uint32_t*)(ws + pl.off_pstart);
     uint32_t* cursor = (uint32_t*)(ws + pl.off_cursor);
     uint32_t* segs = (uint32_t*)(ws + pl.off_segs);
-    uint64_t* out_cursor = (uint64_t*)(ws + pl.off_out);
     SPK_CUDA(cudaMemsetAsync(psize, 0, (pl.P + 1) * 4, st));
-    SPK_CUDA(cudaMemsetAsync(out_cursor, 0, 256, st));
-    if (pl.n_tiles == 0) return SPK_OK;
-    const int sms = spk_num_sms();
     const unsigned pass_grid = (unsigned)min((uint64_t)sms * 4, pl.n_tiles);
     const uint64_t nseg = (pl.P + 1023) / 1024;
     if (pl.two_level && !ENT64) {
@@ -1057,12 +1587,9 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
                                    (SC_TILES * SPK_TILE_VALID_BYTES + SPK_HALO_VALID_BYTES) + 8 + 16 + 15) / 16 * 16;
         const size_t smem1 = tile_bytes + scatter_smem_bytes(1 << pl.b1);
         const size_t smem2 = scatter_smem_bytes(1 << pl.b2);
-        static bool l_attr = false;
-        if (!l_attr) {
-            SPK_CUDA(cudaFuncSetAttribute(k_scatter_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            SPK_CUDA(cudaFuncSetAttribute(k_scatter_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            l_attr = true;
-        }
+        // (the attribute is per device: set it on every call, not once per process)
+        SPK_CUDA(cudaFuncSetAttribute(k_scatter_l1, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        SPK_CUDA(cudaFuncSetAttribute(k_scatter_l2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         const uint64_t n_super = (pl.n_tiles + SC_TILES - 1) / SC_TILES;
         k_scatter_l1<<<(unsigned)min((uint64_t)sms * 2, n_super), SPK_TILE_THREADS, smem1, st>>>(
             pk, vl, pl.n_tiles, pl.k, pl.mx, pl.b1, cur1, buf1, psize, red_split);
@@ -1093,27 +1620,20 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         SPK_LAUNCH_CHECK();
     }
     const size_t smem = (size_t)PC_SLOTS * (ENT64 ? 12 : 8) + (size_t)PC_LIST * 2;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[ENT64 ? 1 : 0]) {
-        SPK_CUDA(cudaFuncSetAttribute(k_part_count<ENT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[ENT64 ? 1 : 0] = true;
-    }
+    SPK_CUDA(cudaFuncSetAttribute(k_part_count<ENT64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower, d_pindex};
     const unsigned cgrid = (unsigned)min((uint64_t)sms * (ENT64 ? 2 : 3), pl.P);
     const char* v1 = getenv("SPK_PCOUNT_DUMP");        // "list": the 64-bit-slot kernel with the occupied-slot list
     if (!ENT64 && pl.mx.rbits <= 31 && lower >= 1 && !(v1 && v1[0] == 'l')) {
-        static bool attr32 = false;
-        if (!attr32) {
-            SPK_CUDA(cudaFuncSetAttribute(k_part_count32, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SLOTS * 8 + PC_RETRY * 4));
-            attr32 = true;
-        }
+        SPK_CUDA(cudaFuncSetAttribute(k_part_count32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PC_SLOTS * 8 + PC_RETRY * 4));
         uint32_t retry_cap = PC_RETRY;
         if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
             const long v = atol(e);
             if (v >= 0 && v < PC_RETRY) retry_cap = (uint32_t)v;
         }
-        k_part_count32<<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P, pl.mx, o,
-                                                                              retry_cap);
+        k_part_count32<false><<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P,
+                                                                                     pl.mx, o, retry_cap, GatherIn{});
     } else {
         k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);
     }

@@ -75,10 +75,9 @@ __device__ __forceinline__ uint32_t spk_rev2_32(uint32_t x) {
 //   forward_j = (rev2(W) >> 2(48-k-j)) & kmask          (rev2 = order of the 2-bit groups reversed)
 // rev2(W) is shifted once per thread by the k-dependent 2(33-k) bits, so every per-position shift is a
 // compile-time constant: 2 funnel shifts + 2 masks per word instead of a 64-bit shift/or/and chain.
-__device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_t* vd, const SpkKmerParams& p,
-                                               uint64_t (&key)[SPK_KMERS_PER_THREAD],
-                                               uint32_t& okmask) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void spk_kmers_from_t(const uint32_t* pk, const uint32_t* vd, const int tid,
+                                                 const SpkKmerParams& p, uint64_t (&key)[SPK_KMERS_PER_THREAD],
+                                                 uint32_t& okmask) {
     const uint32_t w0 = pk[tid], w1 = pk[tid + 1], w2 = pk[tid + 2];
     const uint32_t v0 = vd[tid >> 1], v1 = vd[(tid >> 1) + 1];
     const uint64_t vbits = (((uint64_t)v1 << 32) | v0) >> ((tid & 1) * 16);
@@ -113,6 +112,12 @@ __device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_
         }
     }
     okmask = (uint32_t)(~x) & 0xffffu;
+}
+
+__device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_t* vd, const SpkKmerParams& p,
+                                               uint64_t (&key)[SPK_KMERS_PER_THREAD],
+                                               uint32_t& okmask) {
+    spk_kmers_from_t(pk, vd, threadIdx.x, p, key, okmask);
 }
 
 // Canonical k-mer starting at base `o` of a tile (shared-memory words `pk`), for out-of-line paths that need

@@ -103,6 +103,74 @@ def gen_fisher_enrich(S_mod):
     jdump(cases, "fisher_enrich.json")
 
 
+def gen_enrich_ltr(S_mod):
+    """Stats.enrich_ltr (Stats.py:33-73) on per-sequence rows: ids `chrom:start-end` (LTRs) and ids of chromosomes
+    that are not in d_sg; the 6-column TSV and both returned dicts are the fixture."""
+    rng = np.random.default_rng(21)
+    cases = []
+    for S, nrow, scale in ((2, 60, 40), (3, 80, 300), (3, 25, 5000)):
+        colnames = ["SG%d" % (i + 1) for i in range(S)]
+        chroms = ["%d%s" % (c + 1, "ABD"[s]) for c in range(3) for s in range(S)]
+        d_sg = {c: colnames["ABD".index(c[-1])] for c in chroms}
+        d_sg.pop(chroms[-1])                       # a chromosome without an assignment -> obs_sg None
+        rownames, matrix = [], []
+        for r in range(nrow):
+            c = chroms[int(rng.integers(0, len(chroms)))] if r % 11 else "scaffold_%d" % r
+            a = int(rng.integers(0, 10_000_000))
+            rid = "%s:%d-%d" % (c, a, a + int(rng.integers(100, 9000)))
+            own = "ABD".index(c[-1]) if c[-1] in "ABD"[:S] and r % 5 else int(rng.integers(0, S))
+            row = rng.integers(0, max(scale // 8, 2), S)
+            row[own] += int(rng.integers(0, scale))
+            if r % 13 == 0:
+                row[:] = 0
+                row[int(rng.integers(0, S))] = 1
+            rownames.append((rid, 0, 100000000))
+            matrix.append([int(x) for x in row])
+        matrix = [m for m in matrix]
+        keep = [i for i, m in enumerate(matrix) if sum(m) > 0]     # stack_matrix never emits all-zero rows
+        rownames = [rownames[i] for i in keep]
+        matrix = [matrix[i] for i in keep]
+        out = io.StringIO()
+        d_enriched, d_exchange = S_mod.enrich_ltr(out, d_sg, matrix, colnames=colnames, rownames=rownames,
+                                                  max_pval=0.05, ncpu=1)
+        cases.append(dict(S=S, colnames=colnames, d_sg=d_sg, rownames=[list(r) for r in rownames], matrix=matrix,
+                          text=out.getvalue(), d_enriched=d_enriched, d_exchange=d_exchange))
+    jdump(cases, "enrich_ltr.json")
+
+
+def gen_stat_enrich():
+    """stat_enrich.main (stat_enrich.py:4-37) on 4-column enrich tables (the layout it unpacks, :11)."""
+    argv = sys.argv
+    sys.argv = [argv[0], os.devnull]               # the reference evaluates sys.argv[1] at definition time (:4)
+    try:
+        SE = ref_shims.load("stat_enrich")
+    finally:
+        sys.argv = argv
+    rng = np.random.default_rng(22)
+    cases = []
+    for S, nrow in ((2, 40), (3, 90)):
+        sgs = ["SG%d" % (i + 1) for i in range(S)]
+        anns = ["Copia", "Gypsy", "Ty3", "unknown", "LINE"]
+        lines = ["#id\tsubgenome\tp_value\tcounts"]
+        # every (annotation, subgenome) pair occurs at least once: the reference adds a zero vector of length
+        # len(subgenomes) for a missing pair, which only broadcasts when that equals the number of count columns
+        pairs = [(a, g) for a in anns for g in sgs]
+        for r in range(nrow):
+            a, g = pairs[r] if r < len(pairs) else (anns[int(rng.integers(0, len(anns)))], sgs[int(rng.integers(0, S))])
+            counts = ",".join(str(int(x)) for x in rng.integers(0, 500, S))
+            lines.append("%s-%d_%s\t%s\t%r\t%s" % (a, r, "x" * int(rng.integers(1, 4)), g, float(rng.random()), counts))
+        text = "\n".join(lines) + "\n"
+        tmp = tempfile.mkdtemp()
+        path = os.path.join(tmp, "enrich.tsv")
+        with open(path, "w") as f:
+            f.write(text)
+        out = io.StringIO()
+        SE.main(inTsv=path, outStat=out)
+        shutil.rmtree(tmp)
+        cases.append(dict(input=text, output=out.getvalue()))
+    jdump(cases, "stat_enrich.json")
+
+
 def gen_map_stack(Seqs, Circos):
     rng = np.random.default_rng(3)
     cases = []
@@ -290,7 +358,7 @@ def gen_pipeline(J, C, Seqs, Circos, S_mod):
     print("wrote pipeline_small/: union", n_union, "diff", len(d_mat2), "sig", len(d_kmers) // 2, "d_sg", dict(cluster.d_sg))
 
 
-def main():
+def main(only=None):
     if not ref_shims.available():
         sys.exit("reference not present: fixtures can only be regenerated in the build container")
     J = ref_shims.load("Jellyfish")
@@ -302,6 +370,8 @@ def main():
     logging.getLogger().setLevel(logging.WARNING)
     gen_filter(J)
     gen_fisher_enrich(S_mod)
+    gen_enrich_ltr(S_mod)
+    gen_stat_enrich()
     gen_map_stack(Seqs, Circos)
     gen_map_multi(Seqs)
     gen_cluster_units(C)

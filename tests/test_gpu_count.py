@@ -138,3 +138,79 @@ def test_retry_queue_overflow_paths(monkeypatch):
         _check(fa, 17, 1)
         _check(fa, 15, 2)
     monkeypatch.delenv("SPK_PCOUNT_RETRY_CAP")
+
+
+def _gpu_count_forced(fasta_bytes, k, lower, genome_max_bases):
+    """Partitioned counter with the partition bits of a genome whose largest chromosome has `genome_max_bases`
+    bases (what hotpath does for every chromosome of a genome): small inputs then run the large-genome kernels."""
+    from subphaser_b200 import engine
+    d, n = engine.to_device_bytes(fasta_bytes)
+    seq = engine.pack_fasta(d, n)
+    table = engine.CountTable(max(seq.n_bases, 1), k, lower, mode="partitioned", genome_max_bases=genome_max_bases)
+    dump = engine.count_packed(seq, k, lower, table=table)
+    keys, counts = dump.to_host()
+    order = np.argsort(keys, kind="stable")
+    return seq, dump, table, keys[order], counts[order]
+
+
+def _check_forced(fa, k, lower, genome_max_bases, want_pbits):
+    from oracle import kmers
+    okeys, ocounts, st = kmers.count_fasta(fa, k, lower)
+    seq, dump, table, keys, counts = _gpu_count_forced(fa, k, lower, genome_max_bases)
+    assert table.pbits == want_pbits
+    assert dump.n_valid_kmers == st["n_valid_kmers"]
+    assert dump.n_distinct == st["n_distinct"]
+    assert dump.length == st["sum_dumped"]
+    np.testing.assert_array_equal(keys, okeys)
+    np.testing.assert_array_equal(counts, ocounts)
+    # the dump is grouped by partition and pindex describes it exactly
+    pidx = dump.pindex.cpu().numpy().astype(np.int64)
+    assert int(pidx[1::2].sum()) == len(keys)
+    return dump
+
+
+@pytest.mark.parametrize("k,gmax,pbits", [(17, 100_000_000, 15), (17, 800_000_000, 18), (15, 300_000_000, 17),
+                                          (20, 1_500_000_000, 19), (16, 600_000_000, 18)])
+def test_v3_descriptor_pipeline(k, gmax, pbits, monkeypatch):
+    """Partition bits 15..19 select the descriptor pipeline (k_v3_l1 / k_v3_chunks / k_v3_l2 / gathering counter):
+    bit-exact against the oracle, and identical to the two-level scatter pipeline (SPK_PCOUNT_PIPE=v2)."""
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    rng = np.random.default_rng(k + pbits)
+    unit = util.random_seq(rng, 3000)
+    parts = []
+    for i in range(8):
+        parts.append(util.messy_seq(rng, 250_000, repeat_unit="ACGTTGCA" if i == 3 else None))
+        parts.append(unit if i % 3 else unit[:1500] + "N" * 20 + unit[1500:])
+    fa = util.fasta([("big", "".join(parts))])
+    for lower in (1, 3):
+        d3 = _check_forced(fa, k, lower, gmax, pbits)
+        monkeypatch.setenv("SPK_PCOUNT_PIPE", "v2")
+        d2 = _check_forced(fa, k, lower, gmax, pbits)
+        monkeypatch.delenv("SPK_PCOUNT_PIPE")
+        # same partition function: the per-partition dump sizes agree between the two pipelines
+        np.testing.assert_array_equal(d3.pindex.cpu().numpy()[1::2], d2.pindex.cpu().numpy()[1::2])
+
+
+def test_v3_skewed_buckets():
+    """Low-complexity input: one bucket receives (almost) everything — runs of 16384 entries, chunks that start in
+    the middle of a run, a bucket with more chunks than the counter's descriptor registers cover (> 256), empty
+    buckets, and sub-partitions far above the table's first-probe capacity."""
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    rng = np.random.default_rng(77)
+    seq = "A" * 4_600_000 + util.random_seq(rng, 40_000) + "AC" * 300_000 + "N" * 100 + "ACGGT" * 100_000
+    fa = util.fasta([("skew", seq)])
+    _check_forced(fa, 17, 1, 700_000_000, 18)
+    _check_forced(fa, 17, 3, 700_000_000, 18)
+    _check_forced(fa, 15, 2, 100_000_000, 15)
+
+
+def test_v3_tiny_and_empty_inputs():
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    rng = np.random.default_rng(78)
+    for seq in ("", "ACGTACGTAC", util.random_seq(rng, 5000), "N" * 20000, util.random_seq(rng, 16384 + 16),
+                util.random_seq(rng, 4 * 16384 + 17)):
+        fa = util.fasta([("t", seq)])
+        _check_forced(fa, 17, 1, 700_000_000, 18)
