@@ -37,7 +37,8 @@ def parse_args():
     ap.add_argument("--replicates", type=int, default=1000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-bases", type=float, default=3e8)
+    ap.add_argument("--cpu-sample-bases", type=float, default=7.1e7,
+                    help="size of the replica of the workload the CPU arm runs (bases)")
     return ap.parse_args()
 
 
@@ -98,63 +99,119 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_count_sample(fasta_bytes, k, lower, threads):
-    """The CPU arm: oracle/kmer_count.c (jellyfish-semantics port) on all host cores."""
-    from oracle import kmers
+def cpu_replica(args, threads):
+    """The workload shrunk to ~70 Mb (same chromosome count, subgenomes, thresholds; repeat library scaled so that
+    copy numbers stay those of the full genome), generated on the HOST by the numpy twin of the synthetic
+    generator — nothing of libspk is touched."""
+    import numpy as np  # noqa: F401
+    from concurrent.futures import ThreadPoolExecutor
+    from subphaser_b200 import synth
+    full, cfg = synth.plan_for(args.config, scale=args.scale)
+    g_full = sum(c["length"] for c in full.chroms)
+    cscale = args.scale * min(1.0, args.cpu_sample_bases / g_full)
+    plan, _ = synth.plan_for(args.config, scale=cscale)
+    with ThreadPoolExecutor(max(1, min(threads, 16))) as ex:
+        fastas = list(ex.map(lambda c: synth.synth_chromosome_host(plan, c), plan.chroms))
+    return plan, cfg, fastas, g_full, cscale
+
+
+def cpu_path_once(plan, cfg, fastas, threads, replicates):
+    from oracle import cpu_path
     t0 = time.perf_counter()
-    keys, counts, st = kmers.count_fasta(fasta_bytes, k, lower, nthreads=threads)
-    dt = time.perf_counter() - t0
-    return st["n_valid_kmers"], dt
+    res = cpu_path.run(fastas, plan.labels, plan.sgs, cfg["k"], cfg["window"], threads, lower_count=3, min_freq=200,
+                       max_freq=10000, min_fold=2, baseline=1, ratio=1, nsg=len(plan.sg_letters),
+                       replicates=replicates, max_pval=0.05, bin_size=10000, chunk_size=10_000_000)
+    return res, time.perf_counter() - t0
+
+
+def cpu_baseline_dict(res, full, g_full, cscale, wall):
+    """`cpu_baseline` object of the JSON line: per-stage seconds on the replica + the whole-path rate extrapolated to the
+    full workload (oracle/cpu_path.extrapolate)."""
+    stages = {k_: {"seconds": round(v["seconds"], 4), "measured": v["measured"], "units": int(v["units"]), "unit": v["unit"],
+                   **({"extrapolated": v["extrapolated"]} if "extrapolated" in v else {})}
+              for k_, v in res["stages"].items()}
+    return {"value": full["kmers_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+            "windows_per_s": full["windows_per_s"],
+            "sample": "whole path (count -> matrix -> filter -> cluster+bootstrap -> t-test -> map -> stack -> enrich) on a "
+                      "scale-%.4g replica of the workload (%d bases, %d chromosomes): C port of the jellyfish semantics "
+                      "for the counter, numpy/scipy/sklearn restatement of the reference's Python for the rest "
+                      "(oracle/cpu_path.py); %.1f s of CPU work; per-element Python stages credited with perfect "
+                      "scaling over %d cores; rates extrapolated linearly to %.3g bases (bootstrap held fixed)" % (
+                          cscale, res["n_bases"], len(res["labels"]), wall, res["cores"], g_full),
+            "replica": {"kmers_per_s": res["kmers_per_s"], "windows_per_s": res["windows_per_s"], "seconds": res["seconds"],
+                        "n_kmers": int(res["n_kmers"]), "n_union": int(res["n_union"]), "n_diff": int(res["n_diff"]),
+                        "n_windows": int(res["n_windows"]), "labels": [int(x) for x in res["labels"]]},
+            "stages": stages}
 
 
 def run_reference(args):
-    """--impl reference: the path's CPU implementation timed on the box's host cores.  jellyfish is not
-    installable here, so the counter is the documented port (oracle/kmer_count.c); rank 0 only."""
+    """--impl reference: the path's CPU implementation (oracle/cpu_path.py) on the box's host cores, every stage of the
+    path, on a bounded replica of the same workload; rank 0 only.  jellyfish / fisher cannot be installed here, so the
+    arm is kind "port" (see cpu_path.py for what stands in for what)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
+    from oracle import cpu_path
     from subphaser_b200 import synth
-    plan, cfg = synth.plan_for(args.config, scale=args.scale)
     threads = len(os.sched_getaffinity(0))
-    sample_bases = int(min(args.cpu_sample_bases, plan.chroms[0]["length"]))
-    fasta = host_sample(plan, sample_bases)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_count_sample(fasta, cfg["k"], 3, threads)
-    n_k, total = 0, 0.0
+    plan, cfg, fastas, g_full, cscale = cpu_replica(args, threads)
+    full_plan, _ = synth.plan_for(args.config, scale=args.scale)
+    for _ in range(1 if args.warmup > 0 else 0):          # one warm-up pass (imports, page cache) bounds the run time
+        cpu_path_once(plan, cfg, fastas, threads, args.replicates)
+    walls, last = [], None
     for _ in range(args.steps):
-        nk, dt = cpu_count_sample(fasta, cfg["k"], 3, threads)
-        n_k += nk
-        total += dt
-    value = n_k / total
-    sample = "count+dump (C port of jellyfish semantics, %d threads) of the first %d bases of chromosome %s of %s" % (
-        threads, sample_bases, plan.chroms[0]["name"], args.config)
+        last, wall = cpu_path_once(plan, cfg, fastas, threads, args.replicates)
+        walls.append(wall)
+    full = cpu_path.extrapolate(last, g_full)
+    cb = cpu_baseline_dict(last, full, g_full, cscale, sum(walls) / len(walls))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "impl": "reference", "metric": METRIC, "value": full["kmers_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args, plan, cfg), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(args, full_plan, cfg), "sample": cb["sample"]},
+        "windows_per_s": full["windows_per_s"], "cpu_baseline": cb,
+        "e2e": {"value": full["kmers_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "windows_per_s": full["windows_per_s"]},
     }))
 
 
 def host_sample(plan, sample_bases):
-    """FASTA bytes of a prefix of chromosome 0, generated on the device and copied back (or with the
-    numpy twin of the generator when no GPU is present, e.g. for the reference arm on a CPU box)."""
-    import numpy as np
-    import torch
+    """FASTA bytes of a prefix-length copy of chromosome 0, generated on the device and copied back."""
     from subphaser_b200 import synth
     chrom = dict(plan.chroms[0])
     chrom["length"] = int(sample_bases)
-    if torch.cuda.is_available():
-        d, nbytes = synth.synth_chromosome(plan, chrom)
-        return d[:nbytes].cpu().numpy()
-    rng = np.random.default_rng(plan.seed)
-    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, chrom["length"])]
-    lines = [b">" + chrom["name"].encode()]
-    lines += [seq[i:i + 60].tobytes() for i in range(0, len(seq), 60)]
-    return np.frombuffer(b"\n".join(lines) + b"\n", dtype=np.uint8)
+    d, nbytes = synth.synth_chromosome(plan, chrom)
+    return d[:nbytes].cpu().numpy()
+
+
+def parity_at_scale(plan, threads, sample_bases):
+    """GPU counter == CPU oracle on a BASELINE-scale chromosome (300 Mb): every dumped k-mer and count, `lengths`, the
+    number of valid / distinct k-mers; k = 17 with the partition bits of the wheat run (descriptor pipeline) and k = 21
+    with those of a 2.38-Gb chromosome (22 bits: two-level scatter pipeline)."""
+    import numpy as np
+    from oracle import kmers
+    from subphaser_b200 import engine
+    fasta = host_sample(plan, sample_bases)
+    d, nb = engine.to_device_bytes(fasta)
+    seq = engine.pack_fasta(d, nb)
+    del d
+    out = []
+    for k, gmax in ((17, 851_000_000), (21, 2_380_000_000)):
+        t0 = time.perf_counter()
+        okeys, ocounts, st = kmers.count_fasta(fasta, k, 3, nthreads=threads)
+        cpu_s = time.perf_counter() - t0
+        tab = engine.CountTable(seq.n_bases, k, 3, mode="partitioned", genome_max_bases=gmax)
+        dump = engine.count_packed(seq, k, 3, table=tab)
+        keys, counts = dump.to_host()
+        o = np.argsort(keys, kind="stable")
+        equal = bool(np.array_equal(keys[o], okeys) and np.array_equal(counts[o], ocounts) and
+                     dump.length == st["sum_dumped"] and dump.n_valid_kmers == st["n_valid_kmers"] and
+                     dump.n_distinct == st["n_distinct"])
+        out.append({"bases": int(seq.n_bases), "k": k, "pbits": int(tab.pbits), "dumped": int(len(keys)),
+                    "sum_dumped": int(dump.length), "equal": equal, "cpu_count_s": round(cpu_s, 2),
+                    "cpu_count_kmers_per_s": st["n_valid_kmers"] / cpu_s})
+        del tab, dump
+    return out
 
 
 def workload_name(args, plan, cfg):
@@ -295,16 +352,18 @@ def main():
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * esecs / args.steps,
                "windows_per_s": eres["n_windows"] * args.steps / esecs}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) ----
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the whole path on a replica + counts checked at scale ----
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_path
         threads = len(os.sched_getaffinity(0))
-        sample_bases = int(min(args.cpu_sample_bases, lengths[0]))
-        fasta = host_sample(plan, sample_bases)
-        nk, dt = cpu_count_sample(fasta, k, 3, threads)
-        cpu = {"value": nk / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "count+dump stage only (C port of jellyfish semantics, oracle/kmer_count.c) on the first "
-                         "%d bases of chromosome %s; %.1f s" % (sample_bases, labels[0], dt)}
+        hotpath.release_scratch()
+        torch.cuda.empty_cache()
+        parity = parity_at_scale(plan, threads, int(min(3e8, lengths[0])))
+        rplan, rcfg, fastas, g_full, cscale = cpu_replica(args, threads)
+        cres, wall = cpu_path_once(rplan, rcfg, fastas, threads, args.replicates)
+        cpu = cpu_baseline_dict(cres, cpu_path.extrapolate(cres, g_full, full_windows=n_windows), g_full, cscale, wall)
 
     if rank == 0:
         win_s = (stage_ms.get("map", 0) + stage_ms.get("stack", 0) + stage_ms.get("enrich", 0)) / 1e3
@@ -321,7 +380,8 @@ def main():
             "loop_ms_per_step": {k_[1:]: v / args.steps for k_, v in sorted(stage_ms.items()) if k_.startswith("_")},
             "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],
                         "n_windows": n_windows, "labels": res["labels_full"]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_at_scale": parity, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(out))
     if world > 1:

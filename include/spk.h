@@ -201,6 +201,33 @@ int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t* const* d_c
 int spk_dump_regroup(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_pindex,
                      const uint32_t* d_new_start, int pbits, uint64_t* d_out_keys, uint32_t* d_out_counts,
                      void* stream);
+/* spk_dump_scatter_peers: the exchange step without a collective — write every hash-partition run of a dump
+ * (d_pindex) directly into the receive buffers of the rank that merges its class (p mod world) over peer-mapped
+ * memory (NVLink P2P stores; replaces the reference's single-process dict merge of Jellyfish.py:447-458 across
+ * GPUs).  d_peer_keys / d_peer_counts / d_peer_psize: device arrays of `world` pointers (one per rank, symmetric
+ * allocations).  The run of partition p lands at region_off + (exclusive sum of the earlier partitions of its class)
+ * in the destination's key / count buffers and its length at psize_off + p / world in the destination's size table;
+ * a class that would exceed region_cap entries is not written and *d_overflow is incremented (caller falls back to
+ * the collective exchange).  d_dst_off: uint32[1 << pbits] scratch; d_class_tot: uint64[world] out, entries per
+ * class.  syncs: no. */
+int spk_dump_scatter_peers(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_pindex, int pbits,
+                           uint32_t world, uint64_t region_off, uint64_t region_cap, uint64_t psize_off,
+                           uint64_t* const* d_peer_keys, uint32_t* const* d_peer_counts,
+                           uint32_t* const* d_peer_psize, uint32_t* d_dst_off, uint64_t* d_class_tot,
+                           uint64_t* d_overflow, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text wire formats on the device.  spk_format_rows writes the rows of `.kmer.mat` (kind 0:
+ * `KMER\tv1\t...\tvn\n`, JellyfishDumps.write_matrix, Jellyfish.py:515-520) or of `.sig.kmer-subgenome.tsv`
+ * (kind 1: `KMER\tLABEL\tp\tm1,...,mn\n`, Cluster.output_kmers, Cluster.py:158-172) exactly as Python's str()
+ * prints them (floats: shortest round-trip repr).  d_rows (optional, uint32[n_rows]): the rows to write, else all M.
+ * Call it twice: with d_row_len (uint32[n_rows] out) and d_out = NULL to get the row lengths, then — after an
+ * exclusive scan into d_row_off (uint64[n_rows]) — with d_row_off and d_out to write the bytes.
+ * kind 1: d_label int32[M] (index into d_label_text, 16 bytes per label, lengths in d_label_len), d_pval [M]. */
+int spk_format_rows(const uint64_t* d_keys, const double* d_vals, uint64_t M, int n, int k, int kind,
+                    const uint32_t* d_rows, uint64_t n_rows, const int32_t* d_label, const char* d_label_text,
+                    const int32_t* d_label_len, const double* d_pval, const uint64_t* d_row_off,
+                    uint32_t* d_row_len, char* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sorting helper (stable LSD radix sort of uint64 keys with a uint32 payload, ascending).
@@ -338,12 +365,26 @@ size_t spk_kmeans_workspace_bytes(int R);
 int spk_kmeans_gram(const double* d_G, int R, int n, int S, int n_init, int max_iter, uint64_t seed,
                     const int32_t* d_order, int32_t* d_labels, double* d_inertia, void* d_ws,
                     size_t ws_bytes, void* stream);
+/* the same for replicates r0 .. r0+R-1 of a larger batch (the random stream of a replicate is a function of its
+ * global number): ranks that split the bootstrap replicates of Cluster.py:82-112 reproduce the one-rank result */
+int spk_kmeans_gram_at(const double* d_G, int R, int r0, int n, int S, int n_init, int max_iter, uint64_t seed,
+                       const int32_t* d_order, int32_t* d_labels, double* d_inertia, void* d_ws,
+                       size_t ws_bytes, void* stream);
 int spk_cluster_scores(const int32_t* d_ref_labels, const int32_t* d_labels, int R, int n,
                        double* d_ari, double* d_vmeasure, void* stream);
 int spk_centroids(const double* d_Z, uint64_t M, int n, const int32_t* d_labels, int S,
                   double* d_C, void* stream);
 int spk_ttest_groups(const double* d_X, uint64_t M, int n, const int32_t* d_col_group, int S,
                      int32_t* d_best, double* d_pval, double* d_means, void* stream);
+/* spk_ranktest_groups: the other `test_method` choices of Cluster.output_kmers (Cluster.py:160,191): method 1 =
+ * scipy.stats.kruskal, 2 = mannwhitneyu, 3 = wilcoxon (default arguments; wilcoxon with the mode rules of the pinned
+ * scipy 1.7.1) on the two groups with the largest means.  d_pair_off (int32[S*S], index g_top * S + g_second): offset
+ * of that pair's exact null distribution in d_tables (built by the caller with integer arithmetic) or -1.
+ * d_flags (uint32, caller zeroes): bit 0 wilcoxon on groups of different size, bit 1 kruskal on identical values —
+ * scipy raises ValueError for those; the rows get NaN. */
+int spk_ranktest_groups(const double* d_X, uint64_t M, int n, const int32_t* d_col_group, int S, int method,
+                        const int32_t* d_pair_off, const double* d_tables, int32_t* d_best, double* d_pval,
+                        double* d_means, uint32_t* d_flags, void* stream);
 size_t spk_pca_workspace_bytes(int n);
 int spk_pca_gram(const double* d_G, int n, int ncomp, double* d_eigvals, double* d_scores,
                  double* d_ratio, void* d_ws, size_t ws_bytes, void* stream);

@@ -57,3 +57,35 @@ def stack_matrix(inBedCount, window_size=100000):
     lc = np.concatenate(line_counts, axis=0)
     out = engine.stack_windows(lc, lw, len(coords))
     return coords, out.tolist()
+
+
+def abnormal(data, k=1.5, high_tile=99, low_tile=1):
+    """Circos.py:973-980: the clipping bounds of a density track (99th / 1st percentile, numpy 'linear')."""
+    return np.percentile(data, high_tile), np.percentile(data, low_tile)
+
+
+def stack_bed_density(inBedCount, outpre, colnames, window_size=100000, trim=True):
+    """Circos.py:777-806: one circos density track per subgenome from the 10-kb bin table — windows stacked on the
+    device (`stack_matrix`), every column clipped at its 99th percentile, written as `chrom start end count`.
+    Returns {subgenome: file}."""
+    import sys
+    coords, counts = stack_matrix(inBedCount, window_size=window_size)
+    colnames = list(colnames)
+    d_outfiles = {key: "{}.{}.txt".format(outpre, key) for key in colnames}
+    arr = np.array(counts, dtype=np.int64).reshape(len(coords), -1) if coords else np.zeros((0, len(colnames)), np.int64)
+    assert arr.shape[0] == 0 or arr.shape[1] == len(colnames), "{} != {}".format(len(colnames), arr.shape[1])
+    uppers = {}
+    if trim:
+        for j, key in enumerate(colnames):
+            upper, _ = abnormal(arr[:, j])          # np.percentile of an empty column raises, like the reference
+            uppers[key] = upper
+            print("using cutoff: upper {} for {}".format(upper, key), file=sys.stderr)
+    prefix = ["{} {} {} ".format(*c) for c in coords]
+    for j, key in enumerate(colnames):
+        col = arr[:, j].tolist()
+        if trim:
+            up = uppers[key]
+            col = [c if c <= up else up for c in col]        # min(count, upper): the float bound prints as a float
+        with open(d_outfiles[key], "w") as f:
+            f.write("".join(p + str(c) + "\n" for p, c in zip(prefix, col)))
+    return d_outfiles

@@ -102,6 +102,7 @@ class Cluster:
             self.chrs = list(dm.labels)
             self._X = dm.norm
             self._keys = engine.u64_numpy(dm.keys)
+            self._d_keys = dm.keys
             self._k = dm.k
             self._kmers = None
         else:
@@ -241,31 +242,38 @@ class Cluster:
 
     def output_kmers(self, fout=sys.stdout, max_pval=0.05, ncpu=4, method="map", test_method="ttest_ind"):
         """Cluster.py:151-176 -> KmerSGMap (the d_kmers mapping)."""
-        if test_method != "ttest_ind":
-            raise NotImplementedError(
-                "test_method={!r}: only the default `ttest_ind` runs on the GPU path".format(test_method))
+        if test_method not in ("ttest_ind", "kruskal", "mannwhitneyu", "wilcoxon"):     # the CLI's choices (__main__.py)
+            raise AttributeError("module 'scipy.stats' has no attribute {!r}".format(test_method))   # eval() at :160
         sgs = sorted(set(self.d_sg.values()))                 # groups in sorted-SG order (:180)
         col_group = [sgs.index(self.d_sg[chr]) for chr in self.chrs]
         S = len(sgs)
         if S < 2:
             raise IndexError("list index out of range")      # grouped[1] in the reference (:187)
-        best, pval, means = engine.ttest_groups(self._X, col_group, S)
-        best, pval, means = best.cpu().numpy(), pval.cpu().numpy(), means.cpu().numpy()
-        keep = ~(pval > max_pval)                             # NaN p-values are kept (:167)
+        if test_method == "ttest_ind":
+            best, pval, means = engine.ttest_groups(self._X, col_group, S)
+        else:
+            best, pval, means, flags = engine.ranktest_groups(self._X, col_group, S, test_method)
+            if flags & 1:       # what scipy raises inside the reference's Pool workers
+                raise ValueError("The samples x and y must have the same length.")
+            if flags & 2:
+                raise ValueError("All numbers are identical in kruskal")
+        import torch
+        d_keep = ~(pval > max_pval)                           # NaN p-values are kept (:167)
+        d_idx = torch.nonzero(d_keep).flatten().to(torch.int32)
         print("\t".join(["#kmer", "subgenome", "p_value", "ratios"]), file=fout)
-        kmers = self.kmers
-        idxs = np.nonzero(keep)[0]
-        step = 65536
-        for a in range(0, len(idxs), step):
-            chunk = idxs[a:a + step]
-            pv = pval[chunk].tolist()
-            mv = means[chunk].tolist()
-            fout.write("".join(
-                "{}\t{}\t{}\t{}\n".format(kmers[i], sgs[b], _fmt(p), ",".join(map(_fmt, m)))
-                for i, b, p, m in zip(chunk.tolist(), best[chunk].tolist(), pv, mv)))
-        keys = self._keys[idxs] if self._keys is not None else kmer_codec.strs_to_keys(
-            [kmers[i] for i in idxs], self._k)[0]
-        return KmerSGMap(keys, best[idxs], sgs, self._k)
+        if self._keys is None:                                # matrix came from a text file: encode its k-mers once
+            keys_np, valid = kmer_codec.strs_to_keys(self.kmers, self._k)
+            if not valid.all():
+                raise ValueError("non-ACGT k-mer in {}".format("the matrix file"))
+            self._keys = keys_np
+        d_keys = getattr(self, "_d_keys", None)
+        if d_keys is None:
+            d_keys = self._d_keys = torch.from_numpy(self._keys.view(np.int64).copy()).to(engine._dev())
+        # rows are formatted on the device (spk_format_rows kind 1): kmer, subgenome, p-value, comma-joined group means
+        engine.write_text(fout, engine.format_rows(d_keys, means, self._k, kind=1, rows=d_idx, label=best,
+                                                   label_names=sgs, pval=pval))
+        idxs = d_idx.cpu().numpy().astype(np.int64)
+        return KmerSGMap(self._keys[idxs], best.cpu().numpy()[idxs], sgs, self._k)
 
     def pca(self, outfig, n_components=2, sg_color=None):
         """Cluster.py:48-75.  Scores/explained variance come from the exact Gram-matrix PCA; they are

@@ -270,14 +270,8 @@ class JellyfishDumps:
         """Jellyfish.py:515-520: header `kmer<TAB>labels`, rows `KMER<TAB>str(float)...`."""
         fout.write("\t".join(["kmer"] + list(self.labels)) + "\n")
         if isinstance(d_mat, engine.DiffMatrix):
-            keys = engine.u64_numpy(d_mat.keys)
-            norm = d_mat.norm.cpu().numpy()
-            strs = kmer_codec.keys_to_strs(keys, d_mat.k)
-            step = 65536
-            for a in range(0, len(strs), step):
-                rows = norm[a:a + step].tolist()
-                fout.write("".join(
-                    s + "\t" + "\t".join(map(repr, r)) + "\n" for s, r in zip(strs[a:a + step], rows)))
+            # rows are formatted on the device (k-mer strings, shortest-repr floats: spk_format_rows)
+            engine.write_text(fout, engine.format_rows(d_mat.keys, d_mat.norm, d_mat.k, kind=0))
             fout.flush()
             name = getattr(fout, "name", None)
             if isinstance(name, str) and os.path.exists(name):

@@ -37,6 +37,7 @@ SIGNATURES = {
     "spk_pmatrix_filter": (c_i, [c_p, c_p, c_p, c_i, c_i, c_u32, c_u32, c_p, c_p, c_i, c_p, c_i, c_p, c_i, c_d, c_i, c_i,
                                  c_d, c_d, c_d, c_p, c_p, c_u64, c_u64, c_p, c_p]),
     "spk_dump_regroup": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p]),
+    "spk_dump_scatter_peers": (c_i, [c_p, c_p, c_p, c_i, c_u32, c_u64, c_u64, c_u64, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spk_table_scan_blocks": (c_i, []),
     "spk_table_stats": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u32, c_p]),
     "spk_table_extract": (c_i, [c_p, c_sz, c_i, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p]),
@@ -46,6 +47,7 @@ SIGNATURES = {
                                       c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "spk_filter_select": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_p, c_u64, c_p]),
     "spk_filter_emit": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_p, c_p, c_p, c_p]),
+    "spk_format_rows": (c_i, [c_p, c_p, c_u64, c_i, c_i, c_i, c_p, c_u64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spk_sort_workspace_bytes": (c_sz, [c_u64]),
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),
     "spk_stack_windows": (c_i, [c_p, c_p, c_u64, c_i, c_p, c_p]),
@@ -70,9 +72,11 @@ SIGNATURES = {
     "spk_gram_batched": (c_i, [c_p, c_u64, c_i, c_p, c_i, c_i, c_p, c_p]),
     "spk_kmeans_workspace_bytes": (c_sz, [c_i]),
     "spk_kmeans_gram": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_u64, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "spk_kmeans_gram_at": (c_i, [c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_u64, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "spk_cluster_scores": (c_i, [c_p, c_p, c_i, c_i, c_p, c_p, c_p]),
     "spk_centroids": (c_i, [c_p, c_u64, c_i, c_p, c_i, c_p, c_p]),
     "spk_ttest_groups": (c_i, [c_p, c_u64, c_i, c_p, c_i, c_p, c_p, c_p, c_p]),
+    "spk_ranktest_groups": (c_i, [c_p, c_u64, c_i, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spk_pca_workspace_bytes": (c_sz, [c_i]),
     "spk_pca_gram": (c_i, [c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "spk_count_fasta_host": (c_i, [c_p, c_sz, c_i, c_u32, c_p, c_p, c_p, c_u64, c_p, c_sz, c_p, c_sz,

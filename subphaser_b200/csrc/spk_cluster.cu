@@ -291,13 +291,15 @@ __device__ void canonical_relabel(const int* labels, int n, int S, const int32_t
 
 __global__ void __launch_bounds__(32)
 k_kmeans_gram(const double* __restrict__ G, int R, int n, int S, int n_init, int max_iter,
-              uint64_t seed, const int32_t* __restrict__ order, int32_t* __restrict__ labels_out,
+              uint64_t seed, int r0, const int32_t* __restrict__ order, int32_t* __restrict__ labels_out,
               double* __restrict__ inertia_out, KmScratch* __restrict__ scratch) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const double* g = G + (uint64_t)r * n * n;
     KmScratch& w = scratch[r];
-    Rng rng{seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(r + 1))};
+    // (the random stream belongs to the GLOBAL replicate number r0 + r: ranks that share the replicates of a
+    //  bootstrap get the results one rank would)
+    Rng rng{seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(r0 + r + 1))};
     int best[CL_MAX_N];
     double best_inertia = INFINITY;
     for (int t = 0; t < n_init; t++) {
@@ -489,6 +491,157 @@ k_ttest_groups(const double* __restrict__ X, uint64_t M, int n, const int32_t* _
     }
 }
 
+
+// ---- K7b: rank tests for `-test_method kruskal | mannwhitneyu | wilcoxon` (Cluster.py:160,191) -----------------------
+// Same row handling as k_ttest_groups (regroup by subgenome, np.mean per group, groups ordered by descending
+// Python-sum mean, top two tested); the test is scipy.stats.<method>(top, second) with default arguments:
+//   kruskal       H with tie correction, p = chi2.sf(H, 1)                         (scipy/stats/_stats_py.py kruskal)
+//   mannwhitneyu  two-sided, continuity correction, method 'auto': exact null distribution when min(n1, n2) <= 8 and
+//                 the pooled values have no ties, normal approximation with tie correction otherwise
+//   wilcoxon      paired, zero_method 'wilcox', two-sided, no continuity correction, mode 'auto' AS IN THE PINNED
+//                 scipy 1.7.1: exact distribution when n <= 25 and no difference is zero (ranks of tied |d| are
+//                 averaged and r_plus truncated, as that version does), normal approximation otherwise
+// Exact null distributions are built on the host with integer arithmetic (Cluster.py side) and indexed per ordered
+// pair of groups: pair_off[g0 * S + g1] = offset into `tables` or -1.
+//   mannwhitneyu table: cdf[u] for u = 0 .. n1*n2/2 ;  wilcoxon table: cdf[k], k = 0..K, then sf[k], k = 0..K (K = n(n+1)/2)
+// flags: bit 0 = wilcoxon on groups of different size (scipy raises ValueError), bit 1 = kruskal on identical values
+// (scipy raises ValueError): the row's p-value is NaN and the host raises like the reference would.
+enum { RT_KRUSKAL = 1, RT_MANNWHITNEYU = 2, RT_WILCOXON = 3 };
+
+__device__ __forceinline__ double norm_sf(double z) { return 0.5 * erfc(z * 0.70710678118654752440); }
+
+__global__ void __launch_bounds__(128)
+k_ranktest_groups(const double* __restrict__ X, uint64_t M, int n, const int32_t* __restrict__ col_group, int S,
+                  int method, const int32_t* __restrict__ pair_off, const double* __restrict__ tables,
+                  int32_t* __restrict__ best, double* __restrict__ pval, double* __restrict__ means,
+                  uint32_t* __restrict__ flags) {
+    double vals[CL_MAX_N];
+    double pool[CL_MAX_N];
+    int off[CL_MAX_S + 1];
+    for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M;
+         m += (uint64_t)gridDim.x * blockDim.x) {
+        const double* x = X + m * n;
+        int pos = 0;
+        for (int g = 0; g < S; g++) {
+            off[g] = pos;
+            for (int c = 0; c < n; c++)
+                if (col_group[c] == g) vals[pos++] = x[c];
+        }
+        off[S] = pos;
+        double key[CL_MAX_S];
+        for (int g = 0; g < S; g++) {
+            const int ng = off[g + 1] - off[g];
+            means[m * S + g] = np_pairwise(vals + off[g], ng) / (double)ng;
+            double s = 0.0;
+            for (int i = off[g]; i < off[g + 1]; i++) s += vals[i];
+            key[g] = -s / (double)ng;
+        }
+        int g0 = 0;
+        for (int g = 1; g < S; g++)
+            if (key[g] < key[g0]) g0 = g;
+        int g1 = -1;
+        for (int g = 0; g < S; g++) {
+            if (g == g0) continue;
+            if (g1 < 0 || key[g] < key[g1]) g1 = g;
+        }
+        const int n1 = off[g0 + 1] - off[g0], n2 = off[g1 + 1] - off[g1];
+        const double* a = vals + off[g0];
+        const double* b = vals + off[g1];
+        double p = NAN;
+        if (method == RT_WILCOXON) {
+            if (n1 != n2) {
+                atomicOr(flags, 1u);
+            } else {
+                // d = x - y; zeros dropped ('wilcox'); ranks of |d| (average ranks)
+                int cnt = 0, nzero = 0;
+                for (int i = 0; i < n1; i++) {
+                    const double d = a[i] - b[i];
+                    if (d == 0.0) nzero++;
+                    else pool[cnt++] = d;
+                }
+                double r_plus = 0.0, r_minus = 0.0, tie = 0.0;
+                for (int i = 0; i < cnt; i++) {
+                    const double ai = fabs(pool[i]);
+                    int less = 0, eq = 0;
+                    for (int j = 0; j < cnt; j++) {
+                        const double aj = fabs(pool[j]);
+                        less += aj < ai;
+                        eq += aj == ai;
+                    }
+                    const double r = (double)less + 0.5 * (double)(eq + 1);
+                    if (pool[i] > 0) r_plus += r;
+                    else r_minus += r;
+                    tie += (double)eq * (double)eq - 1.0;            // sum over ties of t^3 - t, element-wise
+                }
+                const int tab = pair_off[g0 * S + g1];
+                if (n1 <= 25 && nzero == 0 && tab >= 0) {
+                    const int K = n1 * (n1 + 1) / 2;
+                    const int rp = (int)r_plus;                        // truncation, as scipy 1.7.1
+                    if (rp == K / 2) p = 1.0;                          // `r_plus == (len(cnt) - 1) // 2`: centre of the distribution
+                    else p = 2.0 * fmin(tables[tab + rp], tables[tab + K + 1 + rp]);
+                } else {
+                    const double c = (double)cnt;
+                    const double mn = c * (c + 1.0) * 0.25;
+                    double se = c * (c + 1.0) * (2.0 * c + 1.0);
+                    se = sqrt((se - 0.5 * tie) / 24.0);
+                    const double T = fmin(r_plus, r_minus);
+                    const double z = (T - mn) / se;
+                    p = 2.0 * norm_sf(fabs(z));
+                }
+            }
+        } else {
+            // pooled ranks
+            const int N = n1 + n2;
+            for (int i = 0; i < n1; i++) pool[i] = a[i];
+            for (int i = 0; i < n2; i++) pool[n1 + i] = b[i];
+            double R1 = 0.0, R2 = 0.0, tie = 0.0;
+            bool has_ties = false;
+            for (int i = 0; i < N; i++) {
+                int less = 0, eq = 0;
+                for (int j = 0; j < N; j++) {
+                    less += pool[j] < pool[i];
+                    eq += pool[j] == pool[i];
+                }
+                const double r = (double)less + 0.5 * (double)(eq + 1);
+                if (i < n1) R1 += r;
+                else R2 += r;
+                tie += (double)eq * (double)eq - 1.0;
+                has_ties |= eq > 1;
+            }
+            const double dN = (double)N;
+            if (method == RT_KRUSKAL) {
+                const double ties = 1.0 - tie / (dN * dN * dN - dN);
+                if (ties == 0.0) {
+                    atomicOr(flags, 2u);
+                } else {
+                    const double ssbn = R1 * R1 / (double)n1 + R2 * R2 / (double)n2;
+                    double h = 12.0 / (dN * (dN + 1.0)) * ssbn - 3.0 * (dN + 1.0);
+                    h /= ties;
+                    p = h <= 0.0 ? 1.0 : erfc(sqrt(0.5 * h));      // chi2.sf(h, df = 1)
+                }
+            } else {
+                const double U1 = R1 - (double)n1 * ((double)n1 + 1.0) * 0.5;
+                const double U2 = (double)n1 * (double)n2 - U1;
+                const double U = fmax(U1, U2);
+                const int tab = pair_off[g0 * S + g1];
+                if (!((n1 > 8 && n2 > 8) || has_ties) && tab >= 0) {
+                    const int kc = n1 * n2 - (int)U;                   // sf(U) = cdf(n1 n2 - U) by symmetry (U >= n1 n2 / 2)
+                    p = fmin(1.0, fmax(0.0, 2.0 * tables[tab + kc]));
+                } else {
+                    const double mu = (double)n1 * (double)n2 * 0.5;
+                    const double sd = sqrt((double)n1 * (double)n2 / 12.0 * ((dN + 1.0) - tie / (dN * (dN - 1.0))));
+                    double num = U - mu;
+                    if (num > 0.0) num -= 0.5;                        // continuity correction, sign(num) * 0.5
+                    const double z = num / sd;
+                    p = fmin(1.0, fmax(0.0, 2.0 * norm_sf(z)));
+                }
+            }
+        }
+        best[m] = g0;
+        pval[m] = p;
+    }
+}
+
 // ---- K8 PCA from the Gram matrix: cyclic Jacobi eigen-decomposition (one CTA) -----------------------------
 __global__ void __launch_bounds__(128)
 k_pca_gram(const double* __restrict__ G, int n, int ncomp, double* __restrict__ eigvals,
@@ -639,9 +792,21 @@ extern "C" int spk_gram_batched(const double* d_Z, uint64_t M, int n, const uint
 
 extern "C" size_t spk_kmeans_workspace_bytes(int R) { return (size_t)R * sizeof(KmScratch) + 256; }
 
+extern "C" int spk_kmeans_gram_at(const double* d_G, int R, int r0, int n, int S, int n_init, int max_iter,
+                                  uint64_t seed, const int32_t* d_order, int32_t* d_labels,
+                                  double* d_inertia, void* d_ws, size_t ws_bytes, void* stream);
+
 extern "C" int spk_kmeans_gram(const double* d_G, int R, int n, int S, int n_init, int max_iter,
                                uint64_t seed, const int32_t* d_order, int32_t* d_labels,
                                double* d_inertia, void* d_ws, size_t ws_bytes, void* stream) {
+    return spk_kmeans_gram_at(d_G, R, 0, n, S, n_init, max_iter, seed, d_order, d_labels, d_inertia, d_ws, ws_bytes,
+                              stream);
+}
+
+extern "C" int spk_kmeans_gram_at(const double* d_G, int R, int r0, int n, int S, int n_init, int max_iter,
+                                  uint64_t seed, const int32_t* d_order, int32_t* d_labels,
+                                  double* d_inertia, void* d_ws, size_t ws_bytes, void* stream) {
+    SPK_CHECK_ARG(r0 >= 0, "r0 must be >= 0");
     SPK_CHECK_ARG(n >= 1 && n <= CL_MAX_N, "n must be in [1, 128]");
     SPK_CHECK_ARG(S >= 1 && S <= CL_MAX_S && S <= n, "n_clusters must be in [1, min(16, n)]");
     SPK_CHECK_ARG(n_init >= 1 && max_iter >= 1, "n_init/max_iter must be >= 1");
@@ -651,7 +816,7 @@ extern "C" int spk_kmeans_gram(const double* d_G, int R, int n, int S, int n_ini
         spk_set_error("spk_kmeans_gram: workspace too small");
         return SPK_ECAP;
     }
-    k_kmeans_gram<<<(R + 31) / 32, 32, 0, (cudaStream_t)stream>>>(d_G, R, n, S, n_init, max_iter, seed,
+    k_kmeans_gram<<<(R + 31) / 32, 32, 0, (cudaStream_t)stream>>>(d_G, R, n, S, n_init, max_iter, seed, r0,
                                                                   d_order, d_labels, d_inertia,
                                                                   (KmScratch*)d_ws);
     SPK_LAUNCH_CHECK();
@@ -703,6 +868,19 @@ extern "C" int spk_pca_gram(const double* d_G, int n, int ncomp, double* d_eigva
     }
     k_pca_gram<<<1, 128, 0, (cudaStream_t)stream>>>(d_G, n, ncomp, d_eigvals, d_scores, d_ratio,
                                                     (double*)d_ws);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_ranktest_groups(const double* d_X, uint64_t M, int n, const int32_t* d_col_group, int S, int method,
+                                   const int32_t* d_pair_off, const double* d_tables, int32_t* d_best, double* d_pval,
+                                   double* d_means, uint32_t* d_flags, void* stream) {
+    SPK_CHECK_ARG(n >= 2 && n <= CL_MAX_N && S >= 2 && S <= CL_MAX_S, "bad shape");
+    SPK_CHECK_ARG(method >= RT_KRUSKAL && method <= RT_WILCOXON, "method: 1 kruskal, 2 mannwhitneyu, 3 wilcoxon");
+    if (M == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_X && d_col_group && d_pair_off && d_best && d_pval && d_means && d_flags, "null pointer");
+    k_ranktest_groups<<<row_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(d_X, M, n, d_col_group, S, method, d_pair_off,
+                                                                         d_tables, d_best, d_pval, d_means, d_flags);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

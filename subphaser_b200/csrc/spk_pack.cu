@@ -9,6 +9,7 @@
 //   C  classify again and OR the 2-bit codes / validity bits of each thread's <= 16 kept bases straight
 //      into the zero-initialised output words (<= 4 RED.OR per thread; no byte stores, no code array)
 // A byte is in a header iff the first byte of its line is '>'.
+#include <stdlib.h>
 #include "spk_common.cuh"
 
 namespace {
@@ -95,8 +96,10 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c) { return ze
 __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t* __restrict__ in,
                                                                    size_t nbytes, size_t ntiles,
                                                                    int64_t* __restrict__ tile_last_nl,
-                                                                   uint32_t* __restrict__ tile_skip) {
+                                                                   uint32_t* __restrict__ tile_skip,
+                                                                   const uint32_t* __restrict__ run_if) {
     __shared__ int s_max[PK_THREADS / 32];
+    if (run_if && *run_if == 0) return;
     __shared__ uint32_t s_skip[PK_THREADS / 32];
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t pos = tile * PK_TILE + (size_t)threadIdx.x * PK_BYTES_PER_THREAD;
@@ -151,9 +154,10 @@ __global__ void __launch_bounds__(PK_THREADS) k_tile_last_newline(const uint8_t*
 // them); 8 consecutive elements per thread per round keep the number of latency-bound rounds small
 constexpr int SCAN_PER = 8;
 
-__global__ void __launch_bounds__(1024) k_scan_max_excl(int64_t* data, size_t n) {
+__global__ void __launch_bounds__(1024) k_scan_max_excl(int64_t* data, size_t n, const uint32_t* run_if) {
     __shared__ int64_t s_warp[32];
     __shared__ int64_t s_carry;
+    if (run_if && *run_if == 0) return;
     if (threadIdx.x == 0) s_carry = -1;
     __syncthreads();
     for (size_t base = 0; base < n; base += 1024 * SCAN_PER) {
@@ -189,9 +193,11 @@ __global__ void __launch_bounds__(1024) k_scan_max_excl(int64_t* data, size_t n)
     }
 }
 
-__global__ void __launch_bounds__(1024) k_scan_sum_excl(const uint32_t* in, uint64_t* out, size_t n) {
+__global__ void __launch_bounds__(1024) k_scan_sum_excl(const uint32_t* in, uint64_t* out, size_t n,
+                                                         const uint32_t* run_if) {
     __shared__ uint64_t s_warp[32];
     __shared__ uint64_t s_carry;
+    if (run_if && *run_if == 0) return;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (size_t base = 0; base < n; base += 1024 * SCAN_PER) {
@@ -347,11 +353,13 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
                                                           const uint64_t* __restrict__ tile_off,
                                                           uint32_t* __restrict__ packed,
                                                           uint32_t* __restrict__ valid_out,
-                                                          uint64_t* __restrict__ totals) {
+                                                          uint64_t* __restrict__ totals,
+                                                          const uint32_t* __restrict__ run_if) {
     __shared__ int s_wi[PK_THREADS / 32];
     __shared__ uint32_t s_w32[PK_THREADS / 32];
     __shared__ int s_carry_hdr;
     __shared__ uint32_t s_pk[EMIT ? PK_TILE / 16 + 4 : 1];
+    if (run_if && *run_if == 0) return;
     __shared__ uint32_t s_vd[EMIT ? PK_TILE / 32 + 2 : 1];
     uint64_t my_valid = 0, my_hdr = 0;
     for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -460,12 +468,228 @@ __global__ void __launch_bounds__(PK_THREADS) k_classify(const uint8_t* __restri
     }
 }
 
-__global__ void k_write_info(const uint64_t* tile_off, size_t ntiles, const uint64_t* totals,
+
+// ---- single pass (default) -----------------------------------------------------------------------------------------
+// The three-pass scheme above reads the FASTA twice and scans two per-tile arrays with a single CTA.  For ordinary
+// (line-wrapped) FASTA all of that can be decided locally: the state a tile starts in ("is the line that contains
+// the tile's first byte a header line?") follows from the last '\n' within the 512 bytes before the tile, and the
+// only global quantity left — how many kept bases precede the tile — is a prefix sum that the tiles resolve among
+// themselves with decoupled look-back (tiles are handed out in order by a ticket; each publishes its kept count,
+// then the inclusive prefix, in one 64-bit status word).  One read of the input, no scan kernels.
+// A tile that finds no line break in its look-back window (lines longer than 512 bytes: unwrapped FASTA) raises
+// *need_slow; the three-pass kernels then run (they return immediately otherwise) — decided on the device, no
+// host synchronisation.
+constexpr int PK_LOOKBACK = 512;
+constexpr uint64_t PK_FLAG_AGG = 1ull << 62, PK_FLAG_INC = 2ull << 62, PK_VAL_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_status(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// exclusive prefix of tile `tile` (sum of the kept counts of all earlier tiles); called by warp 0
+__device__ __forceinline__ uint64_t pk_lookback(const uint64_t* status, int64_t tile) {
+    const int lane = threadIdx.x & 31;
+    uint64_t excl = 0;
+    int64_t j = tile - 1;
+    while (true) {
+        const int64_t idx = j - lane;
+        uint64_t sv = PK_FLAG_INC;                       // before the first tile: inclusive prefix 0
+        if (idx >= 0) {
+            sv = ld_status(status + idx);
+            while ((sv >> 62) == 0) sv = ld_status(status + idx);
+        }
+        const uint32_t inc = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+        uint64_t v = sv & PK_VAL_MASK;
+        if (inc) {
+            const int first = __ffs(inc) - 1;            // nearest tile with a complete prefix
+            if (lane > first) v = 0;
+            excl += spk_warp_sum_u64(v);
+            break;
+        }
+        excl += spk_warp_sum_u64(v);
+        j -= 32;
+    }
+    return excl;
+}
+
+constexpr int PK_SUB = 4;                       // 4-KiB sub-tiles per look-back unit (one ticket, one status word per 16 KiB)
+
+__global__ void __launch_bounds__(PK_THREADS)
+k_pack_single(const uint8_t* __restrict__ in, size_t nbytes, size_t nunits, uint64_t* __restrict__ status,
+              uint32_t* __restrict__ ticket, uint32_t* __restrict__ packed, uint32_t* __restrict__ valid_out,
+              uint64_t* __restrict__ totals, uint32_t* __restrict__ need_slow) {
+    __shared__ int s_wi[PK_THREADS / 32];
+    __shared__ uint32_t s_w32[PK_THREADS / 32];
+    __shared__ int s_carry_hdr;
+    __shared__ long long s_carry;
+    __shared__ uint32_t s_unit;
+    __shared__ unsigned long long s_o0;
+    __shared__ uint32_t s_T[PK_SUB];
+    __shared__ uint32_t s_pk[PK_TILE / 16 + 4];
+    __shared__ uint32_t s_vd[PK_TILE / 32 + 2];
+    __shared__ __align__(16) uint8_t s_bytes[PK_TILE];
+    uint64_t my_valid = 0, my_hdr = 0;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        if (threadIdx.x == 0) s_unit = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const size_t unit = s_unit;
+        if (unit >= nunits) break;
+        uint32_t bits_s[PK_SUB], vbits_s[PK_SUB], off_s[PK_SUB];
+        // ---- phase 1: classify the unit's sub-tiles (state at a sub-tile's first byte from its look-back window) ----
+#pragma unroll
+        for (int sub = 0; sub < PK_SUB; sub++) {
+            const size_t tbase = (unit * PK_SUB + sub) * PK_TILE;
+            const size_t pos = tbase + (size_t)threadIdx.x * PK_BYTES_PER_THREAD;
+            uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+            int my_last = -1;
+            if (pos < nbytes) {
+                v = load_tile_bytes(in, nbytes, pos);
+                const int l = last_newline16(v);
+                if (l >= 0) my_last = threadIdx.x * 16 + l;   // padded '\n' past the end are harmless here
+            }
+            *reinterpret_cast<uint4*>(s_bytes + threadIdx.x * 16) = v;
+            if (threadIdx.x < 32) {
+                long long found = -1;
+                int hdr = 0;
+                if (tbase < nbytes) {
+                    const size_t w0 = tbase >= (size_t)PK_LOOKBACK ? tbase - PK_LOOKBACK : 0;
+                    const size_t p = w0 + (size_t)lane * 16;       // w0 is a multiple of 16
+                    if (p < tbase) {
+                        const uint4 b = *reinterpret_cast<const uint4*>(in + p);
+                        const int l = last_newline16(b);
+                        if (l >= 0) found = (long long)(p + l);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, o));
+                    if (lane == 0) {
+                        if (found < 0 && w0 > 0) {
+                            atomicOr(need_slow, 1u);           // a line longer than the window: the three-pass path decides
+                        } else {
+                            const size_t ls = (size_t)(found + 1);
+                            hdr = (ls < tbase) ? (in[ls] == '>') : 0;
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    s_carry = found;
+                    s_carry_hdr = hdr;
+                }
+            }
+            const int prev_nl = block_excl_max(my_last, s_wi);   // (barriers inside: s_bytes, s_carry visible)
+            const long long carry = s_carry;
+            bool bol = false, hdr = false;
+            const int my_off = threadIdx.x * 16;
+            if (pos >= nbytes) {
+            } else if (prev_nl >= 0) {
+                bol = (prev_nl + 1 == my_off);
+                hdr = bol ? false : (s_bytes[prev_nl + 1] == '>');
+            } else {
+                bol = ((long long)tbase + my_off == carry + 1);
+                hdr = bol ? false : (((size_t)(carry + 1) >= tbase) ? (s_bytes[(size_t)(carry + 1) - tbase] == '>')
+                                                                    : (s_carry_hdr != 0));
+            }
+            uint32_t bits, vbits;
+            int kept, nvalid, headers = 0;
+            if (!(pos + 16 <= nbytes && !hdr && classify16_fast(v, bits, vbits, kept, nvalid)))
+                classify16(v, pos, nbytes, bol, hdr, bits, vbits, kept, nvalid, headers);
+            my_valid += nvalid;
+            my_hdr += headers;
+            uint32_t T;
+            off_s[sub] = block_excl_sum((uint32_t)kept, s_w32, &T) | ((uint32_t)kept << 16);   // offset < 4096, kept <= 16
+            bits_s[sub] = bits;
+            vbits_s[sub] = vbits;
+            if (threadIdx.x == 0) s_T[sub] = T;
+            __syncthreads();       // s_bytes / s_carry are rewritten by the next sub-tile
+        }
+        // ---- phase 2: publish the kept count, resolve the prefix by look-back, publish the inclusive prefix ----
+        if (threadIdx.x < 32) {
+            uint32_t T = 0;
+#pragma unroll
+            for (int sub = 0; sub < PK_SUB; sub++) T += s_T[sub];
+            if (lane == 0) st_status(status + unit, PK_FLAG_AGG | (uint64_t)T);
+            const uint64_t excl = pk_lookback(status, (int64_t)unit);
+            if (lane == 0) {
+                st_status(status + unit, PK_FLAG_INC | (excl + T));
+                s_o0 = excl;
+                if (unit + 1 == nunits) totals[2] = excl + T;     // number of bases
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: emit ----
+        uint64_t o0 = s_o0;
+#pragma unroll
+        for (int sub = 0; sub < PK_SUB; sub++) {
+            const uint32_t T = s_T[sub];
+            const uint32_t off = off_s[sub] & 0xffffu, kept = off_s[sub] >> 16;
+            const uint32_t bits = bits_s[sub], vbits = vbits_s[sub];
+            for (int i = threadIdx.x; i < PK_TILE / 16 + 4; i += PK_THREADS) s_pk[i] = 0;
+            for (int i = threadIdx.x; i < PK_TILE / 32 + 2; i += PK_THREADS) s_vd[i] = 0;
+            __syncthreads();
+            const uint32_t lb = (uint32_t)(o0 & 31);
+            if (kept) {
+                const uint32_t l = lb + off;
+                const int sh = 2 * (int)(l & 15);
+                if (bits) {
+                    if (bits << sh) atomicOr(&s_pk[l >> 4], bits << sh);
+                    if (sh && (bits >> (32 - sh))) atomicOr(&s_pk[(l >> 4) + 1], bits >> (32 - sh));
+                }
+                if (vbits) {
+                    const int vs = (int)(l & 31);
+                    atomicOr(&s_vd[l >> 5], vbits << vs);
+                    if (vs > 16 && (vbits >> (32 - vs))) atomicOr(&s_vd[(l >> 5) + 1], vbits >> (32 - vs));
+                }
+            }
+            __syncthreads();
+            if (T) {
+                const uint32_t npw = ((lb + T - 1) >> 4) + 1;
+                const uint32_t nvw = ((lb + T - 1) >> 5) + 1;
+                uint32_t* gp = packed + (o0 >> 5) * 2;
+                uint32_t* gv = valid_out + (o0 >> 5);
+                for (uint32_t i = threadIdx.x; i < npw; i += PK_THREADS) {
+                    const uint32_t wv = s_pk[i];
+                    if (i < 2 || i + 1 >= npw) { if (wv) atomicOr(&gp[i], wv); }
+                    else gp[i] = wv;
+                }
+                for (uint32_t i = threadIdx.x; i < nvw; i += PK_THREADS) {
+                    const uint32_t wv = s_vd[i];
+                    if (i == 0 || i + 1 == nvw) { if (wv) atomicOr(&gv[i], wv); }
+                    else gv[i] = wv;
+                }
+            }
+            o0 += T;
+            __syncthreads();   // staging words are cleared by the next sub-tile
+        }
+    }
+    my_valid = spk_warp_sum_u64(my_valid);
+    my_hdr = spk_warp_sum_u64(my_hdr);
+    if (lane == 0) {
+        if (my_valid) atomicAdd((unsigned long long*)&totals[0], (unsigned long long)my_valid);
+        if (my_hdr) atomicAdd((unsigned long long*)&totals[1], (unsigned long long)my_hdr);
+    }
+}
+
+// the three-pass path runs only when the single pass gave up: its outputs and totals are reset on the device
+__global__ void __launch_bounds__(256) k_zero_if(const uint32_t* __restrict__ flag, uint4* __restrict__ p, size_t n16) {
+    if (*flag == 0) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void k_reset_totals_if(const uint32_t* flag, uint64_t* totals) {
+    if (*flag) totals[0] = totals[1] = totals[2] = 0;
+}
+
+__global__ void k_write_info(const uint64_t* tile_off, size_t ntiles, const uint64_t* totals, const uint32_t* slow,
                              uint64_t* info) {
-    info[0] = tile_off[ntiles];
+    info[0] = (slow && *slow == 0) ? totals[2] : tile_off[ntiles];
     info[1] = totals[0];
     info[2] = totals[1];
-    info[3] = 0;
+    info[3] = slow ? *slow : 1;      // 1: the three-pass path produced the result
 }
 
 }  // namespace
@@ -500,29 +724,53 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ntiles = (nbytes + PK_TILE - 1) / PK_TILE;
     const int sms = spk_num_sms();
-    SPK_CUDA(cudaMemsetAsync(w.totals, 0, 32, st));
+    SPK_CUDA(cudaMemsetAsync(w.totals, 0, 64, st));
+    uint32_t* ticket = (uint32_t*)(w.totals + 4);
+    uint32_t* need_slow = ticket + 1;
+    const char* mode = getenv("SPK_PACK_MODE");            // "3pass": skip the single pass (tests)
+    const bool single = !(mode && mode[0] == '3');
     // outputs are OR-accumulated: zero the whole tile-aligned extent (this is also the padding)
-    SPK_CUDA(cudaMemsetAsync(d_packed, 0, spk_packed_words(cap_bases) * 4, st));
-    SPK_CUDA(cudaMemsetAsync(d_valid, 0, spk_valid_words(cap_bases) * 4, st));
-    if (ntiles > 0) {
-        const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
-        k_tile_last_newline<<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip);
+    const size_t pbytes = spk_packed_words(cap_bases) * 4, vbytes = spk_valid_words(cap_bases) * 4;
+    SPK_CUDA(cudaMemsetAsync(d_packed, 0, pbytes, st));
+    SPK_CUDA(cudaMemsetAsync(d_valid, 0, vbytes, st));
+    const uint32_t* run_if = nullptr;
+    if (single && ntiles > 0) {
+        uint64_t* status = (uint64_t*)w.tile_last_nl;      // (one 64-bit word per PK_SUB tiles fits the per-tile array)
+        const size_t nunits = (ntiles + PK_SUB - 1) / PK_SUB;
+        SPK_CUDA(cudaMemsetAsync(status, 0, nunits * 8, st));
+        const unsigned grid1 = (unsigned)min((size_t)sms * 6, nunits);
+        k_pack_single<<<grid1, PK_THREADS, 0, st>>>(d_ascii, nbytes, nunits, status, ticket, d_packed, d_valid, w.totals,
+                                                    need_slow);
         SPK_LAUNCH_CHECK();
-        k_scan_max_excl<<<1, 1024, 0, st>>>(w.tile_last_nl, ntiles);
+        // fallback (lines longer than the look-back window), decided on the device: every kernel below returns at once
+        // unless *need_slow is set
+        run_if = need_slow;
+        k_zero_if<<<sms * 4, 256, 0, st>>>(need_slow, (uint4*)d_packed, pbytes / 16);
         SPK_LAUNCH_CHECK();
-        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip,
-                                                       w.tile_kept, nullptr, nullptr, nullptr, w.totals);
+        k_zero_if<<<sms * 4, 256, 0, st>>>(need_slow, (uint4*)d_valid, vbytes / 16);
+        SPK_LAUNCH_CHECK();
+        k_reset_totals_if<<<1, 1, 0, st>>>(need_slow, w.totals);
         SPK_LAUNCH_CHECK();
     }
-    k_scan_sum_excl<<<1, 1024, 0, st>>>(w.tile_kept, w.tile_off, ntiles);
+    if (ntiles > 0) {
+        const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
+        k_tile_last_newline<<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip, run_if);
+        SPK_LAUNCH_CHECK();
+        k_scan_max_excl<<<1, 1024, 0, st>>>(w.tile_last_nl, ntiles, run_if);
+        SPK_LAUNCH_CHECK();
+        k_classify<false><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip,
+                                                       w.tile_kept, nullptr, nullptr, nullptr, w.totals, run_if);
+        SPK_LAUNCH_CHECK();
+    }
+    k_scan_sum_excl<<<1, 1024, 0, st>>>(w.tile_kept, w.tile_off, ntiles, ntiles > 0 ? run_if : nullptr);
     SPK_LAUNCH_CHECK();
     if (ntiles > 0) {
         const unsigned grid = (unsigned)min((size_t)sms * 8, ntiles);
         k_classify<true><<<grid, PK_THREADS, 0, st>>>(d_ascii, nbytes, ntiles, w.tile_last_nl, w.tile_skip, nullptr,
-                                                      w.tile_off, d_packed, d_valid, w.totals);
+                                                      w.tile_off, d_packed, d_valid, w.totals, run_if);
         SPK_LAUNCH_CHECK();
     }
-    k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, d_info);
+    k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, ntiles > 0 ? run_if : nullptr, d_info);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -212,6 +212,78 @@ k_dump_regroup(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ c
     }
 }
 
+
+// ---- multi-GPU exchange over peer memory (NVLink / NVSwitch P2P stores) ----------------------------------------
+// Rank r merges the union rows of the hash partitions p = r (mod world), so it needs that class of every
+// chromosome's dump.  Instead of regrouping the dump and handing it to a collective (which needs the sizes on the
+// host: a synchronisation per chromosome), the owner writes every partition run straight into the destination
+// rank's receive buffer (symmetric allocation, peer-mapped): k_class_offsets gives partition p its offset inside
+// its class (exclusive scan over the partitions of the class, ascending), k_dump_scatter_peers copies the run with
+// one warp and stores the run length into the destination's per-partition size table.  No host round trip, no
+// collective; the transfers ride the same stream as the counting kernels and overlap the next chromosome's work.
+__global__ void __launch_bounds__(1024)
+k_class_offsets(const uint32_t* __restrict__ pindex, uint64_t P, uint32_t world, uint32_t* __restrict__ dst_off,
+                uint64_t* __restrict__ class_tot) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t cls = blockIdx.x;
+    const uint64_t npc = (P - cls + world - 1) / world;             // partitions of this class
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < npc; base += 1024) {
+        const uint64_t q = base + threadIdx.x;
+        const uint64_t p = cls + q * world;
+        const uint32_t c = q < npc ? pindex[2 * p + 1] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t wt = s_warp[threadIdx.x & 31], wi = wt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if ((threadIdx.x & 31) >= o) wi += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, wi, 31);
+        const uint32_t prefix = __shfl_sync(0xffffffffu, wi - wt, threadIdx.x >> 5);
+        if (q < npc) dst_off[p] = s_carry + prefix + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) class_tot[cls] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_dump_scatter_peers(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts,
+                     const uint32_t* __restrict__ pindex, const uint32_t* __restrict__ dst_off, uint64_t P,
+                     uint32_t world, uint64_t region_off, uint64_t region_cap, uint64_t psize_off,
+                     uint64_t* const* __restrict__ peer_keys, uint32_t* const* __restrict__ peer_counts,
+                     uint32_t* const* __restrict__ peer_psize, uint64_t* __restrict__ overflow) {
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (uint64_t p = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < P; p += nw) {
+        const uint32_t s = pindex[2 * p], c = pindex[2 * p + 1], d = dst_off[p];
+        const uint32_t dst = (uint32_t)(p % world);
+        const bool fits = (uint64_t)d + c <= region_cap;
+        if (lane == 0) {
+            peer_psize[dst][psize_off + p / world] = fits ? c : 0u;
+            if (!fits) atomicAdd((unsigned long long*)overflow, 1ull);
+        }
+        if (!fits) continue;
+        uint64_t* ok = peer_keys[dst] + region_off + d;
+        uint32_t* oc = peer_counts[dst] + region_off + d;
+        for (uint32_t i = lane; i < c; i += 32) {
+            ok[i] = keys[s + i];
+            oc[i] = counts[s + i];
+        }
+    }
+}
+
 uint32_t pm_table_slots(int n, double mean_entries) {
     // smallest power of two that takes an average partition in ONE round (entries <= 7/8 of the slots), capped
     // by shared memory: a slot is an 8-byte key + n 4-byte counters and the table must stay under ~190 KB
@@ -288,6 +360,26 @@ extern "C" int spk_dump_regroup(const uint64_t* d_keys, const uint32_t* d_counts
     const unsigned grid = (unsigned)min((P * 32 + 255) / 256, (uint64_t)spk_num_sms() * 16);
     k_dump_regroup<<<grid, 256, 0, (cudaStream_t)stream>>>(d_keys, d_counts, d_pindex, d_new_start, P, d_out_keys,
                                                            d_out_counts);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_dump_scatter_peers(const uint64_t* d_keys, const uint32_t* d_counts, const uint32_t* d_pindex,
+                                      int pbits, uint32_t world, uint64_t region_off, uint64_t region_cap,
+                                      uint64_t psize_off, uint64_t* const* d_peer_keys,
+                                      uint32_t* const* d_peer_counts, uint32_t* const* d_peer_psize,
+                                      uint32_t* d_dst_off, uint64_t* d_class_tot, uint64_t* d_overflow, void* stream) {
+    SPK_CHECK_ARG(d_pindex && d_peer_keys && d_peer_counts && d_peer_psize && d_dst_off && d_class_tot && d_overflow,
+                  "null pointer");
+    SPK_CHECK_ARG(pbits >= 0 && pbits <= 30, "bad pbits");
+    SPK_CHECK_ARG(world >= 1 && world <= 1024, "bad world size");
+    const uint64_t P = 1ull << pbits;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_class_offsets<<<world, 1024, 0, st>>>(d_pindex, P, world, d_dst_off, d_class_tot);
+    SPK_LAUNCH_CHECK();
+    const unsigned grid = (unsigned)min((P * 32 + 255) / 256, (uint64_t)spk_num_sms() * 16);
+    k_dump_scatter_peers<<<grid, 256, 0, st>>>(d_keys, d_counts, d_pindex, d_dst_off, P, world, region_off, region_cap,
+                                               psize_off, d_peer_keys, d_peer_counts, d_peer_psize, d_overflow);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -188,8 +188,16 @@ def count_packed(seq, k, lower_count, table=None, histo_len=0, timer=None):
              histo_len, table.pbits, _p(pindex), st)
         tock(e)
         n_valid, n_fail, _, _, distinct, n_ge, sum_ge, _ = (int(x) for x in table.stats.cpu().tolist())
-        if n_fail:
-            raise OverflowError("k-mer table full: %d inserts failed" % n_fail)
+        if n_fail or os.environ.get("SPK_PCOUNT_FORCE_FAIL") == "1":      # (the variable is a test hook)
+            # a hash partition did not fit its shared-memory table (low-complexity / adversarial input): count this
+            # chromosome with the global open-addressed table instead.  Its dump has no partition index, so the
+            # genome's union goes through the plain path (spk_union_insert) — slower, never wrong.
+            import logging
+            logging.getLogger("subphaser_b200").warning(
+                "partitioned counter: %d inserts did not fit a shared-memory partition table; "
+                "recounting %s with the global table", n_fail, seq.name or "chromosome")
+            gtab = CountTable(max(seq.n_bases, 1), k, lower_count, mode="global")
+            return count_packed(seq, k, lower_count, table=gtab, histo_len=histo_len, timer=timer)
         if n_ge > table.cap:
             raise OverflowError("dump capacity exceeded: %d > %d" % (n_ge, table.cap))
         e = tick("scan")
@@ -351,7 +359,7 @@ def pmatrix_union_size(dumps):
          None, 0, None, 0, None, 0, 0.0, 0, 0, 0.0, 0.0, 0.0, None, None, 0, sum(len(d) for d in dumps),
          _p(counters), _stream())
     n_union, _, _, n_over = (int(x) for x in counters[:4].cpu().tolist())
-    if n_over:
+    if n_over or os.environ.get("SPK_PMATRIX_FORCE_OVERFLOW") == "1":     # (the variable is a test hook)
         raise OverflowError("partition table overflow in spk_pmatrix_filter")
     return n_union
 
@@ -400,7 +408,7 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
              int(baseline), int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt),
              cap, total, _p(counters), st)
         n_union, _, n_cand, n_over = (int(x) for x in counters[:4].cpu().tolist())
-        if n_over:
+        if n_over or os.environ.get("SPK_PMATRIX_FORCE_OVERFLOW") == "1":
             raise OverflowError("partition table overflow in spk_pmatrix_filter")
         if n_cand <= cap:
             break
@@ -464,8 +472,9 @@ def gram(Z, idx=None):
     return G
 
 
-def kmeans_gram(G, S, order=None, n_init=10, max_iter=300, seed=0):
-    """K-Means of the n points behind Gram matrices G [R, n, n] -> (labels int32 [R, n], inertia [R])."""
+def kmeans_gram(G, S, order=None, n_init=10, max_iter=300, seed=0, r0=0):
+    """K-Means of the n points behind Gram matrices G [R, n, n] -> (labels int32 [R, n], inertia [R]).
+    r0: global number of the first replicate (ranks sharing a bootstrap keep the one-rank random streams)."""
     require_cuda()
     lib = _lib.load()
     if G.dim() == 2:
@@ -477,7 +486,7 @@ def kmeans_gram(G, S, order=None, n_init=10, max_iter=300, seed=0):
     ws_bytes = lib.spk_kmeans_workspace_bytes(R)
     ws = _empty(ws_bytes, torch.uint8)
     d_order = None if order is None else torch.as_tensor(order, dtype=torch.int32, device=_dev())
-    call("spk_kmeans_gram", _p(G), R, n, S, n_init, max_iter, seed, _p(d_order), _p(labels), _p(inertia),
+    call("spk_kmeans_gram_at", _p(G), R, int(r0), n, S, n_init, max_iter, seed, _p(d_order), _p(labels), _p(inertia),
          _p(ws), ws_bytes, _stream())
     return labels, inertia
 
@@ -521,6 +530,90 @@ def ttest_groups(X, col_group, S):
     cg = torch.as_tensor(col_group, dtype=torch.int32, device=_dev()).contiguous()
     call("spk_ttest_groups", _p(X), M, n, _p(cg), S, _p(best), _p(pval), _p(means), _stream())
     return best, pval, means
+
+
+_RANK_METHODS = {"kruskal": 1, "mannwhitneyu": 2, "wilcoxon": 3}
+
+
+def _mwu_cdf(n1, n2):
+    """P(U <= u), u = 0 .. n1*n2//2, of the Mann-Whitney statistic without ties: exact integer counts (number of ways to
+    pick the n1 ranks of the first sample) divided by C(n1+n2, n1)."""
+    import math
+    from functools import lru_cache
+    umax = n1 * n2 // 2
+
+    @lru_cache(maxsize=None)
+    def ways(u, m, n):          # arrangements of m x-values and n y-values with U = u
+        if u < 0:
+            return 0
+        if m == 0 or n == 0:
+            return 1 if u == 0 else 0
+        return ways(u - n, m - 1, n) + ways(u, m, n - 1)
+
+    total = math.comb(n1 + n2, n1)
+    acc, out = 0, []
+    for u in range(umax + 1):
+        acc += ways(u, n1, n2)
+        out.append(acc / total)
+    return out
+
+
+def _wilcoxon_tables(n):
+    """cdf[k] = P(W <= k), then sf[k] = P(W >= k), k = 0 .. n(n+1)/2, of the signed-rank statistic of n untied
+    differences (number of subsets of {1..n} with sum k, over 2^n)."""
+    K = n * (n + 1) // 2
+    cnt = [0] * (K + 1)
+    cnt[0] = 1
+    for r in range(1, n + 1):
+        for k in range(K, r - 1, -1):
+            cnt[k] += cnt[k - r]
+    tot = 2 ** n
+    cdf, acc = [], 0
+    for c in cnt:
+        acc += c
+        cdf.append(acc / tot)
+    sf, acc = [0.0] * (K + 1), 0
+    for k in range(K, -1, -1):
+        acc += cnt[k]
+        sf[k] = acc / tot
+    return cdf + sf
+
+
+def ranktest_groups(X, col_group, S, method):
+    """Cluster._output_kmers with test_method kruskal / mannwhitneyu / wilcoxon -> (best, pval, means, flags)."""
+    require_cuda()
+    if method not in _RANK_METHODS:
+        raise ValueError("unknown test_method {!r}".format(method))
+    M, n = X.shape
+    sizes = [int(sum(1 for g in col_group if g == s)) for s in range(S)]
+    pair_off = np.full(S * S, -1, dtype=np.int32)
+    tables, cache = [], {}
+    for a in range(S):
+        for b in range(S):
+            if a == b or not sizes[a] or not sizes[b]:
+                continue
+            if method == "mannwhitneyu" and min(sizes[a], sizes[b]) <= 8:
+                key = ("m", min(sizes[a], sizes[b]), max(sizes[a], sizes[b]))
+                if key not in cache:
+                    cache[key] = len(tables)
+                    tables.extend(_mwu_cdf(key[1], key[2]))
+                pair_off[a * S + b] = cache[key]
+            elif method == "wilcoxon" and sizes[a] == sizes[b] and sizes[a] <= 25:
+                key = ("w", sizes[a])
+                if key not in cache:
+                    cache[key] = len(tables)
+                    tables.extend(_wilcoxon_tables(sizes[a]))
+                pair_off[a * S + b] = cache[key]
+    d_tab = torch.tensor(tables or [0.0], dtype=torch.float64, device=_dev())
+    d_off = torch.from_numpy(pair_off).to(_dev())
+    best = _empty(M, torch.int32)
+    pval = _empty(M, torch.float64)
+    means = _empty(M * S, torch.float64).view(M, S)
+    flags = _zeros(1, torch.int32)
+    cg = torch.as_tensor(col_group, dtype=torch.int32, device=_dev()).contiguous()
+    call("spk_ranktest_groups", _p(X), M, n, _p(cg), S, _RANK_METHODS[method], _p(d_off), _p(d_tab), _p(best), _p(pval),
+         _p(means), _p(flags), _stream())
+    return best, pval, means, int(flags.item())
 
 
 def pca_gram(G, ncomp):
@@ -641,6 +734,59 @@ def stack_windows(line_counts, line_window, n_windows):
     out = _zeros(max(n_windows, 1) * S, torch.int64).view(max(n_windows, 1), S)
     call("spk_stack_windows", _p(lc), _p(lw), L, S, _p(out), _stream())
     return out[:n_windows].cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------------
+# text wire formats
+# ----------------------------------------------------------------------------------------------------
+def format_rows(keys, vals, k, kind=0, rows=None, label=None, label_names=None, pval=None):
+    """Rows of `.kmer.mat` (kind 0) / `.sig.kmer-subgenome.tsv` (kind 1) formatted on the device (spk_format_rows)
+    -> the text as a host uint8 numpy array (one contiguous buffer, rows in order).
+    keys int64 [M] device, vals float64 [M, n] device; rows: optional int32 device tensor of row ids;
+    kind 1: label int32 [M] device, label_names list of str (<= 16 bytes each), pval float64 [M] device."""
+    require_cuda()
+    M, n = vals.shape
+    vals = vals.contiguous()
+    n_rows = int(rows.numel()) if rows is not None else int(M)
+    if n_rows == 0:
+        return np.zeros(0, np.uint8)
+    d_text = d_len = None
+    if kind == 1:
+        raw = [s.encode() for s in label_names]
+        if any(len(b) > 16 for b in raw):
+            raise ValueError("subgenome names longer than 16 bytes are not supported by the device writer")
+        tab = np.zeros((len(raw), 16), np.uint8)
+        for i, b in enumerate(raw):
+            tab[i, :len(b)] = np.frombuffer(b, np.uint8)
+        d_text = torch.from_numpy(tab).to(_dev())
+        d_len = torch.tensor([len(b) for b in raw], dtype=torch.int32, device=_dev())
+    row_len = _empty(n_rows, torch.int32)
+    st = _stream()
+    args = (_p(keys), _p(vals), M, n, int(k), int(kind), _p(rows), n_rows, _p(label), _p(d_text), _p(d_len), _p(pval))
+    call("spk_format_rows", *args, None, _p(row_len), None, st)
+    off = torch.cumsum(row_len.to(torch.int64), 0)
+    total = int(off[-1].item())
+    off = (off - row_len).contiguous()
+    out = _empty(total, torch.uint8)
+    call("spk_format_rows", *args, _p(off), None, _p(out), st)
+    host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+    host.copy_(out, non_blocking=False)
+    return host.numpy()
+
+
+def write_text(fout, data, chunk=1 << 26):
+    """uint8 array -> an open text (or binary) file handle, without building one giant str."""
+    buf = getattr(fout, "buffer", None)
+    if buf is not None and hasattr(fout, "flush"):
+        fout.flush()
+        buf.write(memoryview(data))
+        return
+    for a in range(0, len(data), chunk):
+        piece = data[a:a + chunk].tobytes()
+        try:
+            fout.write(piece.decode("ascii"))
+        except TypeError:
+            fout.write(piece)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -268,14 +268,17 @@ def exchange_rows(dm, n_union_local, dist, dev):
     return full, int(meta_h[world])
 
 
-def exchange_windows(win_counts, n, nsg, owner, dist, dev):
-    """Per-chromosome window count matrices (int64 [W_i, S]) -> present on every rank (one all_reduce of the
-    row counts, one all_gather of the per-rank concatenations)."""
-    nw = torch.zeros(n, dtype=torch.int64, device=dev)
-    for i, w in win_counts.items():
-        nw[i] = w.shape[0]
-    dist.all_reduce(nw)
-    nw_h = [int(x) for x in nw.cpu().tolist()]
+def exchange_windows(win_counts, n, nsg, owner, dist, dev, nw_known=None):
+    """Per-chromosome window count matrices (int64 [W_i, S]) -> present on every rank (one all_gather of the per-rank
+    concatenations; when the row counts are not known on every rank, one all_reduce of them first)."""
+    if nw_known is not None:
+        nw_h = [int(x) for x in nw_known]
+    else:
+        nw = torch.zeros(n, dtype=torch.int64, device=dev)
+        for i, w in win_counts.items():
+            nw[i] = w.shape[0]
+        dist.all_reduce(nw)
+        nw_h = [int(x) for x in nw.cpu().tolist()]
     flat = _gather_concat({i: w.contiguous().view(-1) for i, w in win_counts.items()}, [x * nsg for x in nw_h],
                           owner, n, dist, dev, torch.int64)
     return {i: flat[i].view(nw_h[i], nsg) for i in range(n)}
@@ -283,6 +286,116 @@ def exchange_windows(win_counts, n, nsg, owner, dist, dev):
 
 _PINNED = {}
 _SCRATCH = {}
+
+class PeerExchange:
+    """The exchange step over peer memory (no collective, no host round trip per chromosome): every rank owns
+    symmetric receive buffers (torch symmetric memory: peer-mapped over NVLink / NVSwitch) with one region per
+    chromosome; the owner of a chromosome writes each hash-partition run of its dump straight into the region of
+    the rank that merges that partition class (`spk_dump_scatter_peers`).  The stores ride the counting stream, so
+    the transfer of chromosome j overlaps the packing / counting of chromosome j + 1; one all_reduce of the sizes
+    at the end is both the barrier and the only host synchronisation.
+    A region holds at most SPK_PEER_CAP_FRAC (default 0.12) of the chromosome's bases per world; a dump that does
+    not fit is reported by `finish()` and the caller uses the collective exchange instead."""
+
+    def __init__(self, dist, nbytes_list, pbits, lower_count, dev):
+        import torch.distributed._symmetric_memory as symm
+        self.dist, self.dev = dist, dev
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n, self.pbits = len(nbytes_list), int(pbits)
+        self.P = 1 << self.pbits
+        self.ncls = (self.P + self.world - 1) // self.world
+        frac = float(os.environ.get("SPK_PEER_CAP_FRAC", "0.12"))
+        self.caps = []
+        for nb in nbytes_list:
+            hard = nb // max(int(lower_count), 1) + 1                 # a dumped k-mer occurs >= lower_count times
+            c = int(min(hard, nb * frac) / self.world * 1.15) + 4096
+            self.caps.append((c + 63) // 64 * 64)
+        self.offs = [0]
+        for c in self.caps:
+            self.offs.append(self.offs[-1] + c)
+        total = self.offs[-1]
+        self.rk = symm.empty(total, dtype=torch.int64, device=dev)
+        self.rc = symm.empty(total, dtype=torch.int32, device=dev)
+        self.rp = symm.empty(self.n * self.ncls, dtype=torch.int32, device=dev)
+        group = dist.group.WORLD
+        self._handles = [symm.rendezvous(t, group) for t in (self.rk, self.rc, self.rp)]
+        ptrs = [[int(p) for p in h.buffer_ptrs] for h in self._handles]
+        self.peer = torch.tensor(ptrs, dtype=torch.int64).to(dev)         # [3, world] device pointer tables
+        self.dst_off = torch.empty(self.P, dtype=torch.int32, device=dev)
+        self.class_tot = torch.zeros(self.n, self.world, dtype=torch.int64, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def key(self):
+        return (self.n, self.world, self.pbits, tuple(self.caps))
+
+    def begin(self):
+        self.class_tot.zero_()
+        self.overflow.zero_()
+
+    def scatter(self, i, dump):
+        """dump of chromosome i (owned by this rank) -> the receive regions of all ranks (asynchronous)."""
+        _lib.call("spk_dump_scatter_peers", engine._p(dump.keys), engine._p(dump.counts), engine._p(dump.pindex),
+                  self.pbits, self.world, self.offs[i], self.caps[i], i * self.ncls, engine._p(self.peer[0]),
+                  engine._p(self.peer[1]), engine._p(self.peer[2]), engine._p(self.dst_off),
+                  engine._p(self.class_tot[i]), engine._p(self.overflow), engine._stream())
+
+    def finish(self, owner, lengths_local, bases_local, n_kmers_local):
+        """Barrier + sizes.  -> ({i: (keys, counts, length, pindex)} for the chromosomes of other ranks, total k-mers,
+        bases of every chromosome), or (None, total, bases) when some dump did not fit its region."""
+        n, world, rank, dev = self.n, self.world, self.rank, self.dev
+        meta = torch.zeros(n + 1, world + 2, dtype=torch.int64, device=dev)
+        meta[:n, :world] = self.class_tot
+        for i, length in lengths_local.items():
+            meta[i, world] = int(length)
+            meta[i, world + 1] = int(bases_local[i])
+        meta[n, 0] = int(n_kmers_local)
+        meta[n, 1:2] = self.overflow
+        self.dist.all_reduce(meta)        # every rank's stores precede its contribution on its stream
+        meta_h = meta.cpu().tolist()
+        total_kmers = int(meta_h[n][0])
+        bases = [int(meta_h[i][world + 1]) for i in range(n)]
+        if int(meta_h[n][1]):
+            return None, total_kmers, bases
+        my_parts = torch.arange(rank, self.P, world, device=dev)
+        npc = int(my_parts.numel())
+        out = {}
+        for i in range(n):
+            if owner[i] == rank:
+                continue
+            m = int(meta_h[i][rank])
+            pc = self.rp[i * self.ncls:i * self.ncls + npc].to(torch.int64)
+            pidx = torch.zeros(2 * self.P, dtype=torch.int32, device=dev)
+            pidx[2 * my_parts] = (torch.cumsum(pc, 0) - pc).to(torch.int32)
+            pidx[2 * my_parts + 1] = pc.to(torch.int32)
+            a = self.offs[i]
+            out[i] = (self.rk[a:a + m], self.rc[a:a + m], int(meta_h[i][world]), pidx)
+        return out, total_kmers, bases
+
+
+def _peer_exchange(dist, nbytes_list, pbits, lower_count, dev):
+    """Cached PeerExchange (allocation + rendezvous are collective and cost milliseconds); None when symmetric
+    memory is unavailable (then the NCCL all-to-all path is used)."""
+    if os.environ.get("SPK_EXCHANGE", "peer") != "peer" or not str(dev).startswith("cuda"):
+        return None
+    px = _SCRATCH.get("peer")
+    want = (len(nbytes_list), dist.get_world_size(), int(pbits), tuple(int(x) for x in nbytes_list), int(lower_count))
+    if px is not None and px[0] == want:
+        return px[1]
+    _SCRATCH.pop("peer", None)
+    try:
+        obj = PeerExchange(dist, nbytes_list, pbits, lower_count, dev)
+        ok = 1
+    except Exception as exc:      # symmetric memory not available on this build / topology
+        import logging
+        logging.getLogger("subphaser_b200").warning("peer-memory exchange unavailable (%s): using NCCL all-to-all", exc)
+        obj, ok = None, 0
+    flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # all ranks take the same path
+    if int(flag.item()) == 0:
+        obj = None
+    _SCRATCH["peer"] = (want, obj)
+    return obj
+
 
 
 def _scratch_table(max_bytes, k, lower_count, genome_max):
@@ -380,13 +493,24 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
             ev.record(copy_stream)
         return d, ev
 
-    pending = start_copy(mine[0]) if (host_inputs and mine) else None
+    # host inputs: the first copy cannot hide behind anything, so the smallest chromosome goes first; two copies are
+    # kept in flight ahead of the chromosome being counted
+    order_in = sorted(mine, key=lambda i: (chrom_inputs[i][1], i)) if host_inputs else list(mine)
+    PREFETCH = 2
+    pending = [start_copy(i) for i in order_in[:PREFETCH]] if host_inputs else []
+    # multi-GPU: dumps travel over peer memory right after they are counted (PeerExchange)
+    px = None
+    if world > 1 and table.pbits > 0 and n <= 128 and os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain":
+        px = _peer_exchange(dist, [c[1] for c in chrom_inputs], table.pbits, lower_count, dev)
+        if px is not None:
+            px.begin()
     e_loop = t.start("_loop_pack_count")      # coarse brackets ("_..."): stage sums vs. whole-loop time = host gaps
-    for pos, i in enumerate(mine):
+    for pos, i in enumerate(order_in):
         buf, nbytes = chrom_inputs[i]
         if host_inputs:
-            d, ev = pending
-            pending = start_copy(mine[pos + 1]) if pos + 1 < len(mine) else None
+            d, ev = pending.pop(0)
+            if pos + PREFETCH < len(order_in):
+                pending.append(start_copy(order_in[pos + PREFETCH]))
             e = t.start("h2d_wait")
             main_stream.wait_event(ev)
             t.stop(e)
@@ -401,11 +525,31 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         dump = engine.count_packed(seq, k, lower_count, table=table, timer=t)
         seqs[i], dumps[i] = seq, dump
         n_kmers += dump.n_valid_kmers
+        if px is not None:
+            e = t.start("scatter")
+            if dump.pindex is not None and dump.pbits == px.pbits:
+                px.scatter(i, dump)
+            else:                               # counted by the global-table fallback: no partition index
+                px.overflow += 1
+            t.stop(e)
     t.stop(e_loop)
     del table          # stays alive in _SCRATCH for the next call
 
     # ---- exchange: every rank needs every dump (exact merge of the global k-mer table) -------------
-    if world > 1:
+    bases_all = None
+    got = None
+    if world > 1 and px is not None:
+        e = t.start("exchange")
+        e2 = t.start("_x_wait")                      # the sizes' all_reduce doubles as the barrier with the slowest rank
+        got, n_kmers_total, bases_all = px.finish(owner, {i: dumps[i].length for i in mine},
+                                                  {i: seqs[i].n_bases for i in mine}, n_kmers)
+        t.stop(e2)
+        if got is not None:
+            for i, (kk, cc, length, pidx) in got.items():
+                dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx, px.pbits)
+            by_class = True
+        t.stop(e)
+    if world > 1 and got is None:
         e = t.start("exchange")
         e2 = t.start("_x_wait")                      # time until the slowest rank has finished counting
         dist.barrier()
@@ -418,7 +562,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         dist.all_reduce(pmeta, op=dist.ReduceOp.MAX)
         pb_max, pb_min = int(pmeta[0].item()), -int(pmeta[1].item())
         by_class = (pb_max == pb_min and pb_max > 0 and n <= 128 and
-                    os.environ.get("SPK_EXCHANGE", "class") == "class" and
+                    os.environ.get("SPK_EXCHANGE", "peer") in ("class", "peer") and
                     os.environ.get("SPK_MATRIX_MODE", "partitioned") != "plain")
         e2 = t.start("_x_dumps")
         if by_class:
@@ -440,7 +584,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
                     kk, cc, length = everything[i]
                     dumps[i] = engine.KmerDump(kk, cc, k, length, 0, 0, labels[i], None, pidx.get(i), pbits)
         t.stop(e)
-    else:
+    elif world == 1:
         n_kmers_total = n_kmers
         by_class = False
     dump_list = [dumps[i] for i in range(n)]
@@ -488,6 +632,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     # the differential matrix is final here: its device->host copy (0.6 GB for wheat, ~25 ms of PCIe) runs on a
     # side stream underneath the clustering and mapping stages
     host_copy = None
+    return_host = bool(return_host) and rank == 0     # one copy of the results leaves the node, not one per rank
     if return_host:
         d2h_stream = _SCRATCH.setdefault("d2h_stream", torch.cuda.Stream())
         d2h_stream.wait_stream(torch.cuda.current_stream())
@@ -503,17 +648,36 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     order = [i for _, i in sorted(zip(labels, range(n)))]
     lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
     lab_full_h = lab_full[0].cpu().numpy()
-    R = int(replicates)
-    d_bs = None
-    if R > 0:
-        d_idx = engine.resample_indices(M, R, seed)
-        Gb = engine.gram_batched(Z, d_idx)
-        lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
-        ari, vm = engine.cluster_scores(lab_full_h, lab_b)
-        lab_b_h = lab_b.cpu().numpy()
-        d_bs = [int(100 * int(np.sum(lab_b_h[:, i] == lab_full_h[i])) / R) for i in range(n)]
-    eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
     t.stop(e)
+    # The bootstrap (replicates x tiny K-Means problems: a few dozen thread blocks for milliseconds) and the PCA (one
+    # thread block) only feed the report; nothing downstream waits for them.  They run on a side stream underneath the
+    # t-test, the table build and the map kernels and are joined at the end.
+    R = int(replicates)
+    side = _SCRATCH.setdefault("side_stream", torch.cuda.Stream())
+    side.wait_stream(torch.cuda.current_stream())
+    lab_b = ari = vm = None
+    with torch.cuda.stream(side):
+        e_side = t.start("bootstrap_pca_side")
+        if R > 0:
+            d_idx = engine.resample_indices(M, R, seed)        # same generator state on every rank: same plan
+            if world > 1:
+                # the replicates are independent: rank r clusters replicates [lo, hi) and the labels are all-gathered
+                per = (R + world - 1) // world
+                lo, hi = min(rank * per, R), min((rank + 1) * per, R)
+                lab_pad = torch.zeros(per, n, dtype=torch.int32, device=dev)
+                if hi > lo:
+                    Gb = engine.gram_batched(Z, d_idx[lo:hi].contiguous())
+                    lab_loc, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1, r0=lo)
+                    lab_pad[:hi - lo] = lab_loc
+                lab_all = torch.empty(world * per, n, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(lab_all.view(-1), lab_pad.view(-1))
+                lab_b = lab_all[:R].contiguous()
+            else:
+                Gb = engine.gram_batched(Z, d_idx)
+                lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
+            ari, vm = engine.cluster_scores(lab_full_h, lab_b)
+        eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
+        t.stop(e_side)
     e = t.start("ttest")
     best, pval, means = engine.ttest_groups(dm.norm, lab_full_h.tolist(), nsg)
     keep = ~(pval > max_pval)
@@ -550,7 +714,10 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     if world > 1:
         e = t.start("exchange")
         e2 = t.start("_x_windows")
-        win_counts = exchange_windows(win_counts, n, nsg, owner, dist, dev)
+        nw_known = None
+        if bases_all is not None:      # window counts per chromosome follow from its length: no size exchange
+            nw_known = [int(((max(L - 1, 0) // bin_size) * bin_size) // window_size) + 1 if L else 0 for L in bases_all]
+        win_counts = exchange_windows(win_counts, n, nsg, owner, dist, dev, nw_known)
         t.stop(e2)
         t.stop(e)
     e = t.start("enrich")
@@ -559,10 +726,16 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     allw = allw[nz].contiguous()
     enr = engine.fisher_enrich(allw, max_pval=max_pval)
     t.stop(e)
+    side.synchronize()
+    d_bs = None
+    if lab_b is not None:
+        lab_b_h = lab_b.cpu().numpy()
+        d_bs = [int(100 * int(np.sum(lab_b_h[:, i] == lab_full_h[i])) / R) for i in range(n)]
     d2h_bytes = int(dm.norm.numel() * 8 + dm.keys.numel() * 8 + allw.numel() * 8 * 4)
     return dict(n_kmers=n_kmers_total, n_kmers_local=n_kmers, n_union=n_union, n_diff=M, n_sig=int(sig_keys.numel()),
                 n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
-                lengths=[d.length for d in dump_list], enrich=enr, dm=dm, pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
+                lengths=[d.length for d in dump_list], enrich=enr, dm=dm, window_counts=allw,
+                pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
                 h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes if return_host else int(allw.numel() * 8 * 4),
                 matrix_host=_matrix_host(host_copy) if return_host else None)
 

@@ -11,7 +11,6 @@ import ctypes
 
 import numpy as np
 
-from . import _lib, engine
 
 # IWGSC RefSeq v2.1-like chromosome lengths (Mb), order 1A 1B 1D 2A ... 7D
 WHEAT_MB = [598, 700, 498, 787, 812, 656, 754, 851, 619, 754, 673, 518, 713, 714, 569, 622, 731, 495, 744,
@@ -113,6 +112,7 @@ class GenomePlan:
 def synth_chromosome(plan, chrom, line_width=60, d_library=None):
     """-> (device uint8 tensor holding the FASTA bytes (16-B padded), nbytes)."""
     import torch
+    from . import _lib, engine
     engine.require_cuda()
     dev = engine._dev()
     hlen, nbytes = plan.fasta_nbytes(chrom, line_width)
@@ -131,6 +131,72 @@ def synth_chromosome(plan, chrom, line_width=60, d_library=None):
               len(rs), float(plan.div), float(plan.soft_frac), plan.seed, engine._stream())
     torch.cuda.current_stream().synchronize()
     return out, nbytes
+
+
+def _hash64(x):
+    x = x ^ (x >> np.uint64(33))
+    x = x * np.uint64(0xff51afd7ed558ccd)
+    x = x ^ (x >> np.uint64(33))
+    x = x * np.uint64(0xc4ceb9fe1a85ec53)
+    return x ^ (x >> np.uint64(33))
+
+
+def _mix(a, b):
+    return _hash64(a * np.uint64(0x9E3779B97F4A7C15) + b + np.uint64(0x632BE59BD9B4E019))
+
+
+def synth_chromosome_host(plan, chrom, line_width=60, block=1 << 22):
+    """numpy twin of spk_synth_fasta (csrc/spk_synth.cu): the same FASTA bytes as synth_chromosome(), built on the
+    host without libspk — for the CPU reference arm of bench.py (which must not load the product library) and for
+    CPU tests.  -> uint8 array of nbytes."""
+    hlen, nbytes = plan.fasta_nbytes(chrom, line_width)
+    starts, src, seeds, rs, re = plan.segments(chrom)
+    L = chrom["length"]
+    lib = plan.library
+    out = np.empty(nbytes, dtype=np.uint8)
+    out[:hlen] = np.frombuffer((">%s\n" % chrom["name"]).encode(), dtype=np.uint8)
+    seed = np.uint64(plan.seed)
+    div_thr = np.uint64(plan.div * 18446744073709551615.0)
+    soft_thr = np.uint64(plan.soft_frac * 18446744073709551615.0)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    old = np.seterr(over="ignore")
+    try:
+        for a in range(hlen, nbytes, block):
+            o = np.arange(a, min(a + block, nbytes), dtype=np.uint64)
+            q = o - np.uint64(hlen)
+            line = q // np.uint64(line_width + 1)
+            col = q - line * np.uint64(line_width + 1)
+            i = line * np.uint64(line_width) + col
+            newline = (col == np.uint64(line_width)) | (i >= np.uint64(L))
+            ii = np.minimum(i, np.uint64(max(L - 1, 0)))
+            isn = np.zeros(len(o), dtype=bool)
+            if len(rs):
+                lo = np.searchsorted(rs, ii, side="right")
+                ok = lo > 0
+                isn[ok] = ii[ok] < re[lo[ok] - 1]
+            sidx = np.searchsorted(starts, ii, side="right")
+            seg = np.maximum(sidx, 1) - 1
+            ssrc = src[seg]
+            bg = (sidx == 0) | (ssrc < 0)
+            b = (_mix(seed, ii) & np.uint64(3)).astype(np.uint32)
+            te = ~bg
+            if te.any():
+                within = ii[te] - starts[seg[te]]
+                pos = np.minimum(ssrc[te].astype(np.uint64) + within, np.uint64(len(lib) - 1))
+                tb = (lib[pos.astype(np.int64)] & 3).astype(np.uint32)
+                h = _mix(seed ^ (seeds[seg[te]].astype(np.uint64) << np.uint64(32)), within)
+                mut = h < div_thr
+                tb[mut] = (tb[mut] + 1 + ((h[mut] >> np.uint64(7)) % np.uint64(3)).astype(np.uint32)) & 3
+                b[te] = tb
+            ch = acgt[b]
+            soft = _mix(seed ^ np.uint64(0xABCDEF), ii >> np.uint64(9)) < soft_thr
+            ch = np.where(soft, ch | 0x20, ch).astype(np.uint8)
+            ch[isn] = ord("N")
+            ch[newline] = ord("\n")
+            out[a:a + len(o)] = ch
+    finally:
+        np.seterr(**old)
+    return out
 
 
 def plan_for(config, seed=None, scale=1.0):

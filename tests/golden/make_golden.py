@@ -209,9 +209,14 @@ def gen_map_stack(Seqs, Circos):
         for ws in (bin_size, bin_size * 3, 1000, 1000000):
             coords, counts = Circos.stack_matrix(bc, window_size=ws)
             stacks[str(ws)] = dict(coords=[list(c) for c in coords], counts=[[int(x) for x in c] for c in counts])
+        # circos density tracks (Circos.py:777-806): files per subgenome, 99th-percentile clipping
+        dens = {}
+        for ws in (bin_size, bin_size * 3):
+            files = Circos.stack_bed_density(bc, os.path.join(tmp, "dens%d" % ws), sg_names, window_size=ws)
+            dens[str(ws)] = {key: open(path).read() for key, path in files.items()}
         shutil.rmtree(tmp)
         cases.append(dict(k=k, seq=seq, bin_size=bin_size, window_size=window, chunk=chunk, sg_names=sg_names,
-                          d_kmers=d_kmers, bin_count_text=text, stacks=stacks))
+                          d_kmers=d_kmers, bin_count_text=text, stacks=stacks, density=dens))
     jdump(cases, "map_stack.json")
 
 
@@ -275,6 +280,45 @@ def gen_cluster_units(C):
             rows.append(dict(array=arr, max_sg=max_sg, pvalue=float(pvalue), mean_vals=[float(m) for m in mean_vals]))
         cases.append(dict(n=n, groups=groups, rows=rows))
     jdump(cases, "ttest_rows.json")
+
+
+def gen_ranktest_units(C):
+    """Cluster._output_kmers (Cluster.py:178-194) with the other `-test_method` choices: scipy.stats.kruskal and
+    mannwhitneyu through the reference's own function with the installed scipy; wilcoxon through the restatement of the
+    pinned scipy 1.7.1 mode rules (oracle/restate.py wilcoxon_171 — the installed 1.18 treats ties / zeros differently)."""
+    from collections import OrderedDict
+
+    from scipy import stats
+
+    from oracle import restate
+    rng = np.random.default_rng(44)
+    cases = []
+    layouts = ((6, {"SG1": [0, 2, 4], "SG2": [1, 3, 5]}),
+               (21, {"SG1": list(range(0, 21, 3)), "SG2": list(range(1, 21, 3)), "SG3": list(range(2, 21, 3))}),
+               (20, {"SG1": list(range(0, 10)), "SG2": list(range(10, 20))}),       # both > 8: normal approximation
+               (14, {"SG1": list(range(0, 5)), "SG2": list(range(5, 14))}),         # unequal sizes (not for wilcoxon)
+               (60, {"SG1": list(range(0, 30)), "SG2": list(range(30, 60))}))       # n > 25: wilcoxon approximation
+    for method in ("kruskal", "mannwhitneyu", "wilcoxon"):
+        fn = dict(kruskal=stats.kruskal, mannwhitneyu=stats.mannwhitneyu, wilcoxon=restate.wilcoxon_171)[method]
+        for n, groups in layouts:
+            sizes = {len(v) for v in groups.values()}
+            if method == "wilcoxon" and len(sizes) > 1:
+                continue
+            rows = []
+            for r in range(100):
+                arr = rng.random(n) * 1e-5
+                own = list(groups.values())[int(rng.integers(0, len(groups)))]
+                arr[own] += rng.random(len(own)) * (5e-5 if r % 3 else 5e-6)
+                if r % 7 == 0:                                 # ties: counts / length of equal counts
+                    arr = np.round(arr * 2e5) / 2e5
+                if r % 11 == 0:                                # zero differences / many ties
+                    arr[:] = 1e-6
+                    arr[own[:2]] = 3e-6
+                arr = [float(x) for x in arr]
+                kmer, max_sg, pvalue, rc_kmer, mean_vals = C._output_kmers(("ACGT", arr, OrderedDict(groups), fn))
+                rows.append(dict(array=arr, max_sg=max_sg, pvalue=float(pvalue), mean_vals=[float(m) for m in mean_vals]))
+            cases.append(dict(method=method, n=n, groups=groups, rows=rows))
+    jdump(cases, "ranktest_rows.json")
 
 
 def gen_pipeline(J, C, Seqs, Circos, S_mod):
@@ -375,6 +419,7 @@ def main(only=None):
     gen_map_stack(Seqs, Circos)
     gen_map_multi(Seqs)
     gen_cluster_units(C)
+    gen_ranktest_units(C)
     gen_pipeline(J, C, Seqs, Circos, S_mod)
 
 

@@ -214,3 +214,48 @@ def test_v3_tiny_and_empty_inputs():
                 util.random_seq(rng, 4 * 16384 + 17)):
         fa = util.fasta([("t", seq)])
         _check_forced(fa, 17, 1, 700_000_000, 18)
+
+
+def _unpack(seq):
+    """PackedSeq -> uint8 codes (0..3, 4 = invalid) on the host"""
+    n = seq.n_bases
+    pk = seq.packed.cpu().numpy().view(np.uint32)
+    vd = seq.valid.cpu().numpy().view(np.uint32)
+    i = np.arange(n, dtype=np.int64)
+    codes = ((pk[i >> 4] >> ((i & 15) * 2).astype(np.uint32)) & 3).astype(np.uint8)
+    ok = ((vd[i >> 5] >> (i & 31).astype(np.uint32)) & 1).astype(bool)
+    codes[~ok] = 4
+    return codes
+
+
+@pytest.mark.parametrize("mode", ["single", "3pass"])
+def test_pack_matches_oracle_codes(mode, monkeypatch):
+    """K1: the single-pass kernel (decoupled look-back, local line state) and the three-pass fallback (lines longer than
+    the look-back window) give the oracle's code stream for wrapped, unwrapped, CRLF, multi-record and odd inputs."""
+    if MODE[0] != "partitioned":
+        pytest.skip("independent of the counter")
+    from oracle import kmers
+    from subphaser_b200 import engine
+    if mode == "3pass":
+        monkeypatch.setenv("SPK_PACK_MODE", "3pass")
+    rng = np.random.default_rng(31)
+    big = util.messy_seq(rng, 300_000)
+    cases = [
+        util.fasta([("a", big)]),                                   # 60-column lines: single pass
+        util.fasta([("a", big)], width=100000),                     # lines of 100 kb: look-back window exceeded
+        util.fasta([("a", big)], width=511), util.fasta([("a", big)], width=512), util.fasta([("a", big)], width=513),
+        util.fasta([("a", big)], width=61, crlf=True),
+        util.fasta([("r%d" % i, util.messy_seq(rng, int(rng.integers(0, 9000)))) for i in range(40)], width=70),
+        util.fasta([("h" * 700, big[:5000]), ("x" * 5000 + " long header", big[5000:9000])]),   # headers longer than the window
+        b">a\n" + big[:4093].encode() + b"\n>b\n" + big[:100].encode(),          # header at a tile boundary, no final newline
+        big[:20000].encode(),                                        # no header, no newline at all
+        b"\n\n>x\n\nAC\n\nGT\n>y\n>z\nN\n",
+    ]
+    for fa in cases:
+        want, nrec = kmers.fasta_to_codes(fa)
+        d, n = engine.to_device_bytes(fa)
+        seq = engine.pack_fasta(d, n)
+        assert seq.n_bases == len(want) and seq.n_records == nrec
+        got = _unpack(seq)
+        np.testing.assert_array_equal(got, np.minimum(want, 4))
+        assert seq.n_valid == int(np.sum(want < 4))

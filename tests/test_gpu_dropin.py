@@ -88,7 +88,7 @@ def test_filter_value_errors(small_dumps):
         dumps2.lengths = [0] + list(dumps2.lengths[1:])
         dumps2.filter(dm2, dumps2.lengths, sgs, outfig="x")
     with pytest.raises(ValueError, match="0 kmer with fold"):                          # :508-509
-        dumps.filter(d_mat, lengths, sgs, outfig=os.path.join(os.path.dirname(files[0]), "h.pdf"), min_fold=1e9,
+        dumps.filter(d_mat, lengths, sgs, outfig=os.path.join(os.path.dirname(files[0]), "h.pdf"), min_fold=1e30,
                      min_freq=1)
     with pytest.raises(IndexError):                                                    # freqs[baseline] of :639-642
         dumps.filter(d_mat, lengths, sgs, outfig="x", baseline=2)
@@ -103,15 +103,15 @@ def test_filter_min_prop_max_prop(small_dumps):
     d_mat = dumps.to_matrix()
     tot = sum(dumps.lengths)
     fig = os.path.join(os.path.dirname(files[0]), "p.pdf")
-    dm = dumps.filter(d_mat, dumps.lengths, sgs, outfig=fig, min_prop=20.0 / tot, max_prop=900.0 / tot,
+    dm = dumps.filter(d_mat, dumps.lengths, sgs, outfig=fig, min_prop=5.0 / tot, max_prop=900.0 / tot,
                       min_freq=10**9, max_freq=0)          # overridden by the proportions
-    dm_ref = dumps.filter(dumps.to_matrix(), dumps.lengths, sgs, outfig=fig, min_freq=20.0, max_freq=900.0)
+    dm_ref = dumps.filter(dumps.to_matrix(), dumps.lengths, sgs, outfig=fig, min_freq=5.0, max_freq=900.0)
     assert len(dm) == len(dm_ref) > 0
     np.testing.assert_array_equal(engine.u64_numpy(dm.keys), engine.u64_numpy(dm_ref.keys))
     # and against the oracle restatement of _filter_kmer
     host = [Jellyfish.load_dump(d).to_host() for d in dumpfiles]
     allk, mat, lengths = restate.to_matrix(host)
-    okeys, onorm, _, _ = restate.filter_matrix(allk, mat, lengths, labels, sgs, min_freq=20.0, max_freq=900.0,
+    okeys, onorm, _, _ = restate.filter_matrix(allk, mat, lengths, labels, sgs, min_freq=5.0, max_freq=900.0,
                                                min_fold=2, baseline=1, ratio=1)
     np.testing.assert_array_equal(engine.u64_numpy(dm.keys), okeys)
     assert dm.norm.cpu().numpy().tobytes() == onorm.tobytes()
@@ -243,17 +243,30 @@ def test_count_fasta_host_entry_point():
     fa = util.fasta([("h", util.messy_seq(rng, 120_000, repeat_unit="ACGT"))])
     k, lower = 17, 2
     cap = len(fa)
-    keys = torch.empty(cap, dtype=torch.int64, device="cuda")
-    counts = torch.empty(cap, dtype=torch.int32, device="cuda")
-    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    dev = "cuda"
+    d_ascii = torch.empty(cap + 16, dtype=torch.uint8, device=dev)
+    d_packed = torch.empty(lib.spk_packed_words(cap), dtype=torch.int32, device=dev)
+    d_valid = torch.empty(lib.spk_valid_words(cap), dtype=torch.int32, device=dev)
+    ws_bytes = lib.spk_pack_workspace_bytes(cap)
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    table_bytes = lib.spk_count_table_bytes(cap, k)
+    d_table = torch.empty(table_bytes, dtype=torch.uint8, device=dev)
+    d_blocks = torch.empty(3 * lib.spk_table_scan_blocks() + 2, dtype=torch.int32, device=dev)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    counts = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_info = torch.zeros(12, dtype=torch.int64, device=dev)
+    h_out = (ctypes.c_uint64 * 8)()
     buf = np.frombuffer(fa, dtype=np.uint8)
-    _lib.call("spk_count_fasta_host", buf.ctypes.data_as(ctypes.c_void_p), len(fa), k, lower, engine._p(keys),
-              engine._p(counts), cap, engine._p(stats), engine._stream())
+    P = engine._p
+    _lib.call("spk_count_fasta_host", buf.ctypes.data_as(ctypes.c_void_p), len(fa), k, lower, P(d_ascii), P(d_packed),
+              P(d_valid), cap, P(d_ws), ws_bytes, P(d_table), table_bytes, P(d_blocks), P(keys), P(counts), cap,
+              P(d_info), ctypes.cast(h_out, ctypes.c_void_p), engine._stream())
     torch.cuda.synchronize()
-    st = stats.cpu().tolist()
     okeys, ocounts, ost = kmers.count_fasta(fa, k, lower)
-    n = int(st[5])
-    assert n == ost["n_dumped"] and int(st[0]) == ost["n_valid_kmers"] and int(st[6]) == ost["sum_dumped"]
+    out = [int(x) for x in h_out]
+    assert out[0] == ost["n_bases"] and out[2] == ost["n_records"] and out[3] == ost["n_valid_kmers"]
+    assert out[4] == ost["n_distinct"] and out[5] == ost["n_dumped"] and out[6] == ost["sum_dumped"] and out[7] == 0
+    n = out[5]
     gk = engine.u64_numpy(keys[:n])
     gc = counts[:n].cpu().numpy().view(np.uint32)
     o = np.argsort(gk, kind="stable")

@@ -327,6 +327,73 @@ def test_ttest_rows_match_reference_vectors():
                 assert pval[i] == pytest.approx(r["pvalue"], rel=1e-9, abs=1e-300)
 
 
+def test_ranktest_rows_match_reference_vectors(tmp_path):
+    """a7: `-test_method kruskal | mannwhitneyu | wilcoxon` (Cluster.py:160,191) — best group, exact group means and the
+    p-value of the reference's _output_kmers with scipy's test (wilcoxon: the pinned scipy 1.7.1 mode rules)."""
+    from subphaser_b200 import engine
+    for case in load("ranktest_rows.json"):
+        sgs = sorted(case["groups"])
+        n = case["n"]
+        col_group = [0] * n
+        for gi, sg in enumerate(sgs):
+            for c in case["groups"][sg]:
+                col_group[c] = gi
+        X = np.array([r["array"] for r in case["rows"]], dtype=np.float64)
+        best, pval, means, flags = engine.ranktest_groups(_dev(X, np.float64), col_group, len(sgs), case["method"])
+        best, pval, means = best.cpu().numpy(), pval.cpu().numpy(), means.cpu().numpy()
+        assert flags == 0
+        for i, r in enumerate(case["rows"]):
+            assert sgs[best[i]] == r["max_sg"]
+            assert means[i].tolist() == r["mean_vals"]
+            if math.isnan(r["pvalue"]):
+                assert math.isnan(pval[i]), (case["method"], n, i)
+            else:
+                assert pval[i] == pytest.approx(r["pvalue"], rel=1e-9, abs=1e-300), (case["method"], n, i)
+
+
+def test_ranktest_against_installed_scipy_and_errors(tmp_path):
+    """The branches both scipy versions share, checked against the installed scipy directly, and the two conditions under
+    which scipy raises (the drop-in raises the same ValueError from Cluster.output_kmers)."""
+    from scipy import stats
+    from subphaser_b200 import engine
+    from subphaser_b200.Cluster import Cluster
+    rng = np.random.default_rng(8)
+    n = 14
+    col_group = [0] * 7 + [1] * 7
+    X = rng.random((400, n)) * 1e-5
+    X[:, :7] += rng.random((400, 7)) * 3e-5
+    dX = _dev(X, np.float64)
+    for method, fn in (("kruskal", stats.kruskal), ("mannwhitneyu", stats.mannwhitneyu), ("wilcoxon", stats.wilcoxon)):
+        best, pval, means, flags = engine.ranktest_groups(dX, col_group, 2, method)
+        pval, best = pval.cpu().numpy(), best.cpu().numpy()
+        for i in range(len(X)):
+            a, b = (X[i, :7], X[i, 7:]) if best[i] == 0 else (X[i, 7:], X[i, :7])
+            assert pval[i] == pytest.approx(float(fn(a, b).pvalue), rel=1e-9, abs=1e-300), (method, i)
+    # wilcoxon on groups of different size, kruskal on identical values
+    _, _, _, flags = engine.ranktest_groups(dX, [0] * 6 + [1] * 8, 2, "wilcoxon")
+    assert flags & 1
+    same = np.full((3, n), 2e-5)
+    _, _, _, flags = engine.ranktest_groups(_dev(same, np.float64), col_group, 2, "kruskal")
+    assert flags & 2
+    # through the drop-in class
+    mat = tmp_path / "m.kmer.mat"
+    chrs = ["c%02d" % i for i in range(n)]
+    with open(mat, "w") as f:
+        f.write("kmer\t" + "\t".join(chrs) + "\n")
+        for i in range(50):
+            kmer = "".join("ACGT"[(i >> (2 * b)) & 3] for b in range(15))
+            f.write(kmer + "\t" + "\t".join(repr(float(v)) for v in X[i]) + "\n")
+    assigned = {c: ("SG1" if i < 6 else "SG2") for i, c in enumerate(chrs)}
+    cl = Cluster(str(mat), n_clusters=2, sg_assigned=assigned, replicates=0)
+    import io
+    with pytest.raises(ValueError, match="same length"):
+        cl.output_kmers(io.StringIO(), test_method="wilcoxon")
+    d = cl.output_kmers(io.StringIO(), test_method="mannwhitneyu")
+    assert len(d) > 0
+    with pytest.raises(AttributeError):
+        cl.output_kmers(io.StringIO(), test_method="no_such_test")
+
+
 def _blobs(rng, n_per, S, M, sep=6.0):
     centers = rng.normal(0, sep, (S, M))
     X = np.concatenate([centers[s] + rng.normal(0, 1.0, (n_per, M)) for s in range(S)])
