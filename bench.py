@@ -214,6 +214,28 @@ def parity_at_scale(plan, threads, sample_bases):
     return out
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this process on the CPUs next to its GPU (sysfs local_cpulist of the PCI device), so that the pinned host
+    buffers it allocates afterwards live on that NUMA node: with 8 ranks on a two-socket box half of the host->device
+    copies otherwise cross the socket interconnect."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
 def workload_name(args, plan, cfg):
     g = sum(c["length"] for c in plan.chroms)
     shape = {"C1": "Arabidopsis-shaped", "C2": "peanut-shaped", "C5": "hexaploid"}.get(args.config, "wheat-shaped")
@@ -331,6 +353,7 @@ def main():
     # ---- end-to-end arm: host (pinned) FASTA bytes -> H2D inside the timed region -> results D2H ----
     e2e = None
     if not args.no_e2e:
+        bind_to_gpu_numa_node(local_rank)       # pinned staging buffers on the GPU's own NUMA node
         host_inputs = [None] * len(lengths)
         for i in range(len(lengths)):
             if i in mine:

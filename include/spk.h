@@ -217,6 +217,32 @@ int spk_dump_scatter_peers(const uint64_t* d_keys, const uint32_t* d_counts, con
                            uint64_t* d_overflow, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Histogram of the totals of the fold-passing k-mers (`.kmer_freq.pdf`, Jellyfish.py:499-511,650-666) without
+ * materialising them on the host.  d_tot / d_flags: outputs of spk_filter_differential (bit 0 of a flag = the row
+ * passed the fold test).  spk_tot_minmax: d_out uint64[3] = count, min, max.  spk_tot_histogram: numpy.histogram
+ * semantics for `nbins` uniform bins over [mn, mx].  spk_tot_select_pass: one 16-bit pass of a radix select (counts of
+ * bits [shift, shift+16) among the values whose higher bits equal `prefix`) — the caller walks the passes to the
+ * order statistics np.percentile needs.  syncs: no. */
+int spk_tot_minmax(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, uint64_t* d_out, void* stream);
+int spk_tot_histogram(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, double mn, double mx, uint32_t nbins,
+                      uint64_t* d_hist, void* stream);
+int spk_tot_select_pass(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, int shift, uint64_t prefix,
+                        uint64_t* d_hist65536, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Genome ingest (Seqs.split_genomes, Seqs.py:27-71, without BioPython): the genome file's bytes are on the device.
+ * spk_fasta_record_starts: positions of every record start ('>' at byte 0 or after '\n') appended, unordered, to
+ *   d_pos (uint64[cap]); *d_count = number of records (may exceed cap: call again with a larger array).
+ * spk_fasta_wrap_check: is the body [beg, end) of a record laid out as BioPython writes it (lines of `width` bytes
+ *   ending in '\n')?  d_out (uint64[2]): [0] bit 0 = irregular line breaks, bit 1 = bytes that need rewriting
+ *   ('\r', blanks, '>'); [1] = number of '\n' bytes.  A regular body is written to `<id>.fasta` verbatim.
+ * syncs: no. */
+int spk_fasta_record_starts(const uint8_t* d_ascii, uint64_t nbytes, uint64_t* d_pos, uint64_t cap, uint64_t* d_count,
+                            void* stream);
+int spk_fasta_wrap_check(const uint8_t* d_ascii, uint64_t beg, uint64_t end, uint32_t width, uint64_t* d_out,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Text wire formats on the device.  spk_format_rows writes the rows of `.kmer.mat` (kind 0:
  * `KMER\tv1\t...\tvn\n`, JellyfishDumps.write_matrix, Jellyfish.py:515-520) or of `.sig.kmer-subgenome.tsv`
  * (kind 1: `KMER\tLABEL\tp\tm1,...,mn\n`, Cluster.output_kmers, Cluster.py:158-172) exactly as Python's str()

@@ -57,7 +57,7 @@ def _fasta_parse(handle, fmt="fasta"):
         line = line.rstrip("\r\n")
         if line.startswith(">"):
             if rid is not None:
-                yield _Record(rid, "".join(chunks), desc)
+                yield _Record(rid, "".join(chunks).replace(" ", "").replace("\r", ""), desc)
             desc = line[1:]
             rid = desc.split()[0] if desc.split() else ""
             chunks = []
@@ -72,7 +72,15 @@ def _fasta_write(records, handle, fmt="fasta"):
         records = [records]
     n = 0
     for rc in records:
-        handle.write(">{}\n".format(rc.description or rc.id))
+        # Bio.SeqIO.FastaIO.FastaWriter.write_record (BioPython 1.79): the parsed title is kept; a changed id goes in front
+        rid, desc = str(rc.id), str(rc.description or "")
+        if desc and desc.split(None, 1)[0] == rid:
+            title = desc
+        elif desc:
+            title = "{} {}".format(rid, desc)
+        else:
+            title = rid
+        handle.write(">{}\n".format(title))
         s = str(rc.seq)
         for i in range(0, len(s), 60):
             handle.write(s[i:i + 60] + "\n")

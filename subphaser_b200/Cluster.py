@@ -250,6 +250,10 @@ class Cluster:
         if S < 2:
             raise IndexError("list index out of range")      # grouped[1] in the reference (:187)
         if test_method == "ttest_ind":
+            if min(col_group.count(g) for g in range(S)) == 1:
+                logger.warning("a subgenome holds a single chromosome: scipy 1.7.1 (pinned by SubPhaser) gives NaN p-values "
+                               "for tests against it and such k-mers are kept (Cluster.py:167); set "
+                               "SPK_TTEST_SINGLETON=zero for the behaviour of scipy >= 1.9")
             best, pval, means = engine.ttest_groups(self._X, col_group, S)
         else:
             best, pval, means, flags = engine.ranktest_groups(self._X, col_group, S, test_method)

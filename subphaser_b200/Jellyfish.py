@@ -94,51 +94,69 @@ def run_jellyfish_dump(seqfile, threads=4, k=17, prefix=None, lower_count=2, met
         if prefix is None:
             prefix = seqfile
     output = "{prefix}_{KMER}.fa".format(KMER=k, prefix=prefix)
+    # Checkpoints.  `<output>.ok` keeps the reference's meaning — a jellyfish-style text dump is complete at `output`
+    # (Jellyfish.py:691-694) — and is only touched when that text is written (SPK_TEXT_DUMPS=1).  The binary side-car
+    # (SPK_DUMP_SIDECAR=1; 12 bytes per dumped k-mer) has its own marker `<output>.spk.ok`, so a later stock SubPhaser
+    # run in the same directory never mistakes an empty placeholder for a finished dump.  Without either, a re-run
+    # simply recounts (the GPU counts a chromosome faster than a multi-GB dump loads).
     ckp_file = output + ".ok"
     side = output + SIDE_SUFFIX
-    if not overwrite and os.path.exists(ckp_file):
-        if _registry.get_dump(output) is not None:
+    side_ckp = output + ".spk.ok"
+    src_sig = tuple(_registry._sig(f) for f in files)
+    if not overwrite:
+        if _registry.get_dump(output, k=int(k), lower_count=int(lower_count), src_sig=src_sig) is not None:
             return output
-        if os.path.exists(side):
+        if os.path.exists(side_ckp) and os.path.exists(side):
             with np.load(side) as z:
                 if int(z["k"]) == int(k) and int(z["lower_count"]) == int(lower_count):
                     return output       # loaded lazily by JellyfishDumps
-        elif os.path.exists(output) and os.path.getsize(output) > 0:
-            return output               # a text dump left by real jellyfish
+        if os.path.exists(ckp_file) and os.path.exists(output) and os.path.getsize(output) > 0:
+            return output               # a text dump left by real jellyfish (or SPK_TEXT_DUMPS=1)
     engine.require_cuda()
-    bufs = [engine.read_fasta_bytes(f) for f in files]
-    if len(bufs) > 1:
-        nl = np.frombuffer(b"\n", dtype=np.uint8)
-        parts = []
-        for b in bufs:
-            parts += [b, nl]
-        buf = np.concatenate(parts)
-    else:
-        buf = bufs[0]
-    d_ascii, nbytes = engine.to_device_bytes(buf)
-    seq = engine.pack_fasta(d_ascii, nbytes, name=os.path.basename(_seqfile))
-    del d_ascii
+    # a chromosome that Seqs.split_genomes produced in this process is already packed on the device
+    seq = _registry.get_seq(files[0]) if len(files) == 1 else None
+    if seq is None:
+        bufs = [engine.read_fasta_bytes(f) for f in files]
+        if len(bufs) > 1:
+            nl = np.frombuffer(b"\n", dtype=np.uint8)
+            parts = []
+            for b in bufs:
+                parts += [b, nl]
+            buf = np.concatenate(parts)
+        else:
+            buf = bufs[0]
+        d_ascii, nbytes = engine.to_device_bytes(buf)
+        seq = engine.pack_fasta(d_ascii, nbytes, name=os.path.basename(_seqfile))
+        del d_ascii
     dump = engine.count_packed(seq, int(k), int(lower_count), table=_table, histo_len=100002)
     if len(files) == 1:
         _registry.put_seq(files[0], seq)
-    _registry.put_dump(output, dump)
-    keys, counts = dump.to_host()
-    extra = {}
-    if dump.pindex is not None:
-        extra = dict(pindex=dump.pindex.cpu().numpy(), pbits=np.int64(dump.pbits))
-    np.savez(side, keys=keys, counts=counts, k=np.int64(k), lower_count=np.int64(lower_count),
-             length=np.int64(dump.length), n_valid_kmers=np.int64(dump.n_valid_kmers),
-             n_distinct=np.int64(dump.n_distinct), **extra)
+    _registry.put_dump(output, dump, k=int(k), lower_count=int(lower_count), src_sig=src_sig)
+    want_text = os.environ.get("SPK_TEXT_DUMPS") == "1"
+    want_side = os.environ.get("SPK_DUMP_SIDECAR") == "1"
+    for stale in (ckp_file, side_ckp) + (() if want_side else (side,)):     # an earlier run's files describe other content now
+        if os.path.exists(stale):
+            os.remove(stale)
+    if want_text or want_side:
+        keys, counts = dump.to_host()
+    if want_side:
+        extra = {}
+        if dump.pindex is not None:
+            extra = dict(pindex=dump.pindex.cpu().numpy(), pbits=np.int64(dump.pbits))
+        np.savez(side, keys=keys, counts=counts, k=np.int64(k), lower_count=np.int64(lower_count),
+                 length=np.int64(dump.length), n_valid_kmers=np.int64(dump.n_valid_kmers),
+                 n_distinct=np.int64(dump.n_distinct), **extra)
+        _touch(side_ckp)
     histo = dump.histo.cpu().numpy()
     with open("{}_{}.histo".format(prefix, k), "w") as f:
         for c in np.nonzero(histo)[0]:
             if c > 0:
                 f.write("%d %d\n" % (c, histo[c]))
-    if os.environ.get("SPK_TEXT_DUMPS") == "1":
+    if want_text:
         _write_text_dump(output, keys, counts, int(k))
-    else:
-        _touch(output)
-    _touch(ckp_file)
+        _touch(ckp_file)
+    elif not os.path.exists(output):
+        _touch(output)                  # the path `__main__.py` carries around; its content lives on the device
     logger.info("Counted {}: {:,} bases, {:,} k-mers, {:,} distinct, {:,} with count >= {}".format(
         _seqfile, seq.n_bases, dump.n_valid_kmers, dump.n_distinct, len(dump), lower_count))
     return output
@@ -153,7 +171,7 @@ def load_dump(dumpfile):
     engine.require_cuda()
     pindex, pbits = None, 0
     side = dumpfile + SIDE_SUFFIX
-    if os.path.exists(side):
+    if os.path.exists(side) and os.path.exists(dumpfile + ".spk.ok"):
         with np.load(side) as z:
             keys, counts, k = z["keys"], z["counts"], int(z["k"])
             length = int(z["length"])
@@ -296,16 +314,21 @@ def _heatmap(matfile, **kargs):
 
 
 def plot_histogram(data, outfig, step=25, xlim=99, xlabel="Kmer occurrence", ylabel="Count", vline=None):
-    """Jellyfish.py:650-666.  Figure if matplotlib is available; the binned counts always go to
-    `<outfig>.tsv` so the information is not lost without it."""
-    data = np.asarray(data)
-    _max = int(data.max()) if data.size else 0
-    nbins = max(int((_max - 0) / step), 1)
-    hist, edges = np.histogram(data, bins=nbins)
+    """Jellyfish.py:650-666.  `data`: the totals themselves (any sequence) or an engine.FoldHistogram (binned on the
+    device).  The binned counts always go to `<outfig>.tsv`; the figure is drawn when matplotlib is available."""
+    if isinstance(data, engine.FoldHistogram):
+        hist, edges, limit = data.hist, data.edges, data.xlim
+    else:
+        data = np.asarray(data)
+        _max = int(data.max()) if data.size else 0
+        nbins = max(int((_max - 0) / step), 1)
+        hist, edges = np.histogram(data, bins=nbins)
+        limit = float(np.percentile(data, xlim)) if data.size else 0.0
     with open(outfig + ".tsv", "w") as f:
         f.write("#bin_start\tbin_end\tcount\n")
         for a, b, c in zip(edges[:-1], edges[1:], hist):
             f.write("%g\t%g\t%d\n" % (a, b, c))
+        f.write("#xlim (percentile %g)\t%r\n" % (xlim, limit))
     try:
         from matplotlib import pyplot as plt
     except Exception:
@@ -313,8 +336,8 @@ def plot_histogram(data, outfig, step=25, xlim=99, xlabel="Kmer occurrence", yla
         return
     plt.switch_backend("agg")
     plt.figure(figsize=(7, 5), dpi=300, tight_layout=True)
-    plt.hist(data, bins=nbins)
-    plt.xlim(0, np.percentile(data, xlim))
+    plt.bar(edges[:-1], hist, width=np.diff(edges), align="edge")       # the bars plt.hist(data, bins=nbins) draws
+    plt.xlim(0, limit)
     plt.xlabel(xlabel)
     plt.ylabel(ylabel, ha="center", va="center")
     plt.ticklabel_format(style="plain")

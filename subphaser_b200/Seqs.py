@@ -6,9 +6,12 @@ HBM from the counting step) is looked up in the specific-k-mer table and counted
 duplicate-coordinate lines at chunk borders (:131-137, :229-236) — byte for byte when the reference
 runs with the ordered `method='map'`.
 
-`split_genomes` (:27-71, FASTA re-writing with BioPython) is the next component of SURVEY.md §8f and
-is provided here as plain host code so that `__main__.py` keeps working.
-Multi-record inputs with `chunk=False` (custom features / LTRs) are not on the GPU path yet.
+Multi-record inputs (custom features / LTRs, `chunk=False`) go through the same kernel with a record index.
+
+`split_genomes` (:27-71, FASTA re-writing with BioPython in the reference) runs on the device as well: the records of
+a genome file are found by `spk_fasta_record_starts`, every wanted chromosome is packed by K1 straight from the device
+copy of the file and registered for the counting / mapping steps, and the per-chromosome FASTA files are written from
+verbatim byte ranges of the input whenever `spk_fasta_wrap_check` finds them already in 60-column layout.
 """
 import copy
 import logging
@@ -159,9 +162,9 @@ def map_kmer3(chromfiles, d_kmers, fout=sys.stdout, k=None, window_size=10e6,
             i += n_chunks
             mapped_num += nhits
             if nhits > 0:
-                # the reference counts chunks ("sequences") containing hits; per-chunk hit flags are not
-                # tracked on the device, records with hits are counted chunk-wise as all-mapped
-                mapped_seqs += n_chunks
+                # the reference counts the chunks ("sequences") that contain a hit (Seqs.py:110-111): a line id encodes
+                # its chunk, so the chunks with hits are the distinct chunk ids of the non-empty lines
+                mapped_seqs += int(len(np.unique(chk))) if (W and len(nz)) else 1
     logger.info("Processed {} sequences".format(i))
     mapped_cat, total = sig.n_mapped(), len(d_kmers)
     try:
@@ -176,47 +179,161 @@ def map_kmer3(chromfiles, d_kmers, fout=sys.stdout, k=None, window_size=10e6,
             _registry.put_bins(name, all_lines)
 
 
-def split_genomes(genomes, prefixes, targets, outdir, d_targets=None, sep="|"):
-    """Seqs.py:27-71 (host code, no BioPython): one FASTA per target chromosome, id remapping."""
-    d_targets2 = OrderedDict()
+def _target_maps(targets, d_targets, sep):
+    """The two id maps of Seqs.py:29-46.  d_targets: id as it occurs in the genome files (possibly with the genome's
+    prefix) -> output id; d_targets2: entry as written in the config -> output id.  A config entry `new|old` renames."""
+    d2 = OrderedDict()
     if not d_targets:
         d_targets = OrderedDict()
-        for t in targets:
-            temp = t.split(sep, 1)
-            id, new_id = temp[-1], temp[0]
-            d_targets[id] = new_id
-            d_targets2[t] = new_id
-    elif set(targets) - set(d_targets):
-        for t in set(targets) - set(d_targets):
-            temp = t.split(sep, 1)
-            id, new_id = temp[-1], temp[0]
-            d_targets[id] = new_id
-            d_targets2[t] = new_id
+        todo = list(targets)
     else:
-        d_targets2 = copy.deepcopy(d_targets)
-    outfas, labels = [], []
-    d_size = {}
-    got_ids = set([])
-    for genome, prefix in zip(genomes, prefixes):
-        for rid, desc, seq in _iter_fasta(genome):
-            old_id, new_id = rid, "{}{}".format(prefix, rid)
-            if d_targets:
-                if new_id in d_targets:
-                    rid = new_id
-                elif old_id in d_targets:
-                    pass
-                else:
-                    continue
-            got_ids.add(rid)
-            rid = d_targets[rid]
-            outfa = "{}{}.fasta".format(outdir, rid)
-            with open(outfa, "w") as fout:
-                fout.write(">{} {}\n".format(rid, desc) if desc else ">{}\n".format(rid))
-                for a in range(0, len(seq), 60):
-                    fout.write(seq[a:a + 60] + "\n")
-            outfas += [outfa]
-            labels += [rid]
-            d_size[rid] = len(seq)
+        todo = list(set(targets) - set(d_targets))
+        if not todo:
+            return d_targets, copy.deepcopy(d_targets)
+    for entry in todo:
+        new_id, _, old_id = entry.partition(sep)
+        d_targets[old_id if _ else new_id] = new_id
+        d2[entry] = new_id
+    return d_targets, d2
+
+
+def _read_genome_bytes(path):
+    """Genome file -> uint8 array in pinned host memory (gzip members inflated by zlib in a worker thread while the
+    previous file is on the GPU: the reference's `zcat` leg, Jellyfish.py:696)."""
+    import torch
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        import zlib
+        pieces, size = [], 0
+        with open(path, "rb") as f:
+            dec = zlib.decompressobj(wbits=31)
+            while True:
+                raw = f.read(1 << 24)
+                if not raw:
+                    break
+                while raw:
+                    out = dec.decompress(raw)
+                    if out:
+                        pieces.append(out)
+                        size += len(out)
+                    if dec.eof:                      # concatenated gzip members (bgzip)
+                        raw = dec.unused_data
+                        dec = zlib.decompressobj(wbits=31)
+                    else:
+                        raw = b""
+        host = torch.empty(size + 16, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        view = host.numpy()
+        at = 0
+        for piece in pieces:
+            view[at:at + len(piece)] = np.frombuffer(piece, np.uint8)
+            at += len(piece)
+        return host, size
+    size = os.path.getsize(path)
+    host = torch.empty(size + 16, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    with open(path, "rb") as f:
+        f.readinto(memoryview(host.numpy())[:size])
+    return host, size
+
+
+def _write_chrom_file(path, title, body, verbatim, wrap=60):
+    """`>title` + the sequence in lines of 60 (what SeqIO.write produces).  verbatim: `body` (uint8 view of the input
+    file) already has that layout."""
+    with open(path, "wb") as f:
+        f.write(b">" + title.encode() + b"\n")
+        if verbatim:
+            f.write(memoryview(body))
+            if len(body) and body[-1] != 10:
+                f.write(b"\n")
+            return
+        seq = body[(body != 10) & (body != 13) & (body != 32)]
+        n = len(seq)
+        full = n // wrap
+        if full:
+            lines = np.empty((full, wrap + 1), np.uint8)
+            lines[:, :wrap] = seq[:full * wrap].reshape(full, wrap)
+            lines[:, wrap] = 10
+            f.write(memoryview(lines.reshape(-1)))
+        if n % wrap:
+            f.write(memoryview(seq[full * wrap:]))
+            f.write(b"\n")
+
+
+def split_genomes(genomes, prefixes, targets, outdir, d_targets=None, sep="|"):
+    """Seqs.py:27-71 with the genome on the GPU instead of BioPython on the host.  Per genome file: the bytes go to the
+    device once (pinned buffer; gz inflated by zlib), `spk_fasta_record_starts` finds the records, the ids are resolved on
+    the host (a few bytes per record), and every wanted record is (a) packed by K1 straight from the device buffer — the
+    2-bit sequence is registered under the chromosome's file path, so the count and map steps never read the file —
+    and (b) written as `<outdir><id>.fasta` by a writer thread, as a verbatim byte range of the input when
+    `spk_fasta_wrap_check` finds it already in 60-column layout.  Returns (files, labels, d_targets2, d_size) as the
+    reference does; `d_size[id]` = number of sequence characters."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from . import _lib
+    engine.require_cuda()
+    d_targets, d_targets2 = _target_maps(targets, d_targets, sep)
+    outfas, labels, d_size, got_ids = [], [], {}, set()
+    pending = []
+    dev = engine._dev()
+    with ThreadPoolExecutor(max_workers=4) as writers, ThreadPoolExecutor(max_workers=1) as reader:
+        nxt = reader.submit(_read_genome_bytes, genomes[0]) if genomes else None
+        for gi, (genome, prefix) in enumerate(zip(genomes, prefixes)):
+            host, size = nxt.result()
+            nxt = reader.submit(_read_genome_bytes, genomes[gi + 1]) if gi + 1 < len(genomes) else None
+            d_file = torch.empty(size + 16, dtype=torch.uint8, device=dev)
+            d_file[:size].copy_(host[:size], non_blocking=True)
+            view = host.numpy()[:size]
+            # ---- record starts (device) ----
+            cap = 1 << 16
+            while True:
+                d_pos = torch.empty(cap, dtype=torch.int64, device=dev)
+                d_cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+                _lib.call("spk_fasta_record_starts", engine._p(d_file), size, engine._p(d_pos), cap, engine._p(d_cnt),
+                          engine._stream())
+                n_rec = int(d_cnt.item())
+                if n_rec <= cap:
+                    break
+                cap = n_rec
+            starts = np.sort(d_pos[:n_rec].cpu().numpy()).tolist() + [size]
+            for r in range(n_rec):
+                a, b = starts[r], starts[r + 1]
+                eol = a + int(np.argmax(view[a:min(b, a + 65536)] == 10)) if (view[a:min(b, a + 65536)] == 10).any() else b
+                title = bytes(view[a + 1:eol]).decode(errors="replace").rstrip("\r")
+                old_id = title.split(None, 1)[0] if title.split() else ""
+                rid = prefix + old_id
+                if d_targets:
+                    if rid in d_targets:
+                        pass
+                    elif old_id in d_targets:
+                        rid = old_id
+                    else:
+                        continue
+                got_ids.add(rid)
+                new_id = d_targets[rid]                 # (no targets at all: KeyError, as in the reference)
+                # FastaWriter: the old title is kept behind a changed id
+                out_title = title if (title.split(None, 1)[:1] == [new_id]) else ("{} {}".format(new_id, title) if title else new_id)
+                body_a = min(eol + 1, b)
+                # ---- K1 on the record's bytes (device) ----
+                nb = b - a
+                d_rec = torch.empty(nb + 16, dtype=torch.uint8, device=dev)
+                d_rec[:nb].copy_(d_file[a:b])
+                seq = engine.pack_fasta(d_rec, nb, name=new_id)
+                del d_rec
+                d_chk = torch.zeros(2, dtype=torch.int64, device=dev)
+                _lib.call("spk_fasta_wrap_check", engine._p(d_file), body_a, b, 60, engine._p(d_chk), engine._stream())
+                flags = int(d_chk[0].item())
+                outfa = "{}{}.fasta".format(outdir, new_id)
+                fut = writers.submit(_write_chrom_file, outfa, out_title, view[body_a:b], flags == 0)
+                pending.append((fut, outfa, seq))
+                outfas.append(outfa)
+                labels.append(new_id)
+                d_size[new_id] = seq.n_bases
+            torch.cuda.current_stream().synchronize()
+            for fut, outfa, seq in pending:
+                fut.result()
+                _registry.put_seq(outfa, seq)          # (after the file exists: the registry keys on its signature)
+            pending = []
+            del d_file, host
     ungot_ids = set(d_targets) - got_ids
     if ungot_ids:
         logger.error("Chromosomes {} are not found in sequences files".format(ungot_ids))

@@ -47,6 +47,11 @@ SIGNATURES = {
                                       c_d, c_d, c_d, c_p, c_p, c_p, c_p]),
     "spk_filter_select": (c_i, [c_p, c_p, c_u64, c_p, c_p, c_p, c_u64, c_p]),
     "spk_filter_emit": (c_i, [c_p, c_p, c_p, c_u64, c_i, c_p, c_p, c_p, c_p]),
+    "spk_tot_minmax": (c_i, [c_p, c_p, c_u64, c_p, c_p]),
+    "spk_tot_histogram": (c_i, [c_p, c_p, c_u64, c_d, c_d, c_u32, c_p, c_p]),
+    "spk_tot_select_pass": (c_i, [c_p, c_p, c_u64, c_i, c_u64, c_p, c_p]),
+    "spk_fasta_record_starts": (c_i, [c_p, c_u64, c_p, c_u64, c_p, c_p]),
+    "spk_fasta_wrap_check": (c_i, [c_p, c_u64, c_u64, c_u32, c_p, c_p]),
     "spk_format_rows": (c_i, [c_p, c_p, c_u64, c_i, c_i, c_i, c_p, c_u64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spk_sort_workspace_bytes": (c_sz, [c_u64]),
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),

@@ -5,7 +5,7 @@ import os
 from collections import OrderedDict
 
 _SEQS = OrderedDict()     # chromosome FASTA path -> engine.PackedSeq
-_DUMPS = {}               # dump path (<chromfile>_<k>.fa) -> engine.KmerDump
+_DUMPS = OrderedDict()    # dump path (<chromfile>_<k>.fa) -> (engine.KmerDump, k, lower_count, source signature)
 _MATS = {}                # .kmer.mat path -> (signature, engine.DiffMatrix)
 _BINS = {}                # .bin.count path -> (signature, parsed arrays)
 
@@ -50,12 +50,31 @@ def get_seq(path):
     return v[1]
 
 
-def put_dump(path, dump):
-    _DUMPS[_key(path)] = dump
+DUMP_BUDGET = 256          # dumps kept on the device at most (a 21-chromosome genome uses 21; oldest go first)
 
 
-def get_dump(path):
-    return _DUMPS.get(_key(path))
+def put_dump(path, dump, k=None, lower_count=None, src_sig=None):
+    """dump of `path`, remembered together with the parameters and the source-file signature it was made from"""
+    key = _key(path)
+    _DUMPS.pop(key, None)
+    _DUMPS[key] = (dump, k, lower_count, src_sig)
+    while len(_DUMPS) > DUMP_BUDGET:
+        _DUMPS.pop(next(iter(_DUMPS)))
+
+
+def get_dump(path, k=None, lower_count=None, src_sig=None):
+    """the registered dump, or None when it was made with other parameters / from a file that changed since"""
+    v = _DUMPS.get(_key(path))
+    if v is None:
+        return None
+    dump, k0, lc0, sig0 = v
+    if k is not None and k0 is not None and int(k) != int(k0):
+        return None
+    if lower_count is not None and lc0 is not None and int(lower_count) != int(lc0):
+        return None
+    if src_sig is not None and sig0 is not None and tuple(src_sig) != tuple(sig0):
+        return None
+    return dump
 
 
 def put_matrix(path, dm):

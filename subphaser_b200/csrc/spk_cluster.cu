@@ -10,6 +10,7 @@
 // so one streaming pass over Z (8 n M bytes, the HBM roofline of this stage) replaces every Lloyd
 // iteration's pass, and the 1000 bootstrap replicates become 1000 tiny Gram problems.
 #include <math.h>
+#include <stdlib.h>
 #include "spk_common.cuh"
 
 namespace {
@@ -425,7 +426,7 @@ __device__ double betainc_xy(double a, double b, double x, double y) {
 __global__ void __launch_bounds__(128)
 k_ttest_groups(const double* __restrict__ X, uint64_t M, int n, const int32_t* __restrict__ col_group,
                int S, int32_t* __restrict__ best, double* __restrict__ pval,
-               double* __restrict__ means) {
+               double* __restrict__ means, int singleton_nan) {
     double vals[CL_MAX_N];   // values regrouped: group g occupies [off[g], off[g+1])
     int off[CL_MAX_S + 1];
     for (uint64_t m = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M;
@@ -473,8 +474,10 @@ k_ttest_groups(const double* __restrict__ X, uint64_t M, int n, const int32_t* _
             d[i] = t * t;
         }
         double v2 = (np_pairwise(d, n2) / (double)n2) * ((double)n2 / (double)(n2 - 1));
-        if (n1 == 1) v1 = 0.0;
-        if (n2 == 1) v2 = 0.0;
+        // one observation in a group: scipy 1.7.1 (the reference's pin) propagates the NaN variance to the p-value — and
+        // the reference KEEPS NaN p-values (Cluster.py:167); scipy >= 1.9 uses variance 0 (SPK_TTEST_SINGLETON=zero)
+        if (n1 == 1) v1 = singleton_nan ? NAN : 0.0;
+        if (n2 == 1) v2 = singleton_nan ? NAN : 0.0;
         const double df = (double)n1 + (double)n2 - 2.0;
         const double svar = ((double)(n1 - 1) * v1 + (double)(n2 - 1) * v2) / df;
         const double denom = sqrt(svar * (1.0 / (double)n1 + 1.0 / (double)n2));
@@ -849,8 +852,10 @@ extern "C" int spk_ttest_groups(const double* d_X, uint64_t M, int n, const int3
     SPK_CHECK_ARG(n >= 2 && n <= CL_MAX_N && S >= 2 && S <= CL_MAX_S, "bad shape");
     if (M == 0) return SPK_OK;
     SPK_CHECK_ARG(d_X && d_col_group && d_best && d_pval && d_means, "null pointer");
+    const char* sm = getenv("SPK_TTEST_SINGLETON");
+    const int singleton_nan = (sm && sm[0] == 'z') ? 0 : 1;
     k_ttest_groups<<<row_grid(M, 128), 128, 0, (cudaStream_t)stream>>>(d_X, M, n, d_col_group, S, d_best,
-                                                                      d_pval, d_means);
+                                                                      d_pval, d_means, singleton_nan);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

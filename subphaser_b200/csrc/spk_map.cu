@@ -173,7 +173,7 @@ k_map_bins(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ valid
                     const uint64_t rel = line - line0;
                     if (rel < MP_SMEM_LINES) atomicAdd(&s_cnt[rel * MP_MAX_S + sg], 1u);
                     else if (line < a.n_lines) atomicAdd(&a.line_counts[line * a.S + sg], 1u);
-                    if (a.hit_flags && !a.hit_flags[sl]) a.hit_flags[sl] = 1;
+                    if (a.hit_flags && !a.hit_flags[sl]) a.hit_flags[sl] = 1;      // (orientation not tracked on this path)
                     n_hit++;
                 }
             }
@@ -393,7 +393,8 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
         while (rare) {
             const int j = __ffs(rare) - 1;
             rare &= rare - 1;
-            const uint64_t kj = spk_kmer_at(sm.packed[buf], tid * SPK_KMERS_PER_THREAD + j, kp);
+            bool as_read;
+            const uint64_t kj = spk_kmer_at(sm.packed[buf], tid * SPK_KMERS_PER_THREAD + j, kp, &as_read);
             const uint64_t h = qa.mx.fwd_light(kj);
             const uint64_t b = (qa.mx.rbits >= 64) ? 0ull : (h >> qa.mx.rbits);
             uint64_t where = 0;
@@ -414,7 +415,13 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
                     sgp[j >> 3] |= (uint64_t)sg << (8 * (j & 7));
                 }
             }
-            if (sg >= 0 && a.hit_flags && !a.hit_flags[where]) a.hit_flags[where] = 1;
+            // bit 0: seen as stored (canonical orientation), bit 1: seen as its reverse complement — the reference's
+            // set of mapped k-mer STRINGS (Seqs.py:109,114-117) holds the two orientations separately
+            if (sg >= 0 && a.hit_flags) {
+                const uint8_t bit = as_read ? 1 : 2;
+                if (!(a.hit_flags[where] & bit)) atomicOr((unsigned int*)(a.hit_flags + (where & ~3ull)),
+                                                          (unsigned int)bit << (8 * (where & 3)));
+            }
         }
         n_hit += __popc(hm);
 

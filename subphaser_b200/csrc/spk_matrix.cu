@@ -305,3 +305,110 @@ extern "C" int spk_filter_emit(const uint32_t* d_matrix, const uint64_t* d_tot, 
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }
+
+// ---- histogram of the totals of all fold-passing k-mers (the `.kmer_freq.pdf` data, Jellyfish.py:499-511,650-666) --------
+// The reference collects `tot` of every k-mer that passes the fold test into a Python list and hands it to
+// matplotlib (bins of 25 occurrences, x axis cut at the 99th percentile).  Here the totals never leave the device:
+// one pass for count / min / max, one pass that bins them with numpy's `histogram` edge rules, and a radix select
+// (16 bits per pass) for the order statistics np.percentile interpolates between.
+namespace {
+
+__global__ void __launch_bounds__(256)
+k_tot_minmax(const uint64_t* __restrict__ tot, const uint8_t* __restrict__ flags, uint64_t n,
+             unsigned long long* __restrict__ out /* [0] count, [1] min, [2] max */) {
+    unsigned long long cnt = 0, mn = ~0ull, mx = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (flags[i] & 1) {
+            const unsigned long long v = tot[i];
+            cnt++;
+            mn = min(mn, v);
+            mx = max(mx, v);
+        }
+    cnt = spk_warp_sum_u64(cnt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, (unsigned long long)__shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, (unsigned long long)__shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicAdd(&out[0], cnt);
+        atomicMin(&out[1], mn);
+        atomicMax(&out[2], mx);
+    }
+}
+
+// numpy.histogram(data, bins=nbins) with range (mn, mx): uniform edges e_i = mn + i * (mx - mn) / nbins (last = mx),
+// index = int((x - mn) / (mx - mn) * nbins) corrected against the edges, the last bin closed on the right
+__global__ void __launch_bounds__(256)
+k_tot_hist(const uint64_t* __restrict__ tot, const uint8_t* __restrict__ flags, uint64_t n, double mn, double mx,
+           uint32_t nbins, unsigned long long* __restrict__ hist) {
+    const double step = (mx - mn) / (double)nbins;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(flags[i] & 1)) continue;
+        const double x = (double)tot[i];
+        uint32_t b = 0;
+        if (mx > mn) {
+            long long f = (long long)(((x - mn) / (mx - mn)) * (double)nbins);     // numpy's order of operations
+            if (f >= (long long)nbins) f = nbins - 1;
+            b = (uint32_t)f;
+            const double lo = (b == nbins) ? mx : mn + (double)b * step;
+            const double hi = (b + 1 == nbins) ? mx : mn + (double)(b + 1) * step;
+            if (x < lo && b > 0) b--;
+            else if (x >= hi && b + 1 != nbins) b++;
+        }
+        atomicAdd(&hist[b], 1ull);
+    }
+}
+
+// radix select pass: 65536-bin histogram of bits [shift, shift + 16) of the values whose higher bits equal `prefix`
+__global__ void __launch_bounds__(256)
+k_tot_select(const uint64_t* __restrict__ tot, const uint8_t* __restrict__ flags, uint64_t n, int shift, uint64_t prefix,
+             unsigned long long* __restrict__ hist) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!(flags[i] & 1)) continue;
+        const uint64_t v = tot[i];
+        if (shift + 16 < 64 && (v >> (shift + 16)) != prefix) continue;
+        atomicAdd(&hist[(v >> shift) & 0xffffu], 1ull);
+    }
+}
+
+}  // namespace
+
+extern "C" int spk_tot_minmax(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, uint64_t* d_out, void* stream) {
+    SPK_CHECK_ARG(d_out, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t init[3] = {0ull, ~0ull, 0ull};
+    SPK_CUDA(cudaMemcpyAsync(d_out, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_tot && d_flags, "null pointer");
+    k_tot_minmax<<<(unsigned)min((n + 255) / 256, (uint64_t)spk_num_sms() * 16), 256, 0, st>>>(d_tot, d_flags, n,
+                                                                                                (unsigned long long*)d_out);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_tot_histogram(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, double mn, double mx,
+                                 uint32_t nbins, uint64_t* d_hist, void* stream) {
+    SPK_CHECK_ARG(d_hist && nbins >= 1, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPK_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)nbins * 8, st));
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_tot && d_flags, "null pointer");
+    k_tot_hist<<<(unsigned)min((n + 255) / 256, (uint64_t)spk_num_sms() * 16), 256, 0, st>>>(d_tot, d_flags, n, mn, mx, nbins,
+                                                                                              (unsigned long long*)d_hist);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}
+
+extern "C" int spk_tot_select_pass(const uint64_t* d_tot, const uint8_t* d_flags, uint64_t n, int shift, uint64_t prefix,
+                                   uint64_t* d_hist65536, void* stream) {
+    SPK_CHECK_ARG(d_hist65536 && shift >= 0 && shift <= 48 && shift % 16 == 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPK_CUDA(cudaMemsetAsync(d_hist65536, 0, 65536 * 8, st));
+    if (n == 0) return SPK_OK;
+    SPK_CHECK_ARG(d_tot && d_flags, "null pointer");
+    k_tot_select<<<(unsigned)min((n + 255) / 256, (uint64_t)spk_num_sms() * 16), 256, 0, st>>>(d_tot, d_flags, n, shift, prefix,
+                                                                                                (unsigned long long*)d_hist65536);
+    SPK_LAUNCH_CHECK();
+    return SPK_OK;
+}

@@ -122,13 +122,16 @@ __device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_
 
 // Canonical k-mer starting at base `o` of a tile (shared-memory words `pk`), for out-of-line paths that need
 // ONE k-mer of the thread's 16 again (cheaper than keeping all 16 addressable in local memory).
-__device__ __forceinline__ uint64_t spk_kmer_at(const uint32_t* pk, int o, const SpkKmerParams& p) {
+// `as_read` (optional): the k-mer as it stands in the sequence is the canonical one (or a palindrome)
+__device__ __forceinline__ uint64_t spk_kmer_at(const uint32_t* pk, int o, const SpkKmerParams& p,
+                                                bool* as_read = nullptr) {
     const int w = o >> 4, sh = 2 * (o & 15);
     const uint32_t w0 = pk[w], w1 = pk[w + 1], w2 = pk[w + 2];
     const uint64_t lo = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);   // 32 bases from o
     const uint64_t le = lo & p.kmask;
     const uint64_t rc = (~lo) & p.kmask;
     const uint64_t fwd = spk_rev2(le) >> (64 - 2 * p.k);
+    if (as_read) *as_read = fwd <= rc;
     return fwd < rc ? fwd : rc;
 }
 

@@ -289,6 +289,56 @@ class DiffMatrix:
         return int(self.keys.numel())
 
 
+class FoldHistogram:
+    """What `plot_histogram(tot_freqs, ...)` (Jellyfish.py:511,650-666) needs of the totals of all fold-passing k-mers —
+    matplotlib's histogram with bins of `step` occurrences and the 99th percentile that limits the x axis — computed on
+    the device from the filter's outputs; the list of totals (10^8 entries for wheat) is never copied to the host."""
+
+    def __init__(self, tot, flags, U, step=25, xlim=99):
+        lib = _lib.load()
+        st = _stream()
+        self._tot, self._flags, self._U = tot, flags, int(U)
+        mm = _zeros(3, torch.int64)
+        call("spk_tot_minmax", _p(tot), _p(flags), self._U, _p(mm), st)
+        self.n, mn, mx = (int(x) for x in mm.cpu().numpy().view(np.uint64).tolist())
+        self.step, self.xlim_pct = step, xlim
+        if self.n == 0:
+            self.min = self.max = 0
+            self.nbins, self.hist, self.edges, self.xlim = 0, np.zeros(0, np.int64), np.zeros(1), 0.0
+            return
+        self.min, self.max = mn, mx
+        self.nbins = max(int((mx - 0) / step), 1)               # `nbins = int((_max-_min)/step)` with _min = 0 (:653-654)
+        hist = _zeros(self.nbins, torch.int64)
+        call("spk_tot_histogram", _p(tot), _p(flags), self._U, float(mn), float(mx), self.nbins, _p(hist), st)
+        self.hist = hist.cpu().numpy()
+        self.edges = np.linspace(float(mn), float(mx), self.nbins + 1)
+        self.xlim = self.percentile(xlim)
+
+    def _order_stat(self, rank):
+        """rank-th smallest total (0-based): radix select, 16 bits per device pass"""
+        prefix, hist = 0, _zeros(65536, torch.int64)
+        for shift in (48, 32, 16, 0):
+            if (self.max >> shift) == 0 and shift:
+                continue                                         # every value is zero in these bits
+            call("spk_tot_select_pass", _p(self._tot), _p(self._flags), self._U, shift, prefix, _p(hist), _stream())
+            h = hist.cpu().numpy()
+            c = np.cumsum(h)
+            b = int(np.searchsorted(c, rank, side="right"))
+            rank -= int(c[b - 1]) if b else 0
+            prefix = (prefix << 16) | b
+        return prefix
+
+    def percentile(self, q):
+        """np.percentile(data, q) ('linear'): interpolation between two order statistics, numpy's _lerp arithmetic."""
+        pos = (q / 100.0) * (self.n - 1)
+        lo = int(np.floor(pos))
+        t = pos - lo
+        a = float(self._order_stat(lo))
+        b = float(self._order_stat(min(lo + 1, self.n - 1)))
+        d = b - a
+        return float(b - d * (1 - t)) if t >= 0.5 else float(a + d * t)
+
+
 def flatten_sgs(sgs, labels):
     """sgs (list of sets -> list of groups -> list of labels) -> CSR int32 arrays of column indices."""
     col = {lab: i for i, lab in enumerate(labels)}
@@ -335,7 +385,7 @@ def filter_matrix(cm, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200
     call("spk_filter_emit", _p(cm.matrix), _p(tot), _p(rows), n_keep, n, _p(d_len), _p(norm), _p(otot), st)
     fold_tots = None
     if want_fold_tots and U:
-        fold_tots = tot[:U][(flags[:U] & 1).bool()].cpu().numpy()
+        fold_tots = FoldHistogram(tot, flags, U)          # histogram on the device; the totals stay there
     return DiffMatrix(keys, norm, otot, cm.k, labels, n_fold, fold_tots)
 
 
@@ -381,7 +431,7 @@ class LazyUnion:
 
 
 def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq=200, max_freq=10000,
-                   by_count=False, want_fold_tots=False, nparts=1, part=0, lengths=None):
+                   by_count=False, want_fold_tots=False, nparts=1, part=0, lengths=None, full_dumps=None):
     """to_matrix + filter in one partition-by-partition pass (spk_pmatrix_filter) -> (DiffMatrix, n_union).
     Rows come back sorted by k-mer, normalised by `lengths` exactly like filter_matrix."""
     require_cuda()
@@ -396,6 +446,14 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
                          [d.pindex.data_ptr() for d in dumps]], dtype=torch.int64).to(_dev())
     counters = _zeros(8, torch.int64)
     total = sum(len(d) for d in dumps)
+    # entries that fall into THIS rank's partitions (full_dumps: which dumps hold all partitions — the rank's own
+    # chromosomes — as opposed to the class slices received from other ranks); the kernel sizes its shared-memory
+    # table for the mean entries per partition, total_entries / 2^pbits
+    if nparts > 1 and full_dumps is not None:
+        mine = sum((len(d) // nparts) if f else len(d) for d, f in zip(dumps, full_dumps))
+        table_total = mine * nparts
+    else:
+        table_total = total
     # candidates are a few % of the union; grown on demand.  (On several ranks `total` counts the foreign dumps by
     # their partition class only, so the share per rank is estimated more generously.)
     cap = max(total // (16 * nparts) if nparts == 1 else total // (4 * nparts), 1 << 16)
@@ -406,7 +464,7 @@ def pmatrix_filter(dumps, sgs, labels, min_fold=2, baseline=1, ratio=1, min_freq
         call("spk_pmatrix_filter", _p(ptrs[0]), _p(ptrs[1]), _p(ptrs[2]), n, pbits, nparts, part, _p(d_len),
              _p(d_set), len(set_off) - 1, _p(d_grp), len(grp_off) - 1, _p(d_mem), len(members), float(min_fold),
              int(baseline), int(bool(by_count)), float(ratio), float(min_freq), float(max_freq), _p(okeys), _p(ocnt),
-             cap, total, _p(counters), st)
+             cap, table_total, _p(counters), st)
         n_union, _, n_cand, n_over = (int(x) for x in counters[:4].cpu().tolist())
         if n_over or os.environ.get("SPK_PMATRIX_FORCE_OVERFLOW") == "1":
             raise OverflowError("partition table overflow in spk_pmatrix_filter")
@@ -679,10 +737,15 @@ class SigTable:
             nflags = self.slots
         if int(fail.item()):
             raise OverflowError("specific k-mer table full")
-        self.hit_flags = _zeros(nflags, torch.uint8) if track_hits else None
+        self.hit_flags = _zeros((nflags + 3) // 4 * 4, torch.uint8) if track_hits else None
 
     def n_mapped(self):
-        return int(self.hit_flags.sum().item()) if self.hit_flags is not None else 0
+        """number of distinct k-mer strings seen in the mapped sequences, both orientations counted separately (what
+        `len(mapped_cat)` is in Seqs.py:113); the plain open-addressed layout only knows the canonical hits"""
+        if self.hit_flags is None:
+            return 0
+        f = self.hit_flags
+        return int(((f & 1) != 0).sum().item() + ((f & 2) != 0).sum().item())
 
 
 def map_bins(seq, sig, S, bin_size, chunk_size, record_lengths=None):

