@@ -644,8 +644,18 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     if nsg is None:
         nsg = max(len(sg) for sg in sgs)
     e = t.start("cluster")
-    Z = engine.zscore_rows(dm.norm)
-    G = engine.gram(Z)
+    if world > 1:
+        # every rank holds the whole matrix here; the Gram pass (one stream over all rows) is split by rows and the
+        # n x n partial sums are all-reduced — the full z-scored matrix the bootstrap gathers from is produced on the
+        # side stream, off the critical path
+        per = (M + world - 1) // world
+        lo, hi = min(rank * per, M), min((rank + 1) * per, M)
+        G = engine.gram(engine.zscore_rows(dm.norm[lo:hi])) if hi > lo else torch.zeros(n, n, dtype=torch.float64, device=dev)
+        dist.all_reduce(G)
+        Z = None
+    else:
+        Z = engine.zscore_rows(dm.norm)
+        G = engine.gram(Z)
     order = [i for _, i in sorted(zip(labels, range(n)))]
     lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
     lab_full_h = lab_full[0].cpu().numpy()
@@ -659,6 +669,8 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     lab_b = ari = vm = None
     with torch.cuda.stream(side):
         e_side = t.start("bootstrap_pca_side")
+        if Z is None and R > 0:
+            Z = engine.zscore_rows(dm.norm)
         if R > 0:
             d_idx = engine.resample_indices(M, R, seed)        # same generator state on every rank: same plan
             if world > 1:

@@ -26,12 +26,17 @@ CONFIGS = {
     # synthetic hexaploid, 21 x 2.38 Gb (chromosomes longer than 2^31 bp), k=21, 100-kb windows
     "C5": dict(sg="ABD", lengths=[2_380_000_000] * 21, k=21, window=100_000),
 }
-CONFIGS["C1"]["lengths"] = [int(x) for x in np.linspace(14e6, 26e6, 13)] + [20_000_000]   # 14 chr, 2 SG
+# C1: the layout of example_data/Arabidopsis_suecica_sg.config — 13 chromosomes renamed 1..13, subgenome A = 1-5,
+# subgenome B = 6-13, three homoeologous sets whose groups hold one to three chromosomes each
+CONFIGS["C1"]["lengths"] = [int(x) for x in np.linspace(14e6, 26e6, 13)]
+CONFIGS["C1"]["names"] = [str(i) for i in range(1, 14)]
+CONFIGS["C1"]["sg_of"] = [0] * 5 + [1] * 8
+CONFIGS["C1"]["sgs"] = [[["1"], ["6", "7"]], [["2", "3"], ["9", "8", "10"]], [["4", "5"], ["13", "11", "12"]]]
 
 
 class GenomePlan:
     def __init__(self, seed, sg_letters, lengths, n_fam=200, n_shared=100, fam_len=(2000, 10000),
-                 te_frac=0.7, div=0.03, soft_frac=0.3, own_frac=0.85, n_per_mb=1.0):
+                 te_frac=0.7, div=0.03, soft_frac=0.3, own_frac=0.85, n_per_mb=1.0, names=None, sg_of=None, sgs=None):
         self.seed = int(seed)
         rng = np.random.default_rng(seed)
         self.sg_letters = list(sg_letters)
@@ -57,13 +62,19 @@ class GenomePlan:
         self.chroms = []
         per = n // S
         for i, L in enumerate(lengths):
+            if names is not None:      # explicit layout (multi-chromosome groups, uneven subgenomes)
+                self.chroms.append(dict(name=names[i], sg=int(sg_of[i]), length=int(L), index=i))
+                continue
             c, s = divmod(i, S) if n % S == 0 else (i // S, i % S)
             self.chroms.append(dict(name="%d%s" % (c + 1, self.sg_letters[s]), sg=s, length=int(L), index=i))
         self.labels = [c["name"] for c in self.chroms]
-        sets = {}
-        for c in self.chroms:
-            sets.setdefault(c["name"][:-1], []).append([c["name"]])
-        self.sgs = [v for v in sets.values()]
+        if sgs is not None:
+            self.sgs = [[list(g) for g in row] for row in sgs]
+        else:
+            sets = {}
+            for c in self.chroms:
+                sets.setdefault(c["name"][:-1], []).append([c["name"]])
+            self.sgs = [v for v in sets.values()]
 
     def segments(self, chrom):
         """Segment table of one chromosome: (seg_start u64, seg_src i64 (-1 = background), seg_seed u32,
@@ -204,10 +215,10 @@ def plan_for(config, seed=None, scale=1.0):
     cfg = CONFIGS[config]
     seeds = {"C1": 101, "C2": 202, "C3": 303, "C4": 303, "C5": 505}
     lengths = [max(int(L * scale), 1000) for L in cfg["lengths"]]
-    if config == "C1":
-        lengths = lengths[:14]
-    # the repeat library shrinks with the genome so that copy numbers per family stay wheat-like
-    n_fam = max(int(round(200 * scale)), 4)
-    n_shared = max(int(round(100 * scale)), 2)
+    # the repeat library is sized for the genome (200 + 100 families per 14.2 Gb) so that copy numbers per family stay
+    # wheat-like whatever the configuration or scale: the default thresholds (min_freq 200) then select k-mers
+    g = float(sum(lengths))
+    n_fam = max(int(round(200 * g / 14.2e9)), 4)
+    n_shared = max(int(round(100 * g / 14.2e9)), 2)
     return GenomePlan(seeds[config] if seed is None else seed, cfg["sg"], lengths, n_fam=n_fam,
-                      n_shared=n_shared), cfg
+                      n_shared=n_shared, names=cfg.get("names"), sg_of=cfg.get("sg_of"), sgs=cfg.get("sgs")), cfg

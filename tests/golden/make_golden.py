@@ -354,13 +354,42 @@ def gen_ranktest_units(C):
     jdump(cases, "ranktest_rows.json")
 
 
-def gen_pipeline(J, C, Seqs, Circos, S_mod):
-    """The reference's step sequence (__main__.py:403-498) on a tiny 2x3-chromosome genome."""
+def arab_genome(seed):
+    """13 chromosomes laid out like example_data/Arabidopsis_suecica_sg.config: ids 1..13, subgenome A = 1-5,
+    subgenome B = 6-13, homoeologous sets whose groups hold one to three chromosomes."""
+    rng = np.random.default_rng(seed)
+    fam = {sg: [util.random_seq(rng, 400) for _ in range(6)] for sg in "AB"}
+    shared = [util.random_seq(rng, 400) for _ in range(3)]
+    records = []
+    for i in range(13):
+        sg = "A" if i < 5 else "B"
+        L = int(26000 * (0.8 + 0.5 * rng.random()))
+        seq = np.array(list(util.random_seq(rng, L)))
+        covered = 0
+        while covered < 0.7 * L:
+            f = fam[sg][int(rng.integers(0, 6))] if rng.random() < 0.9 else shared[int(rng.integers(0, 3))]
+            copy_ = np.array(list(f))
+            mut = rng.random(len(copy_)) < 0.03
+            copy_[mut] = np.array(list("ACGT"))[rng.integers(0, 4, int(mut.sum()))]
+            pos = int(rng.integers(0, L - len(copy_)))
+            seq[pos:pos + len(copy_)] = copy_
+            covered += len(copy_)
+        p = int(rng.integers(0, L - 200))
+        seq[p:p + int(rng.integers(10, 100))] = "N"
+        records.append((str(i + 1), "".join(seq)))
+    sgs = [[["1"], ["6", "7"]], [["2", "3"], ["9", "8", "10"]], [["4", "5"], ["13", "11", "12"]]]
+    return records, sgs
+
+
+def gen_pipeline(J, C, Seqs, Circos, S_mod, fixture="pipeline_small", genome=None):
+    """The reference's step sequence (__main__.py:403-498) on a tiny genome: 2x3 chromosomes (pipeline_small) or the
+    Arabidopsis-like layout with multi-chromosome groups and uneven subgenomes (pipeline_arab)."""
     import sklearn.cluster
-    out = os.path.join(HERE, "pipeline_small")
+    out = os.path.join(HERE, fixture)
     shutil.rmtree(out, ignore_errors=True)
     os.makedirs(out)
-    records, sgs = util.subgenome_genome(7, n_sg=2, chr_per_sg=3, chr_len=30000, n_fam=6, fam_len=400)
+    records, sgs = genome if genome is not None else util.subgenome_genome(7, n_sg=2, chr_per_sg=3, chr_len=30000,
+                                                                           n_fam=6, fam_len=400)
     labels = [name for name, _ in records]
     chromfiles = []
     for name, seq in records:
@@ -432,7 +461,7 @@ def gen_pipeline(J, C, Seqs, Circos, S_mod):
         json.dump(meta, f)
     np.savez_compressed(os.path.join(out, "resample_idx.npz"), idx=np.array(recorded, dtype=np.int32))
     shutil.rmtree(tmp)
-    print("wrote pipeline_small/: union", n_union, "diff", len(d_mat2), "sig", len(d_kmers) // 2, "d_sg", dict(cluster.d_sg))
+    print("wrote", fixture, ": union", n_union, "diff", len(d_mat2), "sig", len(d_kmers) // 2, "d_sg", dict(cluster.d_sg))
 
 
 def main(only=None):
@@ -455,6 +484,7 @@ def main(only=None):
     gen_cluster_units(C)
     gen_ranktest_units(C)
     gen_pipeline(J, C, Seqs, Circos, S_mod)
+    gen_pipeline(J, C, Seqs, Circos, S_mod, fixture="pipeline_arab", genome=arab_genome(13))
 
 
 if __name__ == "__main__":

@@ -68,7 +68,11 @@ def small_dumps(tmp_path_factory):
             f.write(util.fasta([(name, seq)]))
         files.append(p)
     labels = [n for n, _ in records]
-    dumpfiles = Jellyfish.run_jellyfish_dumps(files, k=13, ncpu=1, lower_count=2, threads=1, overwrite=True)
+    os.environ["SPK_DUMP_SIDECAR"] = "1"        # other tests clear the in-process registry: keep the dumps loadable
+    try:
+        dumpfiles = Jellyfish.run_jellyfish_dumps(files, k=13, ncpu=1, lower_count=2, threads=1, overwrite=True)
+    finally:
+        del os.environ["SPK_DUMP_SIDECAR"]
     return files, labels, sgs, dumpfiles
 
 

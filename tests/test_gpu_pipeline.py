@@ -9,12 +9,16 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
-G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pipeline_small")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.fixture(scope="module")
-def run(tmp_path_factory):
-    from subphaser_b200 import pipeline
+# pipeline_small: 2 x 3 chromosomes, single-chromosome groups; pipeline_arab: the layout of
+# example_data/Arabidopsis_suecica_sg.config (13 chromosomes, 5 + 8 per subgenome, groups of one to three chromosomes)
+@pytest.fixture(scope="module", params=["pipeline_small", "pipeline_arab"])
+def run(request, tmp_path_factory):
+    from subphaser_b200 import _registry, pipeline
+    G = os.path.join(GOLDEN, request.param)
+    _registry.clear()
     meta = json.load(open(os.path.join(G, "meta.json")))
     work = tmp_path_factory.mktemp("pipe")
     chromfiles = []
@@ -29,7 +33,7 @@ def run(tmp_path_factory):
                                 replicates=meta["replicates"], bin_size=meta["bin_size"],
                                 map_window=meta["map_window"], window_size=meta["enrich_window"],
                                 resample_idx=idx, seed=0)
-    return meta, res
+    return G, meta, res
 
 
 def _rows(path):
@@ -37,7 +41,7 @@ def _rows(path):
 
 
 def test_counts_and_matrix(run):
-    meta, res = run
+    G, meta, res = run
     assert res["lengths"] == meta["lengths"]
     assert res["kmer_count"] == meta["n_union"]
     assert res["n_diff"] == meta["n_diff"]
@@ -49,7 +53,7 @@ def test_counts_and_matrix(run):
 
 
 def test_cluster_assignment_and_bootstrap(run):
-    meta, res = run
+    G, meta, res = run
     assert dict(res["d_sg"]) == meta["d_sg"]
     assert [int(x) for x in res["cluster"].labels] == meta["labels_full"]
     assert res["cluster"].d_bs == meta["d_bs"]
@@ -61,7 +65,7 @@ def test_cluster_assignment_and_bootstrap(run):
 
 
 def test_centroids_and_pca(run):
-    meta, res = run
+    G, meta, res = run
     c = res["cluster"]
     # rows of the fixture follow sklearn's cluster numbering; match clusters through the labels
     ref_lab, my_lab = meta["centers_labels"], list(c.kmean.labels_)
@@ -82,7 +86,7 @@ def test_centroids_and_pca(run):
 
 
 def test_specific_kmers(run):
-    meta, res = run
+    G, meta, res = run
     assert len(res["d_kmers"]) == meta["n_sig"]
     ref = {r[0]: r for r in _rows(os.path.join(G, "ref.sig.kmer-subgenome.tsv"))[1:]}
     got = {r[0]: r for r in _rows(res["para_prefix"] + ".sig.kmer-subgenome.tsv")[1:]}
@@ -106,13 +110,13 @@ def test_specific_kmers(run):
 
 
 def test_bin_count_file_identical(run):
-    meta, res = run
+    G, meta, res = run
     ref = open(os.path.join(G, "ref.subgenome.bin.count")).read()
     assert open(res["para_prefix"] + ".subgenome.bin.count").read() == ref
 
 
 def test_enrichment_files(run):
-    meta, res = run
+    G, meta, res = run
     ref = _rows(os.path.join(G, "ref.bin.enrich"))
     got = _rows(res["para_prefix"] + ".bin.enrich")
     assert len(ref) == len(got) and got[0] == ref[0]

@@ -24,8 +24,9 @@ for row in csv.DictReader(io.StringIO("".join(lines))):
 for name in agg:
     agg[name]["n"] = len(ids[name])
 tot = sum(a["ms"] for n, a in agg.items() if not n.startswith("k_synth"))
-fam = ["k_hist1", "k_scatter_l1", "k_scatter_l2", "k_part_count32", "k_scan_seg_totals", "k_scan_segs", "k_scan_apply",
-       "k_scatter_prepare", "k_bucket_scan"]
+fam = ["k_v3_l1", "k_v3_plan", "k_v3_chunks", "k_v3_l2", "k_part_count32<1>", "k_part_count32<0>", "k_part_count32",
+       "k_hist1", "k_scatter_l1", "k_scatter_l2", "k_scan_seg_totals", "k_scan_segs", "k_scan_apply", "k_scatter_prepare",
+       "k_bucket_scan"]
 with open(out_md, "w") as f:
     f.write("| kernel | launches | total ms | share of the step (input synthesis excluded) | DRAM read GB | DRAM write GB |\n|---|---|---|---|---|---|\n")
     for name, a in sorted(agg.items(), key=lambda x: -x[1]["ms"]):
@@ -34,7 +35,7 @@ with open(out_md, "w") as f:
         share = "-" if name.startswith("k_synth") else "%.1f%%" % (100 * a["ms"] / tot)
         f.write("| `%s` | %d | %.2f | %s | %.2f | %.2f |\n" % (name[:60], a["n"], a["ms"], share, a["rd"] / 1e9, a["wr"] / 1e9))
     f.write("\nlisted kernel time without input synthesis: %.1f ms\n" % tot)
-calls = agg["k_part_count32"]["n"]
+calls = max(agg[k]["n"] for k in ("k_part_count32<1>", "k_part_count32<0>", "k_part_count32") if k in agg)
 dram = sum(agg[k]["rd"] + agg[k]["wr"] for k in fam if k in agg)
 ms = sum(agg[k]["ms"] for k in fam if k in agg)
 json.dump({"kernel_family": "spk_pcount_canonical_ex (" + ", ".join(k for k in fam if k in agg) + ")",
