@@ -356,6 +356,98 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
         uint32_t okmask;
         spk_tile_kmers(sm, buf, kp, key, okmask);
 
+        // ---- fast path (16-bit slots, the warp's 512 positions fall on one line, no per-entry hit flags wanted) ----
+        // The 8 slots of a bucket are matched with SWAR arithmetic on the four 32-bit words of the 16-byte load (a slot
+        // matches iff (slot ^ q) has no bit above the subgenome field: a zero-halfword test on the masked words), and a
+        // hit goes straight into four packed 16-bit counters — no per-position hit masks, no slot-by-slot compares.
+        // Only hits (and the rare bucket that overflowed into the stash) leave the straight-line code.
+        if constexpr (S16) {
+            const bool one_line_f = (brem + SPK_KMERS_PER_THREAD <= a.bin_size) &&
+                                    (!a.chunk_size || crem + SPK_KMERS_PER_THREAD <= a.chunk_size);
+            const uint64_t line_f = bin + chk;
+            const uint32_t lo_f = (uint32_t)line_f, hi_f = (uint32_t)(line_f >> 32);
+            const uint32_t lo_0 = __shfl_sync(0xffffffffu, lo_f, 0), hi_0 = __shfl_sync(0xffffffffu, hi_f, 0);
+            const bool fast = __all_sync(0xffffffffu, one_line_f && lo_f == lo_0 && hi_f == hi_0) && S <= 4 &&
+                              !a.rec_start && !a.hit_flags;
+            if (fast) {
+                const uint32_t hmask = (0xffffu << qa.sgbits) & 0xffffu;
+                const uint32_t HM = hmask * 0x10001u;                   // bits above the subgenome field, both halfwords
+                uint32_t c01 = 0, c23 = 0, rare = 0;
+                constexpr int QB = 4;
+#pragma unroll
+                for (int j0 = 0; j0 < SPK_KMERS_PER_THREAD; j0 += QB) {
+                    uint4 bv[QB];
+                    uint32_t qq[QB];
+#pragma unroll
+                    for (int jj = 0; jj < QB; jj++) {
+                        const int j = j0 + jj;
+                        const uint64_t h = qa.mx.fwd_light(key[j]);
+                        qq[jj] = (uint32_t)((h & rmask) << qa.sgbits) * 0x10001u;
+                        bv[jj] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        if ((okmask >> j) & 1u)
+                            bv[jj] = __ldg(reinterpret_cast<const uint4*>(qa.buckets) + (uint32_t)(h >> qa.mx.rbits));
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < QB; jj++) {
+                        const int j = j0 + jj;
+                        const uint32_t w[4] = {bv[jj].x ^ qq[jj], bv[jj].y ^ qq[jj], bv[jj].z ^ qq[jj], bv[jj].w ^ qq[jj]};
+                        uint32_t z = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t t = w[i] & HM;
+                            const uint32_t zi = ~(((t & 0x7fff7fffu) + 0x7fff7fffu) | t) & 0x80008000u;   // exact zero-halfword flags
+                            z |= (i == 3) ? (zi & 0x8000u) : zi;        // slot 7 (high half of the last word) is the marker
+                        }
+                        const bool okj = (okmask >> j) & 1u;
+                        if (z && okj) {
+                            int sg = -1;
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+                                if (lo < (uint32_t)S) sg = (int)lo;
+                                if (i < 3 && hi < (uint32_t)S) sg = (int)hi;
+                            }
+                            if (sg >= 0) {
+                                const uint32_t inc = 1u << ((sg & 1) * 16);
+                                if (sg & 2) c23 += inc;
+                                else c01 += inc;
+                            } else if ((bv[jj].w >> 16) != 0xffffu) rare |= 1u << j;
+                        } else if (okj && (bv[jj].w >> 16) != 0xffffu) rare |= 1u << j;
+                    }
+                }
+                while (rare) {                                          // bucket overflowed at build time: the key may be in the stash
+                    const int j = __ffs(rare) - 1;
+                    rare &= rare - 1;
+                    const uint64_t kj = spk_kmer_at(sm.packed[buf], tid * SPK_KMERS_PER_THREAD + j, kp);
+                    uint64_t sl = 0;
+                    const int sg = qt_stash_lookup(qa, kj, sl);
+                    if (sg >= 0) {
+                        const uint32_t inc = 1u << ((sg & 1) * 16);
+                        if (sg & 2) c23 += inc;
+                        else c01 += inc;
+                    }
+                }
+                n_hit += (c01 & 0xffffu) + (c01 >> 16) + (c23 & 0xffffu) + (c23 >> 16);
+                c01 = __reduce_add_sync(0xffffffffu, c01);
+                c23 = __reduce_add_sync(0xffffffffu, c23);
+                if ((tid & 31) == 0 && line_f < a.n_lines) {
+                    const uint32_t c[4] = {c01 & 0xffffu, c01 >> 16, c23 & 0xffffu, c23 >> 16};
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; q4++)
+                        if (c[q4] && q4 < S) atomicAdd(&a.line_counts[line_f * a.S + q4], c[q4]);
+                }
+                pos0 += stride;
+                bin += dbin;
+                brem += dbrem;
+                if (brem >= a.bin_size) { brem -= a.bin_size; bin++; }
+                if (a.chunk_size) {
+                    chk += dchk;
+                    crem += dcrem;
+                    if (crem >= a.chunk_size) { crem -= a.chunk_size; chk++; }
+                }
+                continue;
+            }
+        }
         // bucket lookups in batches of QB independent 16/32-byte loads (issued before any is consumed)
         uint32_t hm = 0;              // bit j: position j hit
         uint32_t rare = 0;            // bit j: position j needs the out-of-line path (stash probe / hit flag)

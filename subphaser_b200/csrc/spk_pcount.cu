@@ -1162,13 +1162,46 @@ __device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cn
 // b: run r = [off2[g][sub], off2[g][sub + 1]) of chunk g = cb[b] + r.  Warp w owns the runs w, w + 8, ...; lane l
 // loads the descriptor of run w + 8 l two partitions ahead, the first 32 entries of the warp's first 16 runs are
 // loaded one partition ahead (lane i = entry i of the run), longer / later runs are read when they are inserted.
+// ---- versioned table (VER): no clearing, no sweep ---------------------------------------------------------------
+// A slot is 64 bits: high word = (generation << rbits) | remainder, low word = count.  The CTA bumps its generation
+// for every partition, so a slot written for an earlier partition is simply "free" — the table is never cleared —
+// and the k-mers to dump (count >= lower) are collected WHEN their count reaches `lower` (that add returns lower - 1
+// exactly once per key) in a small slot list, so the 8192-slot sweep that found them is gone too.  Claiming a free
+// slot is one 64-bit CAS that installs key and count = 1 together; a hit is a 32-bit add on the low word.
+// (A count histogram (`-histo`), or more kept keys than the list holds, falls back to scanning the table.)
+constexpr int PC_KEEP = 2048;            // kept-slot list capacity (u16 slot ids)
+constexpr int PC_RETRY_V = 1024;         // retry queue of the versioned kernel
+
+// -> bit 0: created the key, bit 1: table full, bits 16..: slot + 1 when the count reached `lower` there
+__device__ __noinline__ uint32_t pcv_probe_rest(unsigned long long* s_tab, uint32_t r, uint32_t want, uint32_t gen,
+                                                int rbits, uint32_t lower) {
+    constexpr uint32_t TMASK = PC_SLOTS - 1;
+    uint32_t s = ((r & TMASK) + 1) & TMASK;
+    for (uint32_t probes = 1; probes < PC_SLOTS; probes++) {
+        unsigned long long v = s_tab[s];
+        while (true) {
+            const uint32_t hi = (uint32_t)(v >> 32);
+            if (hi == want) {
+                const uint32_t c = atomicAdd((unsigned int*)&s_tab[s], 1u);        // low word (little endian)
+                return (c + 1 == lower) ? ((s + 1) << 16) : 0u;
+            }
+            if ((hi >> rbits) == gen) break;                                       // another key of this partition
+            const unsigned long long old = atomicCAS(&s_tab[s], v, ((unsigned long long)want << 32) | 1ull);
+            if (old == v) return 1u | ((lower == 1) ? ((s + 1) << 16) : 0u);
+            v = old;                                                               // lost the race: look again
+        }
+        s = (s + 1) & TMASK;
+    }
+    return 2u;
+}
+
 struct GatherIn {
     const uint32_t* cb;       // [2^b1 + 1] first chunk of every bucket
     const uint16_t* off2;     // [(2^b2 + 1) per chunk]
     int b2;
 };
 
-template <bool GATHER>
+template <bool GATHER, bool VER>
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
                CountOut o, uint32_t retry_cap, GatherIn gi) {
@@ -1176,6 +1209,9 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     uint32_t* s_key = (uint32_t*)s_raw;
     uint32_t* s_cnt = s_key + PC_SLOTS;
     uint32_t* s_q = s_cnt + PC_SLOTS;                    // [PC_RETRY]; retry_cap <= PC_RETRY entries are used as queue
+    unsigned long long* s_tab = (unsigned long long*)s_raw;           // VER: [PC_SLOTS] 64-bit slots (same bytes)
+    uint16_t* s_keep = (uint16_t*)(s_q + (VER ? PC_RETRY_V : PC_RETRY));   // VER: [PC_KEEP]
+    __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_red[4][PC_THREADS / 32];
     __shared__ uint32_t s_nq, s_nkeep, s_ndist, s_wr;
@@ -1188,7 +1224,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     constexpr uint32_t TMASK = PC_SLOTS - 1;
     constexpr int SWEEP = PC_SLOTS / (PC_THREADS * 4);   // uint4 loads per thread per sweep (8)
     for (uint32_t i = tid; i < PC_SLOTS; i += PC_THREADS) {
-        s_key[i] = PC_EMPTY32;
+        s_key[i] = VER ? 0u : PC_EMPTY32;                 // VER: generation 0 = never used
         s_cnt[i] = 0;
     }
     if (tid == 0) {
@@ -1196,28 +1232,64 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         s_nkeep = 0;
         s_ndist = 0;
         s_wr = 0;
+        s_nlist = 0;
     }
     __syncthreads();
     const uint32_t lower = o.lower;
     uint32_t my_new = 0, my_keep = 0;    // per partition: keys created / counts that reached `lower` by this thread
+    const int rbits = mx.rbits;                                      // VER: <= 31
+    const uint32_t gmax = VER ? ((rbits >= 32) ? 0u : (0xffffffffu >> rbits)) : 0u;
+    uint32_t gen = 1;                                                // VER: generation of the current partition
+    auto keep_slot = [&](uint32_t slot) {                            // VER: this key is dumped: remember where it lives
+        const uint32_t at = atomicAdd(&s_nlist, 1u);
+        if (at < PC_KEEP) s_keep[at] = (uint16_t)slot;
+    };
 
     // first probe only; false: the home slot belongs to another key
     auto try_home = [&](uint32_t r) -> bool {
         const uint32_t s = r & TMASK;                    // r = low bits of the mixer output: already uniform
-        const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
-        if (old == PC_EMPTY32 || old == r) {
-            const uint32_t c = atomicAdd(&s_cnt[s], 1u);
-            my_new += (old == PC_EMPTY32) ? 1u : 0u;
-            my_keep += (c + 1 == lower) ? 1u : 0u;
-            return true;
+        if constexpr (VER) {
+            const uint32_t want = (gen << rbits) | r;
+            unsigned long long v = s_tab[s];
+            while (true) {
+                const uint32_t hi = (uint32_t)(v >> 32);
+                if (hi == want) {
+                    const uint32_t c = atomicAdd((unsigned int*)&s_tab[s], 1u);    // low word = count
+                    if (c + 1 == lower) keep_slot(s);
+                    return true;
+                }
+                if ((hi >> rbits) == gen) return false;                            // another key of this partition
+                const unsigned long long old = atomicCAS(&s_tab[s], v, ((unsigned long long)want << 32) | 1ull);
+                if (old == v) {
+                    my_new++;
+                    if (lower == 1) keep_slot(s);
+                    return true;
+                }
+                v = old;
+            }
+        } else {
+            const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
+            if (old == PC_EMPTY32 || old == r) {
+                const uint32_t c = atomicAdd(&s_cnt[s], 1u);
+                my_new += (old == PC_EMPTY32) ? 1u : 0u;
+                my_keep += (c + 1 == lower) ? 1u : 0u;
+                return true;
+            }
+            return false;
         }
-        return false;
     };
     auto probe_rest = [&](uint32_t r) {
-        const uint32_t f = pc32_probe_rest(s_key, s_cnt, r, lower);
-        my_new += f & 1u;
-        my_keep += (f >> 1) & 1u;
-        n_fail += (f >> 2) & 1u;
+        if constexpr (VER) {
+            const uint32_t f = pcv_probe_rest(s_tab, r, (gen << rbits) | r, gen, rbits, lower);
+            my_new += f & 1u;
+            n_fail += (f >> 1) & 1u;
+            if (f >> 16) keep_slot((f >> 16) - 1);
+        } else {
+            const uint32_t f = pc32_probe_rest(s_key, s_cnt, r, lower);
+            my_new += f & 1u;
+            my_keep += (f >> 1) & 1u;
+            n_fail += (f >> 2) & 1u;
+        }
     };
     auto insert = [&](uint32_t r) {
         if (!try_home(r)) {
@@ -1401,7 +1473,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         my_new = my_keep = 0;
         __syncthreads();
         if (tid == 0) {
-            const uint32_t total = s_nkeep;
+            const uint32_t total = VER ? s_nlist : s_nkeep;
             const uint64_t base = total ? atomicAdd((unsigned long long*)o.cursor, (unsigned long long)total) : 0ull;
             s_base = base;
             if (o.pindex) {
@@ -1412,10 +1484,57 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
             if constexpr (!GATHER) sumall += end - beg;
         }
         __syncthreads();
-        // ---- sweep: histogram, write the dump, clear ----
         const uint64_t pbase = s_base;
+        if constexpr (VER) {
+            // ---- dump from the kept-slot list (no sweep, nothing to clear) ----
+            const uint32_t nl = s_nlist;
+            const uint32_t rmask = (rbits >= 32) ? 0xffffffffu : ((1u << rbits) - 1u);
+            if (nl <= PC_KEEP && !o.histo) {
+                for (uint32_t i = tid; i < nl; i += PC_THREADS) {
+                    const unsigned long long v = s_tab[s_keep[i]];
+                    const uint32_t cnt = (uint32_t)v;
+                    nge++;
+                    sumge += cnt;
+                    if (pbase + i < o.cap) {
+                        o.keys[pbase + i] = mx.inv((p << mx.rbits) | (uint64_t)((uint32_t)(v >> 32) & rmask));
+                        o.counts[pbase + i] = cnt;
+                    }
+                }
+            } else {
+                // histogram wanted, or more kept keys than the list holds: scan the slots of this generation
+                for (uint32_t sl = tid; sl < PC_SLOTS; sl += PC_THREADS) {
+                    const unsigned long long v = s_tab[sl];
+                    const uint32_t hi = (uint32_t)(v >> 32), cnt = (uint32_t)v;
+                    if ((hi >> rbits) != gen) continue;
+                    if (o.histo) {
+                        const uint32_t b = cnt < o.histo_len - 1 ? cnt : o.histo_len - 1;
+                        if (b == 1) h1++;
+                        else if (b == 2) h2++;
+                        else if (b < 256) atomicAdd(&s_hist[b], 1u);
+                        else atomicAdd((unsigned long long*)&o.histo[b], 1ull);
+                    }
+                    if (cnt >= lower) {
+                        const uint32_t pos = atomicAdd(&s_wr, 1u);
+                        nge++;
+                        sumge += cnt;
+                        if (pbase + pos < o.cap) {
+                            o.keys[pbase + pos] = mx.inv((p << mx.rbits) | (uint64_t)(hi & rmask));
+                            o.counts[pbase + pos] = cnt;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (gen == gmax) {                            // generation space used up: start over with a clean table
+                for (uint32_t i = tid; i < PC_SLOTS; i += PC_THREADS) s_tab[i] = 0ull;
+                gen = 0;
+            }
+            gen++;
+            if (tid == 0) s_nlist = 0;
+        }
+        // ---- sweep: histogram, write the dump, clear ----
 #pragma unroll 1
-        for (int i = 0; i < SWEEP; i++) {
+        for (int i = 0; i < (VER ? 0 : SWEEP); i++) {
             const uint32_t idx = (i * PC_THREADS + tid) * 4;
             const uint4 c = *reinterpret_cast<const uint4*>(s_cnt + idx);
             const bool any = (c.x | c.y | c.z | c.w) != 0;
@@ -1460,7 +1579,8 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
                     }
             }
         }
-        __syncthreads();
+        if constexpr (!VER) __syncthreads();
+        if constexpr (!VER)
         {   // kept entries: f^-1 and the global stores with every lane busy (a lane-at-a-time version cost a third of the kernel)
             const uint32_t nst = min(s_wr, (uint32_t)(PC_RETRY / 2));
             for (uint32_t i = tid; i < nst; i += PC_THREADS) {
@@ -1548,17 +1668,29 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         k_v3_l2<<<(unsigned)min((uint32_t)sms, 2 * pl.n_st + (uint32_t)nb1 + 1u), V3_THREADS, smem2, st>>>(
             buf1, descT, pl.n_st, chunks, cb + nb1, pl.b2, pl.mx.rbits, (uint32_t*)buf, off2);
         SPK_LAUNCH_CHECK();
-        SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      PC_SLOTS * 8 + PC_RETRY * 4));
-        uint32_t retry_cap = PC_RETRY;
+        // "versioned": the no-clear / no-sweep table variant.  Measured slower on B200 (7.0 vs 5.8 ms on a 676-Mb
+        // chromosome: its 64-bit shared-memory loads + CAS cost more than the sweep they save), kept for comparison.
+        const char* ev = getenv("SPK_PCOUNT_TABLE");
+        const bool ver = (ev && ev[0] == 'v');
+        uint32_t retry_cap = ver ? PC_RETRY_V : PC_RETRY;
         if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
             const long v = atol(e);
-            if (v >= 0 && v < PC_RETRY) retry_cap = (uint32_t)v;
+            if (v >= 0 && v < (long)retry_cap) retry_cap = (uint32_t)v;
         }
         CountOut o{d_keys, d_counts, cap, out_cursor, d_stats, d_histo, histo_len, lower, d_pindex};
         GatherIn gi{cb, off2, pl.b2};
-        k_part_count32<true><<<(unsigned)min((uint64_t)sms * 3, pl.P), PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>(
-            (const uint32_t*)buf, nullptr, pl.P, pl.mx, o, retry_cap, gi);
+        const unsigned cgrid3 = (unsigned)min((uint64_t)sms * 3, pl.P);
+        if (ver) {
+            const size_t smv = (size_t)PC_SLOTS * 8 + PC_RETRY_V * 4 + PC_KEEP * 2;
+            SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv));
+            k_part_count32<true, true><<<cgrid3, PC_THREADS, smv, st>>>((const uint32_t*)buf, nullptr, pl.P, pl.mx, o,
+                                                                       retry_cap, gi);
+        } else {
+            SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          PC_SLOTS * 8 + PC_RETRY * 4));
+            k_part_count32<true, false><<<cgrid3, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>(
+                (const uint32_t*)buf, nullptr, pl.P, pl.mx, o, retry_cap, gi);
+        }
         SPK_LAUNCH_CHECK();
         return SPK_OK;
     }
@@ -1625,14 +1757,14 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
     const unsigned cgrid = (unsigned)min((uint64_t)sms * (ENT64 ? 2 : 3), pl.P);
     const char* v1 = getenv("SPK_PCOUNT_DUMP");        // "list": the 64-bit-slot kernel with the occupied-slot list
     if (!ENT64 && pl.mx.rbits <= 31 && lower >= 1 && !(v1 && v1[0] == 'l')) {
-        SPK_CUDA(cudaFuncSetAttribute(k_part_count32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SPK_CUDA(cudaFuncSetAttribute(k_part_count32<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PC_SLOTS * 8 + PC_RETRY * 4));
         uint32_t retry_cap = PC_RETRY;
         if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
             const long v = atol(e);
             if (v >= 0 && v < PC_RETRY) retry_cap = (uint32_t)v;
         }
-        k_part_count32<false><<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P,
+        k_part_count32<false, false><<<cgrid, PC_THREADS, PC_SLOTS * 8 + PC_RETRY * 4, st>>>((const uint32_t*)buf, pstart, pl.P,
                                                                                      pl.mx, o, retry_cap, GatherIn{});
     } else {
         k_part_count<ENT64><<<cgrid, PC_THREADS, smem, st>>>(buf, pstart, pl.P, pl.mx, o);

@@ -185,6 +185,9 @@ def test_v3_descriptor_pipeline(k, gmax, pbits, monkeypatch):
     fa = util.fasta([("big", "".join(parts))])
     for lower in (1, 3):
         d3 = _check_forced(fa, k, lower, gmax, pbits)
+        monkeypatch.setenv("SPK_PCOUNT_TABLE", "versioned")      # the no-clear / no-sweep variant of the counter's table
+        _check_forced(fa, k, lower, gmax, pbits)
+        monkeypatch.delenv("SPK_PCOUNT_TABLE")
         monkeypatch.setenv("SPK_PCOUNT_PIPE", "v2")
         d2 = _check_forced(fa, k, lower, gmax, pbits)
         monkeypatch.delenv("SPK_PCOUNT_PIPE")
@@ -259,3 +262,33 @@ def test_pack_matches_oracle_codes(mode, monkeypatch):
         got = _unpack(seq)
         np.testing.assert_array_equal(got, np.minimum(want, 4))
         assert seq.n_valid == int(np.sum(want < 4))
+
+
+@pytest.mark.parametrize("table", ["sweep", "versioned"])
+def test_v3_dense_partitions_and_histogram(table, monkeypatch):
+    """70 Mb of random sequence, lower_count 1: ~3000 distinct k-mers per partition, all dumped (more than the
+    kept-slot list of the versioned table holds: scan fallback), and the count histogram path (`histo_len`)."""
+    if MODE[0] != "partitioned":
+        pytest.skip("partitioned counter only")
+    monkeypatch.setenv("SPK_PCOUNT_TABLE", table)
+    from oracle import kmers
+    from subphaser_b200 import engine
+    rng = np.random.default_rng(99)
+    codes = rng.integers(0, 4, 70_000_000, dtype=np.uint8)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    fa = b">r\n" + seq.tobytes() + b"\n"
+    d, n = engine.to_device_bytes(fa)
+    ps = engine.pack_fasta(d, n)
+    del d
+    table = engine.CountTable(ps.n_bases, 17, 1, mode="partitioned")
+    assert table.pbits == 15
+    dump = engine.count_packed(ps, 17, 1, table=table, histo_len=300)
+    keys, counts = dump.to_host()
+    okeys, ocounts, st = kmers.count_fasta(fa, 17, 1, nthreads=8)
+    o = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(keys[o], okeys)
+    np.testing.assert_array_equal(counts[o], ocounts)
+    assert dump.n_distinct == st["n_distinct"] and dump.length == st["sum_dumped"]
+    h = dump.histo.cpu().numpy()
+    want = np.bincount(np.minimum(ocounts, 299).astype(np.int64), minlength=300)
+    np.testing.assert_array_equal(h[1:], want[1:])
