@@ -12,6 +12,7 @@
 // then run at full occupancy — the fp64 work of a handful of candidates per partition would otherwise
 // serialise whole CTAs behind two or three active lanes.  The multi-GB union table and the [U x n] matrix
 // of the plain path (spk_matrix.cu: ~6 random HBM accesses per dump entry) never exist.
+#include <stdlib.h>
 #include "spk_common.cuh"
 #include "spk_filter.cuh"
 
@@ -41,8 +42,9 @@ struct PmArgs {
 
 __device__ __forceinline__ uint32_t pm_hash(uint64_t key) { return (uint32_t)(spk_hash64(key) >> 32); }
 
-__global__ void __launch_bounds__(PM_THREADS, 1) k_pmatrix_filter(PmArgs a) {
+__global__ void __launch_bounds__(PM_THREADS, 1) k_pmatrix_filter(PmArgs a, const uint64_t* run_if) {
     extern __shared__ __align__(16) uint8_t s_raw[];
+    if (run_if && *run_if == 0) return;                  // (k_pmatrix_filter2 took the whole call)
     const int n = a.n;
     const uint32_t TS = a.tslots, TM = TS - 1;
     uint64_t* s_key = (uint64_t*)s_raw;                        // [TS]
@@ -194,6 +196,226 @@ __global__ void __launch_bounds__(PM_THREADS, 1) k_pmatrix_filter(PmArgs a) {
     (void)lengths;
 }
 
+
+// ---- k_pmatrix_filter2: presence masks first, count rows only for candidates ------------------------------------
+// The integer pre-screen only asks WHICH homoeologous sets have a nonzero count, and a dumped count is never zero:
+// the decision depends on the set of chromosomes a k-mer was dumped by.  So the table keeps, per k-mer, a 64-bit
+// mask of the (multi-group) sets that contain one of its chromosomes — 16 bytes per slot instead of 8 + 4n — and
+// only the ~2 % of rows whose mask reaches `min_include` sets get a count row, filled from the entries the threads
+// still hold in registers.  No n-wide zero / test / clear loop runs over the union rows any more, the table (4096
+// slots) takes a whole partition in one round, and two CTAs share an SM (k_pmatrix_filter: one, 190 KB).
+// What it cannot take — a partition with more entries than the threads hold, more candidates than its row buffer,
+// more than 64 sets — it reports in counters[5]; k_pmatrix_filter then redoes the call (decided on the device).
+constexpr int PM2_THREADS = 512;
+constexpr int PM2_B = 6;                 // dump entries per thread held in registers (3072 per CTA)
+constexpr int PM2_TS = 4096;             // table slots
+constexpr int PM2_MAXC = 192;            // candidate rows per partition
+
+__global__ void __launch_bounds__(PM2_THREADS, 2) k_pmatrix_filter2(PmArgs a) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    const int n = a.n;
+    constexpr uint32_t TS = PM2_TS, TM = TS - 1;
+    constexpr uint32_t NONE = 0xffffffffu, PENDING = 0xfffffffeu;
+    uint64_t* s_key = (uint64_t*)s_raw;                               // [TS]
+    unsigned long long* s_mask = (unsigned long long*)(s_key + TS);   // [TS] sets present
+    uint64_t* s_colmask = (uint64_t*)(s_mask + TS);                   // [n]  sets that contain chromosome c
+    uint64_t* s_ckey = s_colmask + n;                                 // [MAXC]
+    const uint64_t** s_pk = (const uint64_t**)(s_ckey + PM2_MAXC);    // [n] dump pointers (no double indirection per entry)
+    const uint32_t** s_pc = (const uint32_t**)(s_pk + n);             // [n]
+    uint32_t* s_rowid = (uint32_t*)(s_pc + n);                        // [TS] candidate row of a slot, or NONE
+    uint32_t* s_crow = s_rowid + TS;                                  // [MAXC x n]
+    uint32_t* s_start = s_crow + (size_t)PM2_MAXC * n;                // [n]
+    uint32_t* s_off = s_start + n;                                    // [n + 1]
+    uint8_t* s_cfg = (uint8_t*)(((uintptr_t)(s_off + n + 2) + 7) & ~(uintptr_t)7);
+    __shared__ uint32_t s_fail, s_ncand, s_need;
+    __shared__ unsigned long long s_wbase;
+    const uint64_t* lengths = a.lengths;
+    FilterCfg cfg = a.cfg;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (!a.union_only) cfg = spk_filter_stage(a.cfg, a.n_groups, n, a.lengths, s_cfg, &lengths);
+    for (int c = tid; c < n; c += PM2_THREADS) {
+        s_colmask[c] = 0;
+        s_pk[c] = a.keys[c];
+        s_pc[c] = a.counts[c];
+    }
+    for (uint32_t i = tid; i < TS; i += PM2_THREADS) {
+        s_key[i] = SPK_EMPTY_KEY;
+        s_mask[i] = 0ull;
+        s_rowid[i] = NONE;
+    }
+    for (uint32_t i = tid; i < (uint32_t)PM2_MAXC * n; i += PM2_THREADS) s_crow[i] = 0;
+    if (tid == 0) {
+        s_fail = 0;
+        s_ncand = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t need = 0;
+        if (!a.union_only) {
+            int bit = 0;
+            for (int st = 0; st < cfg.n_sets; st++) {
+                const int g0 = cfg.set_off[st], g1 = cfg.set_off[st + 1];
+                if (g1 - g0 < 2) continue;
+                for (int m = cfg.grp_off[g0]; m < cfg.grp_off[g1]; m++) s_colmask[cfg.members[m]] |= 1ull << bit;
+                bit++;
+            }
+            need = (uint32_t)max(cfg.min_include, 0);
+        }
+        s_need = need;
+    }
+    uint64_t n_union = 0, n_keep = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * a.nparts;
+    uint64_t p = (uint64_t)blockIdx.x * a.nparts + a.part;
+    uint32_t nx_start = 0, nx_len = 0;
+    if (p < a.P && tid < n) {
+        nx_start = a.pindex[tid][2 * p];
+        nx_len = a.pindex[tid][2 * p + 1];
+    }
+    __syncthreads();
+    const uint32_t need = s_need;
+    for (; p < a.P; p += stride) {
+        if (tid < n) {
+            s_start[tid] = nx_start;
+            s_off[tid + 1] = nx_len;
+        }
+        const uint64_t pn = p + stride;
+        if (pn < a.P && tid < n) {
+            nx_start = a.pindex[tid][2 * pn];
+            nx_len = a.pindex[tid][2 * pn + 1];
+        }
+        __syncthreads();
+        if (tid < 32) {                                    // exclusive prefix of the n run lengths
+            uint32_t carry = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int c = base + lane;
+                const uint32_t l = c < n ? s_off[c + 1] : 0u;
+                uint32_t incl = l;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (c < n) s_off[c + 1] = carry + incl;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) s_off[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t E = s_off[n];
+        if (E > (uint32_t)(PM2_B * PM2_THREADS)) {          // (block-uniform) not a partition for this kernel
+            if (tid == 0) s_fail = 1;
+            continue;
+        }
+        uint64_t key[PM2_B];
+        uint32_t cnt[PM2_B], slot[PM2_B];
+        int col[PM2_B];
+        // ---- pass 1: key -> slot, OR the chromosome's set mask into the slot ----
+        {
+            int c = 0;
+#pragma unroll
+            for (int u = 0; u < PM2_B; u++) {
+                const uint32_t e = u * PM2_THREADS + tid;
+                col[u] = -1;
+                if (e < E) {
+                    while (e >= s_off[c + 1]) c++;
+                    const uint32_t i = s_start[c] + (e - s_off[c]);
+                    key[u] = __ldg(s_pk[c] + i);
+                    cnt[u] = __ldg(s_pc[c] + i);
+                    col[u] = c;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PM2_B; u++) {
+            if (col[u] < 0) continue;
+            uint32_t sl = pm_hash(key[u]) & TM;
+            bool done = false;
+            for (uint32_t pr = 0; pr < TS; pr++) {
+                uint64_t cur = s_key[sl];
+                if (cur == SPK_EMPTY_KEY) {
+                    cur = atomicCAS((unsigned long long*)&s_key[sl], (unsigned long long)SPK_EMPTY_KEY,
+                                    (unsigned long long)key[u]);
+                    if (cur == SPK_EMPTY_KEY) {
+                        cur = key[u];
+                        n_union++;
+                    }
+                }
+                if (cur == key[u]) {
+                    const uint64_t m = s_colmask[col[u]];
+                    if (m && cnt[u]) atomicOr(&s_mask[sl], (unsigned long long)m);   // (a zero count is no presence)
+                    slot[u] = sl;
+                    done = true;
+                    break;
+                }
+                sl = (sl + 1) & TM;
+            }
+            if (!done) { s_fail = 1; col[u] = -1; }         // (cannot happen: E <= 3072 < TS)
+        }
+        __syncthreads();
+        if (!a.union_only) {
+            // ---- pass 2a: slots whose sets reach min_include become candidate rows ----
+#pragma unroll
+            for (int u = 0; u < PM2_B; u++) {
+                if (col[u] < 0) continue;
+                if ((uint32_t)__popcll(s_mask[slot[u]]) < need) { col[u] = -1; continue; }
+                if (atomicCAS(&s_rowid[slot[u]], NONE, PENDING) == NONE) {
+                    const uint32_t rid = atomicAdd(&s_ncand, 1u);
+                    if (rid < (uint32_t)PM2_MAXC) s_ckey[rid] = key[u];
+                    s_rowid[slot[u]] = rid;                  // read after the barrier below
+                }
+            }
+            __syncthreads();
+            // ---- pass 2b: the entries of the candidates fill their rows ----
+            const uint32_t nc_all = s_ncand;
+#pragma unroll
+            for (int u = 0; u < PM2_B; u++) {
+                if (col[u] < 0) continue;
+                const uint32_t rid = s_rowid[slot[u]];
+                if (rid < (uint32_t)PM2_MAXC) s_crow[(size_t)rid * n + col[u]] = cnt[u];
+            }
+            if (tid == 0) {
+                if (nc_all > (uint32_t)PM2_MAXC) s_fail = 1;
+                const uint32_t ncw = min(nc_all, (uint32_t)PM2_MAXC);
+                s_wbase = ncw ? atomicAdd((unsigned long long*)&a.counters[4], (unsigned long long)ncw) : 0ull;
+                n_keep += nc_all;
+            }
+            __syncthreads();
+            // ---- emit ----
+            const uint32_t nc = min(nc_all, (uint32_t)PM2_MAXC);
+            const uint64_t wb = s_wbase;
+            for (uint32_t i = tid; i < nc * (uint32_t)n; i += PM2_THREADS) {
+                const uint32_t r = i / (uint32_t)n;
+                if (wb + r < a.cap) a.out_counts[(wb + r) * n + (i - r * n)] = s_crow[i];
+                s_crow[i] = 0;
+            }
+            for (uint32_t r = tid; r < nc; r += PM2_THREADS)
+                if (wb + r < a.cap) a.out_keys[wb + r] = s_ckey[r];
+        }
+        // ---- clear the table ----
+        for (uint32_t i = tid; i < TS; i += PM2_THREADS) {
+            s_key[i] = SPK_EMPTY_KEY;
+            s_mask[i] = 0ull;
+            s_rowid[i] = NONE;
+        }
+        if (tid == 0) s_ncand = 0;
+        __syncthreads();
+    }
+    n_union = spk_warp_sum_u64(n_union);
+    n_keep = spk_warp_sum_u64(n_keep);
+    if (lane == 0) {
+        if (n_union) atomicAdd((unsigned long long*)&a.counters[0], (unsigned long long)n_union);
+        if (n_keep) atomicAdd((unsigned long long*)&a.counters[2], (unsigned long long)n_keep);
+    }
+    __syncthreads();
+    if (tid == 0 && s_fail) atomicAdd((unsigned long long*)&a.counters[5], 1ull);
+    (void)lengths;
+}
+
+// counters of a failed k_pmatrix_filter2 pass are reset before the general kernel redoes the call
+__global__ void k_pm_reset_if(uint64_t* counters) {
+    if (counters[5]) counters[0] = counters[1] = counters[2] = counters[3] = counters[4] = 0;
+}
+
 // Regroup a partition-indexed dump: partition p's run [pindex[2p], +pindex[2p+1]) moves to new_start[p].
 // One warp per partition (runs are a few dozen entries); used by the multi-GPU exchange to make every
 // destination rank's partition class contiguous before the all-to-all.
@@ -337,15 +559,28 @@ extern "C" int spk_pmatrix_filter(const uint64_t* const* d_keys, const uint32_t*
     smem = (smem + 7) / 8 * 8;
     if (!a.union_only) smem += spk_filter_stage_bytes(n_sets, n_groups, n_members, n);
     SPK_CHECK_ARG(smem <= 220 * 1024, "homoeolog configuration too large");
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
+    SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t mine = (a.P + nparts - 1 - part) / nparts;
     if (mine == 0) return SPK_OK;
     const unsigned grid = (unsigned)min((uint64_t)spk_num_sms(), mine);
-    k_pmatrix_filter<<<grid, PM_THREADS, smem, st>>>(a);
+    // presence-mask kernel first (<= 64 sets, a fold threshold that all-zero sets fail); the general kernel runs only
+    // if that pass reports something it could not take (device-side decision, no host synchronisation)
+    const uint64_t* run_if = nullptr;
+    const char* pm = getenv("SPK_PMATRIX_KERNEL");                 // "general": skip the presence-mask kernel (tests)
+    if (n_sets <= 64 && (a.union_only || !(0.0 >= min_fold)) && !(pm && pm[0] == 'g')) {
+        size_t smem2 = (size_t)PM2_TS * 16 + (size_t)n * 8 + (size_t)PM2_MAXC * 8 + (size_t)n * 16 + (size_t)PM2_TS * 4 +
+                       (size_t)PM2_MAXC * n * 4 + (size_t)(2 * n + 2) * 4 + 16;
+        if (!a.union_only) smem2 += spk_filter_stage_bytes(n_sets, n_groups, n_members, n);
+        if (smem2 <= 110 * 1024) {
+            SPK_CUDA(cudaFuncSetAttribute(k_pmatrix_filter2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k_pmatrix_filter2<<<(unsigned)min((uint64_t)spk_num_sms() * 2, mine), PM2_THREADS, smem2, st>>>(a);
+            SPK_LAUNCH_CHECK();
+            k_pm_reset_if<<<1, 1, 0, st>>>(d_counters);
+            SPK_LAUNCH_CHECK();
+            run_if = d_counters + 5;
+        }
+    }
+    k_pmatrix_filter<<<grid, PM_THREADS, smem, st>>>(a, run_if);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

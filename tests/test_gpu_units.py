@@ -123,6 +123,35 @@ def test_partitioned_union_filter_equals_plain_path(k, lower, chr_len, min_freq)
     assert got.norm.cpu().numpy().tobytes() == onorm.tobytes()
 
 
+@pytest.mark.parametrize("ratio,min_fold", [(1, 2), (0.5, 2), (0.3, 1.5), (1, 0)])
+def test_pmatrix_presence_mask_kernel_equals_general_kernel(ratio, min_fold, monkeypatch):
+    """k_pmatrix_filter2 (presence masks, candidate rows only) and k_pmatrix_filter (full count rows) emit the same
+    candidate rows; ratios that make most rows candidates overflow the candidate buffer of the former, which then
+    hands the call to the latter on the device (counters[5]); min_fold 0 never uses the former."""
+    from subphaser_b200 import engine
+    import spk_testutil as util
+    k, lower = 15, 1
+    records, sgs = util.subgenome_genome(k, n_sg=4, chr_per_sg=2, chr_len=150000)
+    labels = [r[0] for r in records]
+    packed = []
+    for name, seq in records:
+        d, n = engine.to_device_bytes(util.fasta([(name, seq)]))
+        packed.append(engine.pack_fasta(d, n))
+    table = engine.CountTable(max(p.n_bases for p in packed), k, lower)
+    dumps = [engine.count_packed(p, k, lower, table=table) for p in packed]
+    kw = dict(min_fold=min_fold, baseline=1, ratio=ratio, min_freq=5, max_freq=10000)
+    a, ua = engine.pmatrix_filter(dumps, sgs, labels, **kw)
+    monkeypatch.setenv("SPK_PMATRIX_KERNEL", "general")
+    b, ub = engine.pmatrix_filter(dumps, sgs, labels, **kw)
+    monkeypatch.delenv("SPK_PMATRIX_KERNEL")
+    cm = engine.build_matrix(dumps, labels)
+    want = engine.filter_matrix(cm, sgs, labels, **kw)
+    assert ua == ub == len(cm) and len(a) == len(b) == len(want) > 0
+    for got in (a, b):
+        np.testing.assert_array_equal(engine.u64_numpy(got.keys), engine.u64_numpy(want.keys))
+        assert got.norm.cpu().numpy().tobytes() == want.norm.cpu().numpy().tobytes()
+
+
 # ---- sort -------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,bits", [(1, 8), (2, 64), (1000, 34), (2049, 64), (300000, 42), (1 << 20, 30)])
 def test_radix_sort(n, bits):
