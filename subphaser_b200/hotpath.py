@@ -526,12 +526,16 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         seqs[i], dumps[i] = seq, dump
         n_kmers += dump.n_valid_kmers
         if px is not None:
-            e = t.start("scatter")
-            if dump.pindex is not None and dump.pbits == px.pbits:
-                px.scatter(i, dump)
-            else:                               # counted by the global-table fallback: no partition index
-                px.overflow += 1
-            t.stop(e)
+            # the peer stores of this dump run on their own stream, underneath the next chromosome's pack + count
+            px_stream = _SCRATCH.setdefault("px_stream", torch.cuda.Stream())
+            px_stream.wait_stream(main_stream)
+            with torch.cuda.stream(px_stream):
+                e = t.start("scatter_side")
+                if dump.pindex is not None and dump.pbits == px.pbits:
+                    px.scatter(i, dump)
+                else:                               # counted by the global-table fallback: no partition index
+                    px.overflow += 1
+                t.stop(e)
     t.stop(e_loop)
     del table          # stays alive in _SCRATCH for the next call
 
@@ -540,6 +544,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     got = None
     if world > 1 and px is not None:
         e = t.start("exchange")
+        main_stream.wait_stream(_SCRATCH["px_stream"]) if "px_stream" in _SCRATCH else None
         e2 = t.start("_x_wait")                      # the sizes' all_reduce doubles as the barrier with the slowest rank
         got, n_kmers_total, bases_all = px.finish(owner, {i: dumps[i].length for i in mine},
                                                   {i: seqs[i].n_bases for i in mine}, n_kmers)
