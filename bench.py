@@ -374,6 +374,10 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     stage_ms = timer.totals_ms()
     stage_n = timer.counts()
+    rank_stages = None
+    if world > 1:                    # every rank's stage times (the step is the slowest rank's)
+        rank_stages = [None] * world
+        dist.all_gather_object(rank_stages, {k_: round(v / args.steps, 2) for k_, v in sorted(stage_ms.items())})
     n_kmers = res["n_kmers"]
     value = n_kmers * args.steps / secs
     n_windows = res["n_windows"]
@@ -421,16 +425,22 @@ def main():
             else:
                 host_inputs[i] = (None, dev_inputs[i][1])
         torch.cuda.synchronize()
-        dev_inputs = None
-        torch.cuda.empty_cache()
-        hotpath.run(host_inputs, host_inputs=True, return_host=True, **kw)          # warm-up
-        esecs, eres = timed(args.steps, True, host_inputs)
+        dev_inputs = None               # (their blocks stay in the allocator's cache: the per-chromosome staging buffers re-use them)
+        for _ in range(max(args.warmup, 1)):        # warm-up: pinned result buffers, allocator pools of the copy streams
+            hotpath.run(host_inputs, host_inputs=True, return_host=True, **kw)
+        etimer = hotpath.StageTimer(True)
+        esecs, eres = timed(args.steps, True, host_inputs, etimer)
+        e2e_stages = {k_: round(v / args.steps, 2) for k_, v in sorted(etimer.totals_ms().items())}
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, e2e_stages)
+            e2e_stages = gathered
         hb = torch.tensor([float(eres["h2d_bytes"]), float(eres["d2h_bytes"])], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(hb)
         e2e = {"value": eres["n_kmers"] * args.steps / esecs, "unit": UNIT, "h2d_bytes_per_step": int(hb[0].item()),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * esecs / args.steps,
-               "windows_per_s": eres["n_windows"] * args.steps / esecs}
+               "windows_per_s": eres["n_windows"] * args.steps / esecs, "stage_ms": e2e_stages}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the whole path on a replica + counts checked at scale ----
     cpu = None
@@ -467,6 +477,7 @@ def main():
             "windows_per_s": n_windows * args.steps / win_s if win_s > 0 else None,
             "stage_ms_per_step": {k_: v / args.steps for k_, v in sorted(stage_ms.items()) if not k_.startswith("_")},
             "loop_ms_per_step": {k_[1:]: v / args.steps for k_, v in sorted(stage_ms.items()) if k_.startswith("_")},
+            "stage_ms_per_rank": rank_stages,
             "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],
                         "n_windows": n_windows, "labels": res["labels_full"]},
             "roofline": roofline, "cpu_baseline": cpu, "parity_at_scale": parity, "e2e": e2e, "e2e_dropin": dropin,

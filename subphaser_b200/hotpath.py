@@ -63,7 +63,7 @@ def lpt_assign(lengths, world):
     return owner
 
 
-def _gather_concat(parts, sizes, owner, n, dist, dev, dtype):
+def _gather_concat(parts, sizes, owner, n, dist, dev, dtype, group=None):
     """parts: {chromosome index: 1-D tensor} owned by this rank; sizes[i]: its length on every rank.
     One all_gather of the per-rank concatenation (padded to the longest) -> {i: view} for every chromosome."""
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -78,9 +78,9 @@ def _gather_concat(parts, sizes, owner, n, dist, dev, dtype):
         off += sizes[i]
     recv = torch.empty(world, width, dtype=dtype, device=dev)
     try:
-        dist.all_gather_into_tensor(recv.view(-1), send)      # one flat collective, no per-rank output copies
+        dist.all_gather_into_tensor(recv.view(-1), send, group=group)   # one flat collective, no per-rank output copies
     except (RuntimeError, NotImplementedError, AttributeError):
-        dist.all_gather(list(recv.unbind(0)), send)
+        dist.all_gather(list(recv.unbind(0)), send, group=group)
     out = {}
     for r in range(world):
         off = 0
@@ -241,31 +241,60 @@ def exchange_dumps_by_class(local, pindex_local, pbits, n, owner, dist, dev, n_k
     return out, int(meta_h[n][0])
 
 
-def exchange_rows(dm, n_union_local, dist, dev):
-    """Differential-matrix shards (rows of this rank's partitions) -> the full matrix, sorted by k-mer, on every
-    rank: one all_reduce of the sizes, three all_gathers (keys, normalised rows, totals), one key sort."""
+def exchange_rows_meta(dm, n_union_local, dist, dev):
+    """Sizes of every rank's differential-matrix shard, union rows and fold-test passes of the whole genome (one
+    all_reduce) -> ([rows per rank], n_union, n_fold_pass)."""
     rank, world = dist.get_rank(), dist.get_world_size()
-    ncol = dm.norm.shape[1]
     meta = torch.zeros(world + 2, dtype=torch.int64, device=dev)
     meta[rank] = len(dm)
     meta[world] = int(n_union_local)
     meta[world + 1] = int(dm.n_fold_pass)
     dist.all_reduce(meta)
-    meta_h = meta.cpu().tolist()
-    m = [int(x) for x in meta_h[:world]]
+    meta_h = [int(x) for x in meta.cpu().tolist()]
+    return meta_h[:world], meta_h[world], meta_h[world + 1]
+
+
+def gather_rows(dm, m, n_fold_pass, dist, dev, group=None):
+    """Differential-matrix shards (rows of this rank's partitions) -> the full matrix, sorted by k-mer, on every
+    rank: three all_gathers (keys, normalised rows, totals) and one key sort.  `group`: the process group the
+    collectives run on (the caller issues this on a side stream with its own communicator)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ncol = dm.norm.shape[1]
     ident = list(range(world))
-    kk = _gather_concat({rank: dm.keys.contiguous()}, m, ident, world, dist, dev, torch.int64)
+    kk = _gather_concat({rank: dm.keys.contiguous()}, m, ident, world, dist, dev, torch.int64, group)
     nn = _gather_concat({rank: dm.norm.contiguous().view(-1)}, [x * ncol for x in m], ident, world, dist, dev,
-                        torch.float64)
-    tt = _gather_concat({rank: dm.tot.contiguous()}, m, ident, world, dist, dev, torch.int64)
+                        torch.float64, group)
+    tt = _gather_concat({rank: dm.tot.contiguous()}, m, ident, world, dist, dev, torch.int64, group)
     keys = torch.cat([kk[r] for r in range(world)])
     norm = torch.cat([nn[r].view(-1, ncol) for r in range(world)])
     tot = torch.cat([tt[r] for r in range(world)])
     # global row order = ascending k-mer, as on one GPU (keys are < 2^63 except k = 32: use the sort kernel)
     order = engine.argsort_keys(keys, 2 * dm.k)
-    full = engine.DiffMatrix(keys[order].contiguous(), norm[order].contiguous(), tot[order].contiguous(), dm.k,
-                             dm.labels, int(meta_h[world + 1]))
-    return full, int(meta_h[world])
+    return engine.DiffMatrix(keys[order].contiguous(), norm[order].contiguous(), tot[order].contiguous(), dm.k,
+                             dm.labels, int(n_fold_pass))
+
+
+def exchange_rows(dm, n_union_local, dist, dev):
+    """exchange_rows_meta + gather_rows on the default group -> (full matrix, n_union)."""
+    m, n_union, n_fold = exchange_rows_meta(dm, n_union_local, dist, dev)
+    return gather_rows(dm, m, n_fold, dist, dev), n_union
+
+
+def gather_sig(keys, vals, key_bits, dist, dev):
+    """Significant k-mers of every rank's row shard -> all of them on every rank, ascending (the table the map stage
+    probes is built from the same list on every rank): one all_reduce of the sizes, two all_gathers, one sort."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sz = torch.zeros(world, dtype=torch.int64, device=dev)
+    sz[rank] = int(keys.numel())
+    dist.all_reduce(sz)
+    m = [int(x) for x in sz.cpu().tolist()]
+    ident = list(range(world))
+    kk = _gather_concat({rank: keys.contiguous()}, m, ident, world, dist, dev, torch.int64)
+    vv = _gather_concat({rank: vals.contiguous()}, m, ident, world, dist, dev, torch.uint8)
+    allk = torch.cat([kk[r] for r in range(world)])
+    allv = torch.cat([vv[r] for r in range(world)])
+    order = engine.argsort_keys(allk, key_bits)
+    return allk[order].contiguous(), allv[order].contiguous()
 
 
 def exchange_windows(win_counts, n, nsg, owner, dist, dev, nw_known=None):
@@ -416,6 +445,20 @@ def release_scratch():
     _PINNED.clear()
 
 
+_COPY_CHUNK = 32 << 20
+
+
+def _copy_chunked(dst, src):
+    """Asynchronous host<->device copy of a flat tensor in 32-MiB pieces.  One cudaMemcpyAsync of a whole chromosome
+    (0.7 GB) or of the differential matrix (0.6 GB) occupies the copy engine of its direction for tens of
+    milliseconds, and every small copy of the main stream in the same direction (kernel parameters, labels, sizes)
+    queues behind it; in pieces, the small copies slip in between."""
+    n = dst.numel()
+    step = max(_COPY_CHUNK // max(dst.element_size(), 1), 1)
+    for off in range(0, n, step):
+        dst[off:off + step].copy_(src[off:off + step], non_blocking=True)
+
+
 def _to_host_pinned(name, t):
     """Device tensor -> numpy through a cached pinned staging buffer (async copy; caller synchronises)."""
     n = t.numel()
@@ -423,9 +466,12 @@ def _to_host_pinned(name, t):
     if buf is None or buf.numel() < n or buf.dtype != t.dtype:
         buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
         _PINNED[name] = buf
-    view = buf[:n].view(t.shape)
-    view.copy_(t, non_blocking=True)
-    return view
+    src = t.contiguous().view(-1)
+    if src.is_cuda and n * src.element_size() >= (1 << 20):
+        _lib.call("spk_store_to_host", engine._p(src), buf.data_ptr(), n * src.element_size(), engine._stream())
+    else:
+        buf[:n].copy_(src, non_blocking=True)
+    return buf[:n].view(t.shape)
 
 
 class StageTimer:
@@ -473,6 +519,8 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         owner = [0] * n
     mine = [i for i in range(n) if owner[i] == rank]
     h2d_bytes = 0
+    e_run = t.start("_run")
+    e_head = t.start("_head")
 
     # ---- K1-K3 per chromosome -----------------------------------------------------------------------
     max_bytes = max([chrom_inputs[i][1] for i in mine] + [1])
@@ -488,7 +536,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         d = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
         copy_stream.wait_stream(main_stream)       # the block may have been used by earlier main-stream work
         with torch.cuda.stream(copy_stream):
-            d[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+            _copy_chunked(d[:nbytes], buf[:nbytes])
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return d, ev
@@ -504,6 +552,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         px = _peer_exchange(dist, [c[1] for c in chrom_inputs], table.pbits, lower_count, dev)
         if px is not None:
             px.begin()
+    t.stop(e_head)
     e_loop = t.start("_loop_pack_count")      # coarse brackets ("_..."): stage sums vs. whole-loop time = host gaps
     for pos, i in enumerate(order_in):
         buf, nbytes = chrom_inputs[i]
@@ -626,22 +675,40 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         t.stop(e)
         n_union = len(cm)
         del cm
+    shard = dm          # world > 1: this rank's rows (its partition class), ascending k-mer
+    full_side = None
+    side = _SCRATCH.setdefault("side_stream", torch.cuda.Stream())
     if world > 1:
         e = t.start("exchange")
         e2 = t.start("_x_rows")
-        dm, n_union = exchange_rows(dm, n_union, dist, dev)
+        m_rows, n_union, n_fold_all = exchange_rows_meta(shard, n_union, dist, dev)
+        M = sum(m_rows)
         t.stop(e2)
         t.stop(e)
-    M = len(dm)
+    else:
+        M = len(dm)
     if M == 0:
         raise ValueError("0 kmer remained after filtering. Please reset the filter options.")
+    if world > 1:
+        # Only the report (bootstrap, PCA input, the matrix handed back to the host) needs every row on every rank:
+        # the 0.6-GB all-gather + sort runs on the side stream over its own communicator, underneath the Gram pass,
+        # the t-test and the map stage, which work on the row shards.
+        side_pg = _SCRATCH.get("side_pg")
+        if side_pg is None or side_pg[0] != world:
+            side_pg = (world, dist.new_group(ranks=list(range(world))))
+            _SCRATCH["side_pg"] = side_pg
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            e_g = t.start("gather_rows_side")
+            dm = gather_rows(shard, m_rows, n_fold_all, dist, dev, group=side_pg[1])
+            t.stop(e_g)
     # the differential matrix is final here: its device->host copy (0.6 GB for wheat, ~25 ms of PCIe) runs on a
     # side stream underneath the clustering and mapping stages
     host_copy = None
     return_host = bool(return_host) and rank == 0     # one copy of the results leaves the node, not one per rank
     if return_host:
         d2h_stream = _SCRATCH.setdefault("d2h_stream", torch.cuda.Stream())
-        d2h_stream.wait_stream(torch.cuda.current_stream())
+        d2h_stream.wait_stream(side if world > 1 else torch.cuda.current_stream())
         with torch.cuda.stream(d2h_stream):
             host_copy = (_to_host_pinned("dm_keys", dm.keys), _to_host_pinned("dm_norm", dm.norm))
 
@@ -650,18 +717,17 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         nsg = max(len(sg) for sg in sgs)
     e = t.start("cluster")
     if world > 1:
-        # every rank holds the whole matrix here; the Gram pass (one stream over all rows) is split by rows and the
-        # n x n partial sums are all-reduced — the full z-scored matrix the bootstrap gathers from is produced on the
-        # side stream, off the critical path
-        per = (M + world - 1) // world
-        lo, hi = min(rank * per, M), min((rank + 1) * per, M)
-        G = engine.gram(engine.zscore_rows(dm.norm[lo:hi])) if hi > lo else torch.zeros(n, n, dtype=torch.float64, device=dev)
+        # the Gram pass (one stream over all rows) runs on the row shards and the n x n partial sums are all-reduced
+        G = (engine.gram(engine.zscore_rows(shard.norm)) if len(shard) else
+             torch.zeros(n, n, dtype=torch.float64, device=dev))
         dist.all_reduce(G)
         Z = None
     else:
         Z = engine.zscore_rows(dm.norm)
         G = engine.gram(Z)
-    order = [i for _, i in sorted(zip(labels, range(n)))]
+    # (device copies of small host lists are made here, on the main stream: a pageable host->device copy issued on
+    # the side stream would block the host until the side stream reaches it, and the main stream would idle)
+    order = torch.tensor([i for _, i in sorted(zip(labels, range(n)))], dtype=torch.int32, device=dev)
     lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
     lab_full_h = lab_full[0].cpu().numpy()
     t.stop(e)
@@ -669,7 +735,6 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     # thread block) only feed the report; nothing downstream waits for them.  They run on a side stream underneath the
     # t-test, the table build and the map kernels and are joined at the end.
     R = int(replicates)
-    side = _SCRATCH.setdefault("side_stream", torch.cuda.Stream())
     side.wait_stream(torch.cuda.current_stream())
     lab_b = ari = vm = None
     with torch.cuda.stream(side):
@@ -688,19 +753,25 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
                     lab_loc, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1, r0=lo)
                     lab_pad[:hi - lo] = lab_loc
                 lab_all = torch.empty(world * per, n, dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(lab_all.view(-1), lab_pad.view(-1))
+                dist.all_gather_into_tensor(lab_all.view(-1), lab_pad.view(-1), group=_SCRATCH["side_pg"][1])
                 lab_b = lab_all[:R].contiguous()
             else:
                 Gb = engine.gram_batched(Z, d_idx)
                 lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
-            ari, vm = engine.cluster_scores(lab_full_h, lab_b)
+            ari, vm = engine.cluster_scores(lab_full[0], lab_b)
         eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
         t.stop(e_side)
     e = t.start("ttest")
-    best, pval, means = engine.ttest_groups(dm.norm, lab_full_h.tolist(), nsg)
-    keep = ~(pval > max_pval)
-    sig_keys = dm.keys[keep].contiguous()
-    sig_vals = best[keep].to(torch.uint8).contiguous()
+    if len(shard):
+        best, pval, means = engine.ttest_groups(shard.norm, lab_full_h.tolist(), nsg)
+        keep = ~(pval > max_pval)
+        sig_keys = shard.keys[keep].contiguous()
+        sig_vals = best[keep].to(torch.uint8).contiguous()
+    else:
+        sig_keys = torch.empty(0, dtype=torch.int64, device=dev)
+        sig_vals = torch.empty(0, dtype=torch.uint8, device=dev)
+    if world > 1:
+        sig_keys, sig_vals = gather_sig(sig_keys, sig_vals, 2 * k, dist, dev)
     t.stop(e)
 
     # ---- K9 map ----------------------------------------------------------------------------------------
@@ -744,16 +815,20 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     allw = allw[nz].contiguous()
     enr = engine.fisher_enrich(allw, max_pval=max_pval)
     t.stop(e)
+    e_tail = t.start("_tail")
     side.synchronize()
     d_bs = None
     if lab_b is not None:
         lab_b_h = lab_b.cpu().numpy()
         d_bs = [int(100 * int(np.sum(lab_b_h[:, i] == lab_full_h[i])) / R) for i in range(n)]
     d2h_bytes = int(dm.norm.numel() * 8 + dm.keys.numel() * 8 + allw.numel() * 8 * 4)
+    pca_host = (scores.cpu().numpy(), pratio.cpu().numpy())
+    t.stop(e_tail)
+    t.stop(e_run)
     return dict(n_kmers=n_kmers_total, n_kmers_local=n_kmers, n_union=n_union, n_diff=M, n_sig=int(sig_keys.numel()),
                 n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
                 lengths=[d.length for d in dump_list], enrich=enr, dm=dm, window_counts=allw,
-                pca=(scores.cpu().numpy(), pratio.cpu().numpy()),
+                pca=pca_host,
                 h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes if return_host else int(allw.numel() * 8 * 4),
                 matrix_host=_matrix_host(host_copy) if return_host else None)
 
