@@ -51,7 +51,12 @@ uint64_t spk_launch_count(void);
  * of d_valid[i/32].  Both arrays must be zero-padded by the caller up to spk_packed_words(cap)/
  * spk_valid_words(cap) — the kernels write every word of that extent.
  * d_info (uint64[4], device): [0] = number of bases emitted, [1] = number of valid bases,
- *                             [2] = number of records (headers seen), [3] = reserved.
+ *                             [2] = number of records (headers seen), [3] = which kernel produced the result
+ *                             (0 regular-layout, 2 general single pass, 1 three-pass; diagnostic).
+ * Three kernels, each handing the call to the next on the device when the input is not what it handles: one record
+ * with lines of a constant width (positions by arithmetic, layout verified byte by byte); any FASTA whose lines are
+ * shorter than 512 bytes (decoupled look-back); anything else (three passes).  SPK_PACK_MODE=single|3pass skips the
+ * earlier ones (tests).
  * ---------------------------------------------------------------------------------------------- */
 size_t spk_packed_words(uint64_t n_bases); /* uint32 words incl. tile padding */
 size_t spk_valid_words(uint64_t n_bases);

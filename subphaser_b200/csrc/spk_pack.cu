@@ -522,7 +522,8 @@ constexpr int PK_SUB = 4;                       // 4-KiB sub-tiles per look-back
 __global__ void __launch_bounds__(PK_THREADS)
 k_pack_single(const uint8_t* __restrict__ in, size_t nbytes, size_t nunits, uint64_t* __restrict__ status,
               uint32_t* __restrict__ ticket, uint32_t* __restrict__ packed, uint32_t* __restrict__ valid_out,
-              uint64_t* __restrict__ totals, uint32_t* __restrict__ need_slow) {
+              uint64_t* __restrict__ totals, uint32_t* __restrict__ need_slow, const uint32_t* __restrict__ run_if) {
+    if (run_if && *run_if == 0) return;              // (the regular-layout kernel took the call)
     __shared__ int s_wi[PK_THREADS / 32];
     __shared__ uint32_t s_w32[PK_THREADS / 32];
     __shared__ int s_carry_hdr;
@@ -674,6 +675,195 @@ k_pack_single(const uint8_t* __restrict__ in, size_t nbytes, size_t nunits, uint
     }
 }
 
+// ---- regular layout (default first attempt) ---------------------------------------------------------------------------
+// One record whose sequence lines all hold exactly W bases and end in '\n' (the last line may be shorter) — what
+// BioPython, samtools faidx and the reference's own split_genomes write.  Base j then sits at byte h + j + j / W
+// (h = length of the header line), so nothing has to be scanned: every thread turns the <= 35 bytes that hold its 32
+// bases into one validity word and two packed words, written once, coalesced, no atomics, no zero-fill beforehand.
+// The layout is not trusted: every thread checks that the line breaks of its byte span are exactly the predicted
+// ones and that the span holds no '\r' and no '>'; any deviation raises *irregular and the general single-pass
+// kernel (and behind it the three-pass one) redoes the call — decided on the device.
+constexpr int PKR_THREADS = 256;
+constexpr int PKR_BASES = PKR_THREADS * 32;                    // 8192 bases per CTA
+constexpr int PKR_MIN_W = 16;
+constexpr int PKR_STAGE = PKR_BASES + PKR_BASES / PKR_MIN_W + 64 + 16;   // bytes staged per CTA (<= 8784)
+constexpr int PKR_PROBE = 1 << 16;                             // the header line and the first sequence line end within 64 KiB
+
+struct PackReg {               // written by k_pack_probe
+    unsigned long long h, W, n;
+};
+
+__global__ void __launch_bounds__(256) k_pack_probe(const uint8_t* __restrict__ in, size_t nbytes, PackReg* reg,
+                                                    uint32_t* irregular, uint64_t* totals) {
+    __shared__ unsigned long long s_first, s_second;
+    if (threadIdx.x == 0) {
+        s_first = ~0ull;
+        s_second = ~0ull;
+    }
+    __syncthreads();
+    const size_t lim = min(nbytes, (size_t)PKR_PROBE);
+    unsigned long long f = ~0ull;
+    for (size_t i = threadIdx.x; i < lim; i += blockDim.x)
+        if (in[i] == '\n') { f = i; break; }
+    if (f != ~0ull) atomicMin(&s_first, f);
+    __syncthreads();
+    const unsigned long long h = s_first == ~0ull ? ~0ull : s_first + 1;
+    const size_t lim2 = h == ~0ull ? 0 : min(nbytes, (size_t)h + PKR_PROBE);
+    unsigned long long g = ~0ull;
+    for (size_t i = (size_t)h + threadIdx.x; i < lim2; i += blockDim.x)
+        if (in[i] == '\n') { g = i; break; }
+    if (g != ~0ull) atomicMin(&s_second, g);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bool ok = nbytes > 0 && in[0] == '>' && h != ~0ull;
+        unsigned long long W = 0, n = 0;
+        if (ok) {
+            const unsigned long long B = nbytes - h;
+            bool only_line = false;                               // the first sequence line is also the last
+            if (s_second != ~0ull) {
+                W = s_second - h;
+                only_line = s_second + 1 == nbytes;
+            } else if (lim2 == nbytes) {                          // a single line without a final '\n' (or no sequence)
+                W = B;
+                only_line = true;
+            } else ok = false;                                    // the first line is longer than the probe window
+            if (only_line && W < (unsigned long long)PKR_MIN_W) W = PKR_MIN_W;   // (any width >= its length describes it)
+            if (ok && B > 0) {
+                if (W < (unsigned long long)PKR_MIN_W) ok = false;
+                else {
+                    const unsigned long long L = W + 1, full = B / L, rem = B % L;
+                    n = full * W + rem - ((rem && in[nbytes - 1] == '\n') ? 1 : 0);
+                }
+            }
+        }
+        reg->h = ok ? h : 0;
+        reg->W = ok ? (W ? W : 1) : 1;
+        reg->n = ok ? n : 0;
+        if (!ok) *irregular = 1;
+        else {
+            totals[1] = 1;       // records
+            totals[2] = n;       // bases
+        }
+    }
+}
+
+// 4 bytes -> per-byte flags (bit b of each result = byte b): 2-bit codes, valid, line break, forbidden ('\r' or '>')
+__device__ __forceinline__ void pkr_word(uint32_t w, uint32_t& code8, uint32_t& v4, uint32_t& nl4, uint32_t& bad4) {
+    const uint32_t u = w & 0xdfdfdfdfu;
+    const uint32_t va = eq_bytes(u, 'A') | eq_bytes(u, 'C') | eq_bytes(u, 'G') | eq_bytes(u, 'T');
+    const uint32_t vb = va >> 7;
+    const uint32_t x = (w >> 1) & 0x03030303u;                                // A0 C1 G3 T2
+    const uint32_t code = (x ^ ((x >> 1) & 0x01010101u)) & (vb | (vb << 1));  // A0 C1 G2 T3, 0 if invalid
+    code8 = (code * 0x01041040u) >> 24;
+    v4 = ((vb * 0x01020408u) >> 24) & 0xfu;
+    nl4 = (((eq_bytes(w, '\n') >> 7) * 0x01020408u) >> 24) & 0xfu;
+    bad4 = ((((eq_bytes(w, '\r') | eq_bytes(w, '>')) >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+
+__global__ void __launch_bounds__(PKR_THREADS)
+k_pack_regular(const uint8_t* __restrict__ in, size_t nbytes, const PackReg* __restrict__ reg, size_t nwords,
+               uint32_t* __restrict__ packed, uint32_t* __restrict__ valid_out, uint64_t* __restrict__ totals,
+               uint32_t* __restrict__ irregular) {
+    __shared__ __align__(16) uint8_t s_in[PKR_STAGE];
+    if (*irregular) return;                                       // (set by the probe: uniform)
+    const unsigned long long h = reg->h, W = reg->W, n = reg->n;
+    const unsigned long long j0 = (unsigned long long)blockIdx.x * PKR_BASES;
+    const size_t t = (size_t)blockIdx.x * PKR_THREADS + threadIdx.x;
+    if (j0 >= n) {                                                // padding words past the sequence
+        if (t < nwords) {
+            valid_out[t] = 0;
+            *reinterpret_cast<uint2*>(packed + 2 * t) = make_uint2(0u, 0u);
+        }
+        return;
+    }
+    // ---- stage the CTA's bytes (aligned 16-byte loads; past the end of the input: '\n') ----
+    const unsigned long long q0 = j0 / W;
+    const size_t sb = (size_t)(h + j0 + q0);                      // first byte of the CTA
+    const size_t a0 = sb & ~(size_t)15;
+    for (int i = threadIdx.x; i < PKR_STAGE / 16; i += PKR_THREADS) {
+        const size_t pos = a0 + (size_t)i * 16;
+        uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        if (pos < nbytes) v = load_tile_bytes(in, nbytes, pos);
+        *reinterpret_cast<uint4*>(s_in + i * 16) = v;
+    }
+    __syncthreads();
+    const unsigned long long j = j0 + 32ull * threadIdx.x;
+    uint32_t vword = 0, bad = 0;
+    uint64_t bits = 0;
+    if (j < n) {
+        // (j / W, j % W) from the CTA's quotient: j = j0 + d, d < 8192, W >= 16
+        const uint32_t d = 32u * threadIdx.x;
+        const unsigned long long r0 = j0 - q0 * W + d;            // < W + 8192
+        const uint32_t dq = (uint32_t)(r0 / W), c0 = (uint32_t)(r0 - (unsigned long long)dq * W);
+        const size_t s = (size_t)(h + j + q0 + dq);               // byte of base j
+        const uint32_t nb = (uint32_t)min((unsigned long long)32, n - j);          // bases of this thread
+        // bytes of this thread: its bases, the line breaks after those that end a line, and (last thread) the final '\n'
+        const uint32_t nbrk = (c0 + nb) / (uint32_t)min(W, (unsigned long long)0xffffffffu);
+        uint32_t span = nb + nbrk;
+        uint64_t expect = 0;
+        {
+            unsigned long long pb = W - c0;                       // span index of the first predicted break
+            for (uint32_t b = 0; b < nbrk; b++, pb += W + 1) expect |= 1ull << pb;
+        }
+        if (j + nb == n && s + span < nbytes) {                   // bytes after the last base: only one final '\n' is regular
+            if (s + span + 1 == nbytes) { expect |= 1ull << span; span++; }
+            else bad = 1;
+        }
+        const uint32_t lo = (uint32_t)(s - a0);
+        const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(s_in + (lo & ~3u));
+        const uint32_t sh = 8u * (lo & 3u);
+        uint32_t raw[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) raw[i] = wsrc[i];
+        uint64_t code = 0, code_hi = 0;                            // 2 bits per byte: bytes 0..31, bytes 32..35
+        uint64_t vm = 0, nl = 0, bd = 0;                           // 1 bit per byte (36 bytes)
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            const uint32_t w = __funnelshift_r(raw[i], raw[i + 1], sh);
+            uint32_t c8, v4, n4, b4;
+            pkr_word(w, c8, v4, n4, b4);
+            if (i < 8) code |= (uint64_t)c8 << (8 * i);
+            else code_hi = c8;
+            vm |= (uint64_t)v4 << (4 * i);
+            nl |= (uint64_t)n4 << (4 * i);
+            bd |= (uint64_t)b4 << (4 * i);
+        }
+        const uint64_t smask = (1ull << span) - 1;                // span <= 35
+        if (((nl ^ expect) | bd) & smask) bad = 1;
+        // drop the line-break bytes (<= 3 inside the span), highest first, then keep the first nb bases
+        uint64_t drop = nl & smask;
+        uint64_t vbits = vm & smask;
+        while (drop) {
+            const int q = 63 - __clzll(drop);
+            drop &= ~(1ull << q);
+            vbits = (vbits & ((1ull << q) - 1)) | ((vbits >> (q + 1)) << q);
+            if (q < 32) {
+                const uint64_t lo2 = code & ((1ull << (2 * q)) - 1);
+                const uint64_t hi2 = (q == 31) ? 0ull : (code >> (2 * q + 2));
+                code = lo2 | (hi2 << (2 * q)) | ((code_hi & 3ull) << 62);
+                code_hi >>= 2;
+            } else {
+                const int qq = q - 32;
+                code_hi = (code_hi & ((1ull << (2 * qq)) - 1)) | ((code_hi >> (2 * qq + 2)) << (2 * qq));
+            }
+        }
+        const uint64_t keep = nb >= 32 ? ~0ull : ((1ull << (2 * nb)) - 1);
+        bits = code & keep;
+        vword = (uint32_t)(vbits & (nb >= 32 ? 0xffffffffull : ((1ull << nb) - 1)));
+    }
+    if (t < nwords) {
+        valid_out[t] = vword;
+        *reinterpret_cast<uint2*>(packed + 2 * t) = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
+    }
+    // ---- totals ----
+    uint32_t nv = spk_warp_sum_u32((uint32_t)__popc(vword));
+    const uint32_t anybad = __ballot_sync(0xffffffffu, bad != 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (nv) atomicAdd((unsigned long long*)&totals[0], (unsigned long long)nv);
+        if (anybad) atomicOr(irregular, 1u);
+    }
+}
+
 // the three-pass path runs only when the single pass gave up: its outputs and totals are reset on the device
 __global__ void __launch_bounds__(256) k_zero_if(const uint32_t* __restrict__ flag, uint4* __restrict__ p, size_t n16) {
     if (*flag == 0) return;
@@ -685,11 +875,12 @@ __global__ void k_reset_totals_if(const uint32_t* flag, uint64_t* totals) {
 }
 
 __global__ void k_write_info(const uint64_t* tile_off, size_t ntiles, const uint64_t* totals, const uint32_t* slow,
-                             uint64_t* info) {
+                             const uint32_t* irregular, uint64_t* info) {
     info[0] = (slow && *slow == 0) ? totals[2] : tile_off[ntiles];
     info[1] = totals[0];
     info[2] = totals[1];
-    info[3] = slow ? *slow : 1;      // 1: the three-pass path produced the result
+    // which kernel produced the result: 0 regular-layout, 2 general single pass, 1 three-pass
+    info[3] = (!slow || *slow) ? 1 : ((irregular && *irregular == 0) ? 0 : 2);
 }
 
 }  // namespace
@@ -724,15 +915,36 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
     cudaStream_t st = (cudaStream_t)stream;
     const size_t ntiles = (nbytes + PK_TILE - 1) / PK_TILE;
     const int sms = spk_num_sms();
-    SPK_CUDA(cudaMemsetAsync(w.totals, 0, 64, st));
+    SPK_CUDA(cudaMemsetAsync(w.totals, 0, 128, st));
     uint32_t* ticket = (uint32_t*)(w.totals + 4);
     uint32_t* need_slow = ticket + 1;
-    const char* mode = getenv("SPK_PACK_MODE");            // "3pass": skip the single pass (tests)
+    uint32_t* irregular = ticket + 2;
+    PackReg* reg = (PackReg*)(w.totals + 8);
+    const char* mode = getenv("SPK_PACK_MODE");            // tests: "3pass" = three-pass only, "single" = skip the regular-layout kernel
     const bool single = !(mode && mode[0] == '3');
-    // outputs are OR-accumulated: zero the whole tile-aligned extent (this is also the padding)
+    const bool regular = single && !(mode && mode[0] == 's') && ntiles > 0;
+    // outputs of the general kernels are OR-accumulated: the whole tile-aligned extent must be zero (this is also the
+    // padding); the regular-layout kernel writes every word of the extent itself
     const size_t pbytes = spk_packed_words(cap_bases) * 4, vbytes = spk_valid_words(cap_bases) * 4;
-    SPK_CUDA(cudaMemsetAsync(d_packed, 0, pbytes, st));
-    SPK_CUDA(cudaMemsetAsync(d_valid, 0, vbytes, st));
+    const uint32_t* run_single = nullptr;
+    if (regular) {
+        const size_t nwords = spk_valid_words(cap_bases);           // (packed words = 2 x validity words)
+        k_pack_probe<<<1, 256, 0, st>>>(d_ascii, nbytes, reg, irregular, w.totals);
+        SPK_LAUNCH_CHECK();
+        k_pack_regular<<<(unsigned)((nwords + PKR_THREADS - 1) / PKR_THREADS), PKR_THREADS, 0, st>>>(
+            d_ascii, nbytes, reg, nwords, d_packed, d_valid, w.totals, irregular);
+        SPK_LAUNCH_CHECK();
+        run_single = irregular;
+        k_zero_if<<<sms * 4, 256, 0, st>>>(irregular, (uint4*)d_packed, pbytes / 16);
+        SPK_LAUNCH_CHECK();
+        k_zero_if<<<sms * 4, 256, 0, st>>>(irregular, (uint4*)d_valid, vbytes / 16);
+        SPK_LAUNCH_CHECK();
+        k_reset_totals_if<<<1, 1, 0, st>>>(irregular, w.totals);
+        SPK_LAUNCH_CHECK();
+    } else {
+        SPK_CUDA(cudaMemsetAsync(d_packed, 0, pbytes, st));
+        SPK_CUDA(cudaMemsetAsync(d_valid, 0, vbytes, st));
+    }
     const uint32_t* run_if = nullptr;
     if (single && ntiles > 0) {
         uint64_t* status = (uint64_t*)w.tile_last_nl;      // (one 64-bit word per PK_SUB tiles fits the per-tile array)
@@ -740,7 +952,7 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
         SPK_CUDA(cudaMemsetAsync(status, 0, nunits * 8, st));
         const unsigned grid1 = (unsigned)min((size_t)sms * 6, nunits);
         k_pack_single<<<grid1, PK_THREADS, 0, st>>>(d_ascii, nbytes, nunits, status, ticket, d_packed, d_valid, w.totals,
-                                                    need_slow);
+                                                    need_slow, run_single);
         SPK_LAUNCH_CHECK();
         // fallback (lines longer than the look-back window), decided on the device: every kernel below returns at once
         // unless *need_slow is set
@@ -770,7 +982,7 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
                                                       w.tile_off, d_packed, d_valid, w.totals, run_if);
         SPK_LAUNCH_CHECK();
     }
-    k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, ntiles > 0 ? run_if : nullptr, d_info);
+    k_write_info<<<1, 1, 0, st>>>(w.tile_off, ntiles, w.totals, ntiles > 0 ? run_if : nullptr, run_single, d_info);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

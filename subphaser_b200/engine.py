@@ -95,13 +95,15 @@ def pack_fasta(d_ascii, nbytes, name=None, trim=True):
     info = _zeros(4, torch.int64)
     call("spk_pack_fasta", _p(d_ascii), nbytes, _p(packed), _p(valid), cap, _p(info), _p(ws), ws_bytes,
          _stream())
-    n_bases, n_valid, n_rec, _ = (int(x) for x in info.cpu().tolist())
+    n_bases, n_valid, n_rec, path = (int(x) for x in info.cpu().tolist())
     if trim:
         pw, vw = lib.spk_packed_words(max(n_bases, 1)), lib.spk_valid_words(max(n_bases, 1))
         packed = packed[:pw].clone()
         valid = valid[:vw].clone()
     del ws
-    return PackedSeq(packed, valid, n_bases, n_valid, n_rec, name)
+    seq = PackedSeq(packed, valid, n_bases, n_valid, n_rec, name)
+    seq.pack_path = ("regular", "3pass", "single")[path]       # which K1 kernel produced it (diagnostic)
+    return seq
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -231,19 +231,41 @@ def _unpack(seq):
     return codes
 
 
-@pytest.mark.parametrize("mode", ["single", "3pass"])
+@pytest.mark.parametrize("mode", ["regular", "single", "3pass"])
 def test_pack_matches_oracle_codes(mode, monkeypatch):
-    """K1: the single-pass kernel (decoupled look-back, local line state) and the three-pass fallback (lines longer than
-    the look-back window) give the oracle's code stream for wrapped, unwrapped, CRLF, multi-record and odd inputs."""
+    """K1: the regular-layout kernel (positions by arithmetic, layout verified), the single-pass kernel (decoupled
+    look-back, local line state) and the three-pass fallback (lines longer than the look-back window) give the oracle's
+    code stream for wrapped, unwrapped, CRLF, multi-record and odd inputs — each mode handing over to the next on the
+    device when the input is not what it handles."""
     if MODE[0] != "partitioned":
         pytest.skip("independent of the counter")
     from oracle import kmers
     from subphaser_b200 import engine
-    if mode == "3pass":
-        monkeypatch.setenv("SPK_PACK_MODE", "3pass")
+    if mode != "regular":
+        monkeypatch.setenv("SPK_PACK_MODE", mode)
     rng = np.random.default_rng(31)
     big = util.messy_seq(rng, 300_000)
-    cases = [
+    reg = []
+    for width in (16, 17, 31, 32, 33, 59, 60, 61, 64, 80, 127, 4096, 8191, 8192, 8193, 70000):
+        for n in (0, 1, width - 1, width, width + 1, 8192, 8192 * 3 + 5, 123_457):
+            body = big[:n]
+            lines = "\n".join(body[i:i + width] for i in range(0, len(body), width))
+            # (a first line longer than the 64-KiB probe window is left to the general kernels)
+            want_reg = width < 65536 or n < 65536
+            reg.append(((">c%d_%d some text\n" % (width, n) + lines + "\n").encode(), want_reg))
+            reg.append(((">c\n" + lines).encode(), want_reg))           # no final newline
+    reg += [
+        (b">a\n" + big[:1000].encode() + b"\n\n", None),                # blank line at the end
+        (b">a\n" + big[:1000].encode() + b"\n\n\n", False),
+        ((">a\n" + big[:60] + "\n" + big[60:100] + "\n" + big[100:160] + "\n").encode(), False),   # a short line in the middle
+        ((">a\n" + big[:60] + "\n" + big[60:120] + "\r\n").encode(), False),
+        ((">a\n" + big[:60] + "\n>" + big[60:119] + "\n").encode(), False),   # '>' at the beginning of a line: a second record
+        ((">a\n" + big[:30] + ">" + big[30:59] + "\n").encode(), False),      # '>' inside a line: an invalid base
+        (b">only a header", None),
+        (b">only a header\n", True),
+        ((">" + "h" * 70000 + "\n" + big[:100] + "\n").encode(), False),       # header longer than the probe window
+    ]
+    cases = reg + [(c, None) for c in [
         util.fasta([("a", big)]),                                   # 60-column lines: single pass
         util.fasta([("a", big)], width=100000),                     # lines of 100 kb: look-back window exceeded
         util.fasta([("a", big)], width=511), util.fasta([("a", big)], width=512), util.fasta([("a", big)], width=513),
@@ -253,11 +275,16 @@ def test_pack_matches_oracle_codes(mode, monkeypatch):
         b">a\n" + big[:4093].encode() + b"\n>b\n" + big[:100].encode(),          # header at a tile boundary, no final newline
         big[:20000].encode(),                                        # no header, no newline at all
         b"\n\n>x\n\nAC\n\nGT\n>y\n>z\nN\n",
-    ]
-    for fa in cases:
+    ]]
+    for ci, (fa, want_reg) in enumerate(cases):
         want, nrec = kmers.fasta_to_codes(fa)
         d, n = engine.to_device_bytes(fa)
         seq = engine.pack_fasta(d, n)
+        if mode == "regular" and want_reg is not None:
+            # wrapped single records take the arithmetic path, and its layout check rejects everything else
+            assert (seq.pack_path == "regular") == want_reg, (ci, fa[:40], len(fa), seq.pack_path)
+        elif mode != "regular":
+            assert seq.pack_path != "regular"
         assert seq.n_bases == len(want) and seq.n_records == nrec
         got = _unpack(seq)
         np.testing.assert_array_equal(got, np.minimum(want, 4))
