@@ -588,6 +588,186 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
     if ((tid & 31) == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
 }
 
+// ---- warp-private variant of k_map_bins_q<16-bit slots> ----------------------------------------------------------
+// The tile pipeline above synchronises 8 warps per 4096 bases (TMA into shared memory, one CTA barrier per tile); with
+// every position a dependent 16-byte gather from L2, the warps of a CTA finish a tile at different times and a third
+// of the issue slots went to waiting at that barrier.  Here a warp owns 512 consecutive positions at a time and
+// nothing is shared: lane l loads packed word l of the warp's 128-byte line (plus two tail words and 17 validity
+// words), neighbours' words arrive by shuffle, the next line is loaded into registers before the lookups of the
+// current one start.  No shared memory, no barrier.  Serves 16-bit slots, S <= 4, one record, no hit flags — the
+// genome-scale calls; everything else stays with k_map_bins_q.
+constexpr int MW_THREADS = 128;
+
+__global__ void __launch_bounds__(MW_THREADS, 6)
+k_map_bins_w(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, uint64_t n_bases, int k, MapArgs a,
+             QtArgs qa) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int WT = 32 * SPK_KMERS_PER_THREAD;                 // 512 positions per warp step
+    const int lane = threadIdx.x & 31;
+    const uint64_t nw = (uint64_t)gridDim.x * (MW_THREADS / 32);
+    uint64_t wt = (uint64_t)blockIdx.x * (MW_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t n_wt = (n_bases + WT - 1) / WT;
+    const SpkKmerParams kp = spk_kmer_params(k);
+    const int S = a.S;
+    const uint64_t rmask = (qa.mx.rbits >= 64) ? ~0ull : ((1ull << qa.mx.rbits) - 1);
+    const uint32_t hmask = (0xffffu << qa.sgbits) & 0xffffu;
+    const uint32_t HM = hmask * 0x10001u;                         // bits above the subgenome field, both halfwords
+    uint64_t n_hit = 0;
+
+    uint64_t pos0 = wt * WT + (uint64_t)lane * SPK_KMERS_PER_THREAD;
+    uint64_t bin = pos0 / a.bin_size;
+    uint64_t brem = pos0 - bin * a.bin_size;
+    uint64_t chk = 0, crem = 0;
+    if (a.chunk_size) {
+        chk = (pos0 + (uint64_t)(k - 1)) / a.chunk_size;
+        crem = (pos0 + (uint64_t)(k - 1)) - chk * a.chunk_size;
+    }
+    const uint64_t stride = nw * WT;
+    const uint64_t dbin = stride / a.bin_size, dbrem = stride - dbin * a.bin_size;
+    const uint64_t dchk = a.chunk_size ? stride / a.chunk_size : 0, dcrem = a.chunk_size ? stride - dchk * a.chunk_size : 0;
+
+    uint32_t pw = 0, pt = 0, vw = 0;
+    auto fetch = [&](uint64_t t, uint32_t& fw, uint32_t& ft, uint32_t& fv) {
+        fw = ft = fv = 0;
+        if (t < n_wt) {                                           // (both arrays are zero-padded past the sequence)
+            fw = __ldg(packed + t * 32 + lane);
+            if (lane < 2) ft = __ldg(packed + t * 32 + 32 + lane);
+            if (lane < 17) fv = __ldg(valid + t * 16 + lane);
+        }
+    };
+    fetch(wt, pw, pt, vw);
+    for (; wt < n_wt; wt += nw) {
+        uint32_t w1 = __shfl_down_sync(FULL, pw, 1), w2 = __shfl_down_sync(FULL, pw, 2);
+        const uint32_t t0 = __shfl_sync(FULL, pt, 0), t1 = __shfl_sync(FULL, pt, 1);
+        if (lane == 31) { w1 = t0; w2 = t1; }
+        else if (lane == 30) w2 = t0;
+        const uint32_t w0 = pw;
+        const uint32_t v0 = __shfl_sync(FULL, vw, lane >> 1), v1 = __shfl_sync(FULL, vw, (lane >> 1) + 1);
+        const uint64_t vbits = (((uint64_t)v1 << 32) | v0) >> ((lane & 1) * 16);
+        uint32_t npw, npt, nvw;
+        fetch(wt + nw, npw, npt, nvw);
+
+        const bool one_line = (brem + SPK_KMERS_PER_THREAD <= a.bin_size) &&
+                              (!a.chunk_size || crem + SPK_KMERS_PER_THREAD <= a.chunk_size);
+        const uint64_t line = bin + chk;
+        const uint32_t lo_f = (uint32_t)line, hi_f = (uint32_t)(line >> 32);
+        const uint32_t lo_0 = __shfl_sync(FULL, lo_f, 0), hi_0 = __shfl_sync(FULL, hi_f, 0);
+        const bool fast = __all_sync(FULL, one_line && lo_f == lo_0 && hi_f == hi_0);
+        if (fast) {
+            uint64_t key[SPK_KMERS_PER_THREAD];
+            uint32_t okmask;
+            spk_kmers_from_words(w0, w1, w2, vbits, kp, key, okmask);
+            uint32_t c01 = 0, c23 = 0, rare = 0;
+            constexpr int QB = 4;
+#pragma unroll
+            for (int j0 = 0; j0 < SPK_KMERS_PER_THREAD; j0 += QB) {
+                uint4 bv[QB];
+                uint32_t qq[QB];
+#pragma unroll
+                for (int jj = 0; jj < QB; jj++) {
+                    const int j = j0 + jj;
+                    const uint64_t h = qa.mx.fwd_light(key[j]);
+                    qq[jj] = (uint32_t)((h & rmask) << qa.sgbits) * 0x10001u;
+                    bv[jj] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    if ((okmask >> j) & 1u)
+                        bv[jj] = __ldg(reinterpret_cast<const uint4*>(qa.buckets) + (uint32_t)(h >> qa.mx.rbits));
+                }
+#pragma unroll
+                for (int jj = 0; jj < QB; jj++) {
+                    const int j = j0 + jj;
+                    const uint32_t w[4] = {bv[jj].x ^ qq[jj], bv[jj].y ^ qq[jj], bv[jj].z ^ qq[jj], bv[jj].w ^ qq[jj]};
+                    uint32_t z = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t t = w[i] & HM;
+                        const uint32_t zi = ~(((t & 0x7fff7fffu) + 0x7fff7fffu) | t) & 0x80008000u;   // exact zero-halfword flags
+                        z |= (i == 3) ? (zi & 0x8000u) : zi;        // slot 7 (high half of the last word) is the marker
+                    }
+                    const bool okj = (okmask >> j) & 1u;
+                    if (z && okj) {
+                        int sg = -1;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+                            if (lo < (uint32_t)S) sg = (int)lo;
+                            if (i < 3 && hi < (uint32_t)S) sg = (int)hi;
+                        }
+                        if (sg >= 0) {
+                            const uint32_t inc = 1u << ((sg & 1) * 16);
+                            if (sg & 2) c23 += inc;
+                            else c01 += inc;
+                        } else if ((bv[jj].w >> 16) != 0xffffu) rare |= 1u << j;
+                    } else if (okj && (bv[jj].w >> 16) != 0xffffu) rare |= 1u << j;
+                }
+            }
+            while (rare) {                                          // bucket overflowed at build time: the key may be in the stash
+                const int j = __ffs(rare) - 1;
+                rare &= rare - 1;
+                uint64_t sl = 0;
+                const int sg = qt_stash_lookup(qa, spk_kmer_of_words(w0, w1, w2, j, kp), sl);
+                if (sg >= 0) {
+                    const uint32_t inc = 1u << ((sg & 1) * 16);
+                    if (sg & 2) c23 += inc;
+                    else c01 += inc;
+                }
+            }
+            n_hit += (c01 & 0xffffu) + (c01 >> 16) + (c23 & 0xffffu) + (c23 >> 16);
+            c01 = __reduce_add_sync(FULL, c01);
+            c23 = __reduce_add_sync(FULL, c23);
+            if (lane == 0 && line < a.n_lines) {
+                const uint32_t c[4] = {c01 & 0xffffu, c01 >> 16, c23 & 0xffffu, c23 >> 16};
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++)
+                    if (c[q4] && q4 < S) atomicAdd(&a.line_counts[line * a.S + q4], c[q4]);
+            }
+        } else {
+            // a bin / chunk border inside the warp's 512 positions (~5 % of the steps): position by position
+            uint64_t x = ~vbits & ((1ull << (15 + k)) - 1);         // (validity as in spk_kmers_from_words)
+            if (x != 0) {
+                int covered = 1;
+                while (covered < k) {
+                    const int sh = min(covered, k - covered);
+                    x |= x >> sh;
+                    covered += sh;
+                }
+            }
+            uint32_t ok = (uint32_t)(~x) & 0xffffu;
+            while (ok) {
+                const int j = __ffs(ok) - 1;
+                ok &= ok - 1;
+                const uint64_t kj = spk_kmer_of_words(w0, w1, w2, j, kp);
+                const uint64_t h = qa.mx.fwd_light(kj);
+                QtBucket<true> bq;
+                bq.load(qa.buckets, (uint32_t)(h >> qa.mx.rbits));
+                int at = 0;
+                bool over;
+                int sg = bq.match((uint32_t)((h & rmask) << qa.sgbits), (uint32_t)S, at, over);
+                if (sg < 0 && over) {
+                    uint64_t sl = 0;
+                    sg = qt_stash_lookup(qa, kj, sl);
+                }
+                if (sg >= 0) {
+                    n_hit++;
+                    const uint64_t l = line_of(pos0 + j, k, a.bin_size, a.chunk_size);
+                    if (l < a.n_lines) atomicAdd(&a.line_counts[l * a.S + sg], 1u);
+                }
+            }
+        }
+        pw = npw; pt = npt; vw = nvw;
+        pos0 += stride;
+        bin += dbin;
+        brem += dbrem;
+        if (brem >= a.bin_size) { brem -= a.bin_size; bin++; }
+        if (a.chunk_size) {
+            chk += dchk;
+            crem += dcrem;
+            if (crem >= a.chunk_size) { crem -= a.chunk_size; chk++; }
+        }
+    }
+    n_hit = spk_warp_sum_u64(n_hit);
+    if (lane == 0 && n_hit && a.nhits) atomicAdd((unsigned long long*)a.nhits, (unsigned long long)n_hit);
+}
+
 // Circos._bed_density(stack=True) (Circos.py:737-741): window row += bin row
 __global__ void __launch_bounds__(256)
 k_stack_windows(const int64_t* __restrict__ line_counts, const uint32_t* __restrict__ line_window,
@@ -791,7 +971,12 @@ extern "C" int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid,
               d_line_counts, n_lines, d_hit_flags, d_nhits, d_rec_start, d_rec_line0, n_rec};
     QtArgs qa{d_buckets, slot_bits, bucket_bits, qt_sgbits(S), spk_make_mixer(k, bucket_bits), d_skeys, d_svals,
               sslots, pack_vals};
-    if (slot_bits == 16)
+    const char* mk = getenv("SPK_MAP_KERNEL");             // "tile": the CTA-tile kernel for every call (tests, A/B)
+    if (slot_bits == 16 && S <= 4 && !d_rec_start && !d_hit_flags && bucket_bits < 2 * k && !(mk && mk[0] == 't')) {
+        const uint64_t n_wt = (n_bases + 511) / 512;
+        const unsigned gridw = (unsigned)min((uint64_t)spk_num_sms() * 6, (n_wt + MW_THREADS / 32 - 1) / (MW_THREADS / 32));
+        k_map_bins_w<<<gridw, MW_THREADS, 0, (cudaStream_t)stream>>>(d_packed, d_valid, n_bases, k, a, qa);
+    } else if (slot_bits == 16)
         k_map_bins_q<true><<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
             (const uint8_t*)d_packed, (const uint8_t*)d_valid, n_bases, k, a, qa);
     else

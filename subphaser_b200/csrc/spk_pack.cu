@@ -693,6 +693,31 @@ struct PackReg {               // written by k_pack_probe
     unsigned long long h, W, n;
 };
 
+// first '\n' at or after `from` within [from, lim): 4-KiB rounds of one 16-byte load per thread, stopping at the first
+// round with a hit (the header and the first sequence line normally end within the first round)
+__device__ unsigned long long pkr_find_newline(const uint8_t* __restrict__ in, size_t nbytes, size_t from, size_t lim,
+                                               unsigned long long* s_min) {
+    for (size_t base = from & ~(size_t)15; base < lim; base += 256 * 16) {
+        const size_t pos = base + (size_t)threadIdx.x * 16;
+        unsigned long long f = ~0ull;
+        if (pos < lim) {
+            const uint4 v = load_tile_bytes(in, nbytes, pos);      // (bytes past the end read as '\n': bounded by lim below)
+#pragma unroll
+            for (int i = 15; i >= 0; i--) {
+                const uint32_t c = (word_of(v, i >> 2) >> (8 * (i & 3))) & 0xffu;
+                if (c == '\n' && pos + i >= from && pos + i < lim) f = pos + i;
+            }
+        }
+        if (f != ~0ull) atomicMin(s_min, f);
+        __syncthreads();
+        const unsigned long long cur = *s_min;
+        __syncthreads();                     // (everyone has read it before the next round may lower it)
+        if (cur != ~0ull) break;
+    }
+    __syncthreads();
+    return *s_min;
+}
+
 __global__ void __launch_bounds__(256) k_pack_probe(const uint8_t* __restrict__ in, size_t nbytes, PackReg* reg,
                                                     uint32_t* irregular, uint64_t* totals) {
     __shared__ unsigned long long s_first, s_second;
@@ -701,18 +726,10 @@ __global__ void __launch_bounds__(256) k_pack_probe(const uint8_t* __restrict__ 
         s_second = ~0ull;
     }
     __syncthreads();
-    const size_t lim = min(nbytes, (size_t)PKR_PROBE);
-    unsigned long long f = ~0ull;
-    for (size_t i = threadIdx.x; i < lim; i += blockDim.x)
-        if (in[i] == '\n') { f = i; break; }
-    if (f != ~0ull) atomicMin(&s_first, f);
-    __syncthreads();
-    const unsigned long long h = s_first == ~0ull ? ~0ull : s_first + 1;
+    const unsigned long long first = pkr_find_newline(in, nbytes, 0, min(nbytes, (size_t)PKR_PROBE), &s_first);
+    const unsigned long long h = first == ~0ull ? ~0ull : first + 1;
     const size_t lim2 = h == ~0ull ? 0 : min(nbytes, (size_t)h + PKR_PROBE);
-    unsigned long long g = ~0ull;
-    for (size_t i = (size_t)h + threadIdx.x; i < lim2; i += blockDim.x)
-        if (in[i] == '\n') { g = i; break; }
-    if (g != ~0ull) atomicMin(&s_second, g);
+    if (h != ~0ull) pkr_find_newline(in, nbytes, (size_t)h, lim2, &s_second);
     __syncthreads();
     if (threadIdx.x == 0) {
         bool ok = nbytes > 0 && in[0] == '>' && h != ~0ull;

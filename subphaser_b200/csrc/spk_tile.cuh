@@ -75,12 +75,10 @@ __device__ __forceinline__ uint32_t spk_rev2_32(uint32_t x) {
 //   forward_j = (rev2(W) >> 2(48-k-j)) & kmask          (rev2 = order of the 2-bit groups reversed)
 // rev2(W) is shifted once per thread by the k-dependent 2(33-k) bits, so every per-position shift is a
 // compile-time constant: 2 funnel shifts + 2 masks per word instead of a 64-bit shift/or/and chain.
-__device__ __forceinline__ void spk_kmers_from_t(const uint32_t* pk, const uint32_t* vd, const int tid,
-                                                 const SpkKmerParams& p, uint64_t (&key)[SPK_KMERS_PER_THREAD],
-                                                 uint32_t& okmask) {
-    const uint32_t w0 = pk[tid], w1 = pk[tid + 1], w2 = pk[tid + 2];
-    const uint32_t v0 = vd[tid >> 1], v1 = vd[(tid >> 1) + 1];
-    const uint64_t vbits = (((uint64_t)v1 << 32) | v0) >> ((tid & 1) * 16);
+// (w0, w1, w2: the three packed words that hold the thread's 48-base window; vbits: its validity bits, bit 0 = base 0)
+__device__ __forceinline__ void spk_kmers_from_words(const uint32_t w0, const uint32_t w1, const uint32_t w2,
+                                                     const uint64_t vbits, const SpkKmerParams& p,
+                                                     uint64_t (&key)[SPK_KMERS_PER_THREAD], uint32_t& okmask) {
     const uint32_t klo = (uint32_t)p.kmask, khi = (uint32_t)(p.kmask >> 32);
 
     const uint32_t n0 = ~w0, n1 = ~w1, n2 = ~w2;
@@ -112,6 +110,25 @@ __device__ __forceinline__ void spk_kmers_from_t(const uint32_t* pk, const uint3
         }
     }
     okmask = (uint32_t)(~x) & 0xffffu;
+}
+
+__device__ __forceinline__ void spk_kmers_from_t(const uint32_t* pk, const uint32_t* vd, const int tid,
+                                                 const SpkKmerParams& p, uint64_t (&key)[SPK_KMERS_PER_THREAD],
+                                                 uint32_t& okmask) {
+    const uint32_t v0 = vd[tid >> 1], v1 = vd[(tid >> 1) + 1];
+    spk_kmers_from_words(pk[tid], pk[tid + 1], pk[tid + 2], (((uint64_t)v1 << 32) | v0) >> ((tid & 1) * 16), p, key,
+                         okmask);
+}
+
+// canonical k-mer starting at base o (< 16) of the window held in (w0, w1, w2)
+__device__ __forceinline__ uint64_t spk_kmer_of_words(const uint32_t w0, const uint32_t w1, const uint32_t w2, int o,
+                                                      const SpkKmerParams& p) {
+    const int sh = 2 * o;
+    const uint64_t lo = ((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh);
+    const uint64_t le = lo & p.kmask;
+    const uint64_t rc = (~lo) & p.kmask;
+    const uint64_t fwd = spk_rev2(le) >> (64 - 2 * p.k);
+    return fwd < rc ? fwd : rc;
 }
 
 __device__ __forceinline__ void spk_kmers_from(const uint32_t* pk, const uint32_t* vd, const SpkKmerParams& p,

@@ -98,8 +98,11 @@ def pack_fasta(d_ascii, nbytes, name=None, trim=True):
     n_bases, n_valid, n_rec, path = (int(x) for x in info.cpu().tolist())
     if trim:
         pw, vw = lib.spk_packed_words(max(n_bases, 1)), lib.spk_valid_words(max(n_bases, 1))
-        packed = packed[:pw].clone()
-        valid = valid[:vw].clone()
+        if pw < 0.9 * packed.numel():          # (a chromosome file is ~98 % bases: not worth a 0.26-GB copy)
+            packed = packed[:pw].clone()
+            valid = valid[:vw].clone()
+        else:
+            packed, valid = packed[:pw], valid[:vw]
     del ws
     seq = PackedSeq(packed, valid, n_bases, n_valid, n_rec, name)
     seq.pack_path = ("regular", "3pass", "single")[path]       # which K1 kernel produced it (diagnostic)

@@ -575,8 +575,14 @@ def test_map_bins_vs_oracle_mapper(k):
             os.environ["SPK_QT_MEAN"] = qt_mean
         try:
             sig = engine.SigTable(torch.from_numpy(keys.view(np.int64).copy()).cuda(), torch.from_numpy(sgs).cuda(), k)
+            # without per-entry hit flags the genome-scale kernel runs (k_map_bins_w: warp-private, 16-bit slots)
+            sig_w = engine.SigTable(torch.from_numpy(keys.view(np.int64).copy()).cuda(), torch.from_numpy(sgs).cuda(), k,
+                                    track_hits=False)
         finally:
             os.environ.pop("SPK_QT_MEAN", None)
+        got_w, nh_w = engine.map_bins(ps, sig_w, 3, bin_size, chunk)
+        assert nh_w == hits
+        np.testing.assert_array_equal(got_w.cpu().numpy().view(np.uint32), want)
         if qt_mean and k == 9:   # (wider k: the remainder width, not the load, fixes the bucket count)
             assert sig.bucket and int((sig.skeys != -1).sum().item()) > 0          # the stash is really in use
         got, nh = engine.map_bins(ps, sig, 3, bin_size, chunk)
