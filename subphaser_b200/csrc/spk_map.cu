@@ -598,7 +598,7 @@ k_map_bins_q(const uint8_t* __restrict__ packed, const uint8_t* __restrict__ val
 // genome-scale calls; everything else stays with k_map_bins_q.
 constexpr int MW_THREADS = 128;
 
-__global__ void __launch_bounds__(MW_THREADS, 6)
+__global__ void __launch_bounds__(MW_THREADS, 8)
 k_map_bins_w(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ valid, uint64_t n_bases, int k, MapArgs a,
              QtArgs qa) {
     constexpr uint32_t FULL = 0xffffffffu;
@@ -654,19 +654,44 @@ k_map_bins_w(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ v
         const uint32_t lo_0 = __shfl_sync(FULL, lo_f, 0), hi_0 = __shfl_sync(FULL, hi_f, 0);
         const bool fast = __all_sync(FULL, one_line && lo_f == lo_0 && hi_f == hi_0);
         if (fast) {
-            uint64_t key[SPK_KMERS_PER_THREAD];
+            // k-mers as in spk_kmers_from_words, but batch by batch inside a ROLLED loop (run-time shift amounts): the
+            // fully unrolled body was 44 KB of code, and with every warp at a different place in it the warps stalled
+            // on instruction fetch more than on anything else
+            const uint32_t klo = (uint32_t)kp.kmask, khi = (uint32_t)(kp.kmask >> 32);
+            const uint32_t n0 = ~w0, n1 = ~w1, n2 = ~w2;
+            uint32_t a0 = spk_rev2_32(w2), a1 = spk_rev2_32(w1), a2 = spk_rev2_32(w0);
+            const int s = 2 * (33 - k);
+            if (s >= 64) { a0 = a2; a1 = 0; a2 = 0; }
+            else if (s >= 32) { a0 = a1; a1 = a2; a2 = 0; }
+            const uint32_t sl5 = (uint32_t)s & 31u;
+            const uint32_t f0 = __funnelshift_r(a0, a1, sl5), f1 = __funnelshift_r(a1, a2, sl5), f2 = a2 >> sl5;
             uint32_t okmask;
-            spk_kmers_from_words(w0, w1, w2, vbits, kp, key, okmask);
+            {
+                uint64_t x = ~vbits & ((1ull << (15 + k)) - 1);
+                if (x != 0) {
+                    int covered = 1;
+                    while (covered < k) {
+                        const int sh = min(covered, k - covered);
+                        x |= x >> sh;
+                        covered += sh;
+                    }
+                }
+                okmask = (uint32_t)(~x) & 0xffffu;
+            }
             uint32_t c01 = 0, c23 = 0, rare = 0;
             constexpr int QB = 4;
-#pragma unroll
+#pragma unroll 1
             for (int j0 = 0; j0 < SPK_KMERS_PER_THREAD; j0 += QB) {
                 uint4 bv[QB];
                 uint32_t qq[QB];
 #pragma unroll
                 for (int jj = 0; jj < QB; jj++) {
                     const int j = j0 + jj;
-                    const uint64_t h = qa.mx.fwd_light(key[j]);
+                    const uint32_t sf = 2u * (15u - (uint32_t)j), sr = 2u * (uint32_t)j;
+                    const uint32_t flo = __funnelshift_r(f0, f1, sf) & klo, fhi = __funnelshift_r(f1, f2, sf) & khi;
+                    const uint32_t rlo = __funnelshift_r(n0, n1, sr) & klo, rhi = __funnelshift_r(n1, n2, sr) & khi;
+                    const uint64_t fwd = ((uint64_t)fhi << 32) | flo, rc = ((uint64_t)rhi << 32) | rlo;
+                    const uint64_t h = qa.mx.fwd_light(fwd < rc ? fwd : rc);
                     qq[jj] = (uint32_t)((h & rmask) << qa.sgbits) * 0x10001u;
                     bv[jj] = make_uint4(~0u, ~0u, ~0u, ~0u);
                     if ((okmask >> j) & 1u)
@@ -974,7 +999,7 @@ extern "C" int spk_map_bins_q(const uint32_t* d_packed, const uint32_t* d_valid,
     const char* mk = getenv("SPK_MAP_KERNEL");             // "tile": the CTA-tile kernel for every call (tests, A/B)
     if (slot_bits == 16 && S <= 4 && !d_rec_start && !d_hit_flags && bucket_bits < 2 * k && !(mk && mk[0] == 't')) {
         const uint64_t n_wt = (n_bases + 511) / 512;
-        const unsigned gridw = (unsigned)min((uint64_t)spk_num_sms() * 6, (n_wt + MW_THREADS / 32 - 1) / (MW_THREADS / 32));
+        const unsigned gridw = (unsigned)min((uint64_t)spk_num_sms() * 8, (n_wt + MW_THREADS / 32 - 1) / (MW_THREADS / 32));
         k_map_bins_w<<<gridw, MW_THREADS, 0, (cudaStream_t)stream>>>(d_packed, d_valid, n_bases, k, a, qa);
     } else if (slot_bits == 16)
         k_map_bins_q<true><<<grid, SPK_TILE_THREADS, 0, (cudaStream_t)stream>>>(
