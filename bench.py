@@ -53,7 +53,10 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock and throttle reasons sampled every 200 ms during the timed region: the counters of the recipe's
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,...,clocks_event_reasons.* -lms 200` line, read through NVML in
+    this process (a polling nvidia-smi child cost the stages that synchronise with the host 10-70 ms per step: its
+    start-up and every query compete with the bench's own thread); the nvidia-smi child is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -62,8 +65,23 @@ class ClockSampler:
         self.index = str(index)
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
 
     def start(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            p = torch.cuda.get_device_properties(int(self.index))
+            bdf = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, h, smax)
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
@@ -72,18 +90,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h, smax = self.nvml
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self.stop_flag:
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if (r & m) else "Not Active" for _, m in bits]
+                self.lines.append((time.perf_counter(), ",".join([self.index, str(sm), str(smax), "0", hex(r)] + flags)))
+            except Exception:
+                pass
+            time.sleep(0.2)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Samples from here on count (the sampler is started earlier, during the warm-up: the start-up of NVML /
+        nvidia-smi — attaching to all GPUs of the box, ~1 s in the first process after boot — holds driver locks)."""
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.25)
-        self.proc.terminate()
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for ts, l in self.lines:
+            if ts < getattr(self, "t0", 0.0):
+                continue
             t = [x.strip() for x in l.split(",")]
             if len(t) < 9:
                 continue
@@ -96,7 +139,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_replica(args, threads):
@@ -362,11 +405,13 @@ def main():
         return float(t.item()), res
 
     # ---- device-resident arm: warm-up, then exactly K timed steps ----
-    for _ in range(args.warmup):
-        hotpath.run(dev_inputs, host_inputs=False, **kw)
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                 # (started before the warm-up, see ClockSampler.mark)
+    for _ in range(args.warmup):
+        hotpath.run(dev_inputs, host_inputs=False, **kw)
+    if rank == 0:
+        sampler.mark()
     timer = hotpath.StageTimer(True)
     launches0 = lib.spk_launch_count()
     secs, res = timed(args.steps, False, dev_inputs, timer)
@@ -398,7 +443,7 @@ def main():
             traffic = None
     avg_launch_s = (stage_ms.get("count", 0.0) / max(stage_n.get("count", 1), 1)) / 1e3
     roofline = {"bound": "hbm",
-                "kernel": "spk_pcount_canonical_ex = k_v3_l1 + k_v3_plan + k_v3_chunks + k_v3_l2 + k_part_count32<gather> "
+                "kernel": "spk_pcount_canonical_ex = k_v3_l1 + k_v3_plan + k_v3_chunks + k_v3_l2 + k_part_count32<gather, list> "
                           "(one call per chromosome)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

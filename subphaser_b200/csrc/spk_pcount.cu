@@ -1143,7 +1143,7 @@ constexpr uint32_t PC_EMPTY32 = 0xffffffffu;
 constexpr int PC_RETRY = 2048;          // retry-queue capacity (entries beyond it probe inline)
 
 // full linear probing from the slot after home (out of line: rare in the first-probe loop, dense in the drain)
-// -> bit 0: created the key, bit 1: its count reached `lower`, bit 2: table full
+// -> bit 0: created the key, bit 1: its count reached `lower` (bits 16..: slot + 1), bit 2: table full
 __device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cnt, uint32_t r, uint32_t lower) {
     constexpr uint32_t TMASK = PC_SLOTS - 1;
     uint32_t s = ((r & TMASK) + 1) & TMASK;
@@ -1151,7 +1151,7 @@ __device__ __noinline__ uint32_t pc32_probe_rest(uint32_t* s_key, uint32_t* s_cn
         const uint32_t old = atomicCAS(&s_key[s], PC_EMPTY32, r);
         if (old == PC_EMPTY32 || old == r) {
             const uint32_t c = atomicAdd(&s_cnt[s], 1u);
-            return ((old == PC_EMPTY32) ? 1u : 0u) | ((c + 1 == lower) ? 2u : 0u);
+            return ((old == PC_EMPTY32) ? 1u : 0u) | ((c + 1 == lower) ? (2u | ((s + 1) << 16)) : 0u);
         }
         s = (s + 1) & TMASK;
     }
@@ -1201,16 +1201,27 @@ struct GatherIn {
     int b2;
 };
 
-template <bool GATHER, bool VER>
+// LIST (default when no count histogram is wanted): the 32-bit key / count arrays of the sweep kernel, but the slots
+// to dump are collected where a count reaches `lower` (u16 list, as in the versioned table), read into registers
+// before the reservation, and the table is then cleared with stores only — the sweep's 2 x 64 KB of shared-memory
+// loads, its per-slot tests and two of the six barriers per partition are gone.  More kept keys than the list holds
+// (a partition of nothing but repeats, lower_count 1): that partition is swept as before.
+constexpr int PC_RETRY_L = 1792;         // retry queue of the list kernel (same 72 KB per CTA as the sweep kernel)
+constexpr int PC_KEEP_L = 512;           // kept-slot list capacity (2 per thread)
+
+template <bool GATHER, bool VER, bool LIST = false>
 __global__ void __launch_bounds__(PC_THREADS, 3)
 k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ pstart, uint64_t P, Mixer mx,
                CountOut o, uint32_t retry_cap, GatherIn gi) {
+    static_assert(!(VER && LIST), "one table variant");
     extern __shared__ __align__(16) uint8_t s_raw[];
+    constexpr int QN = VER ? PC_RETRY_V : (LIST ? PC_RETRY_L : PC_RETRY);   // words of s_q
+    constexpr uint32_t KEEPN = VER ? PC_KEEP : PC_KEEP_L;
     uint32_t* s_key = (uint32_t*)s_raw;
     uint32_t* s_cnt = s_key + PC_SLOTS;
-    uint32_t* s_q = s_cnt + PC_SLOTS;                    // [PC_RETRY]; retry_cap <= PC_RETRY entries are used as queue
+    uint32_t* s_q = s_cnt + PC_SLOTS;                    // [QN]; retry_cap <= QN entries are used as queue
     unsigned long long* s_tab = (unsigned long long*)s_raw;           // VER: [PC_SLOTS] 64-bit slots (same bytes)
-    uint16_t* s_keep = (uint16_t*)(s_q + (VER ? PC_RETRY_V : PC_RETRY));   // VER: [PC_KEEP]
+    uint16_t* s_keep = (uint16_t*)(s_q + QN);            // VER / LIST: [KEEPN]
     __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_hist[256];
     __shared__ uint64_t s_red[4][PC_THREADS / 32];
@@ -1240,9 +1251,9 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
     const int rbits = mx.rbits;                                      // VER: <= 31
     const uint32_t gmax = VER ? ((rbits >= 32) ? 0u : (0xffffffffu >> rbits)) : 0u;
     uint32_t gen = 1;                                                // VER: generation of the current partition
-    auto keep_slot = [&](uint32_t slot) {                            // VER: this key is dumped: remember where it lives
+    auto keep_slot = [&](uint32_t slot) {                            // VER / LIST: this key is dumped: remember where it lives
         const uint32_t at = atomicAdd(&s_nlist, 1u);
-        if (at < PC_KEEP) s_keep[at] = (uint16_t)slot;
+        if (at < KEEPN) s_keep[at] = (uint16_t)slot;
     };
 
     // first probe only; false: the home slot belongs to another key
@@ -1272,7 +1283,11 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
             if (old == PC_EMPTY32 || old == r) {
                 const uint32_t c = atomicAdd(&s_cnt[s], 1u);
                 my_new += (old == PC_EMPTY32) ? 1u : 0u;
-                my_keep += (c + 1 == lower) ? 1u : 0u;
+                if constexpr (LIST) {
+                    if (c + 1 == lower) keep_slot(s);
+                } else {
+                    my_keep += (c + 1 == lower) ? 1u : 0u;
+                }
                 return true;
             }
             return false;
@@ -1287,7 +1302,11 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         } else {
             const uint32_t f = pc32_probe_rest(s_key, s_cnt, r, lower);
             my_new += f & 1u;
-            my_keep += (f >> 1) & 1u;
+            if constexpr (LIST) {
+                if (f >> 16) keep_slot((f >> 16) - 1);
+            } else {
+                my_keep += (f >> 1) & 1u;
+            }
             n_fail += (f >> 2) & 1u;
         }
     };
@@ -1472,8 +1491,27 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         }
         my_new = my_keep = 0;
         __syncthreads();
+        // LIST: the kept entries go to registers now (the table is cleared by other threads after the next barrier)
+        constexpr int KR = PC_KEEP_L / PC_THREADS;
+        uint32_t lk[KR], lc[KR];
+        const uint32_t nl_list = LIST ? s_nlist : 0u;
+        const bool list_ok = LIST && nl_list <= KEEPN && !o.histo;          // (block-uniform)
+        if constexpr (LIST) {
+            if (list_ok) {
+#pragma unroll
+                for (int q = 0; q < KR; q++) {
+                    const uint32_t i = (uint32_t)tid + (uint32_t)q * PC_THREADS;
+                    lk[q] = lc[q] = 0;
+                    if (i < nl_list) {
+                        const uint32_t sl = s_keep[i];
+                        lk[q] = s_key[sl];
+                        lc[q] = s_cnt[sl];
+                    }
+                }
+            }
+        }
         if (tid == 0) {
-            const uint32_t total = VER ? s_nlist : s_nkeep;
+            const uint32_t total = (VER || LIST) ? s_nlist : s_nkeep;
             const uint64_t base = total ? atomicAdd((unsigned long long*)o.cursor, (unsigned long long)total) : 0ull;
             s_base = base;
             if (o.pindex) {
@@ -1532,6 +1570,41 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
             gen++;
             if (tid == 0) s_nlist = 0;
         }
+        if constexpr (LIST) {
+            if (list_ok) {
+                // ---- write the kept entries from registers, clear the table with stores only; no further barrier ----
+#pragma unroll
+                for (int q = 0; q < KR; q++) {
+                    const uint32_t i = (uint32_t)tid + (uint32_t)q * PC_THREADS;
+                    if (i < nl_list) {
+                        nge++;
+                        sumge += lc[q];
+                        if (pbase + i < o.cap) {
+                            o.keys[pbase + i] = mx.inv((p << mx.rbits) | (uint64_t)lk[q]);
+                            o.counts[pbase + i] = lc[q];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < SWEEP; i++) {
+                    const uint32_t idx = (i * PC_THREADS + tid) * 4;
+                    *reinterpret_cast<uint4*>(s_key + idx) = make_uint4(PC_EMPTY32, PC_EMPTY32, PC_EMPTY32, PC_EMPTY32);
+                    *reinterpret_cast<uint4*>(s_cnt + idx) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                if (tid == 0) {
+                    s_nq = 0;
+                    s_nkeep = 0;
+                    s_ndist = 0;
+                    s_nlist = 0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < PC_PF; u++) cur[u] = nxt[u];
+                beg = nbeg; end = nend; nbeg = nnbeg; nend = nnend;
+                cnc = nnc; nnc = nnnc;
+                continue;
+            }
+        }
         // ---- sweep: histogram, write the dump, clear ----
 #pragma unroll 1
         for (int i = 0; i < (VER ? 0 : SWEEP); i++) {
@@ -1564,7 +1637,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
 #pragma unroll
                 for (int e = 0; e < 4; e++)
                     if ((km >> e) & 1u) {
-                        if (pos < PC_RETRY / 2) {            // staged (the retry queue is free by now): written below by all lanes
+                        if (pos < (uint32_t)(QN / 2)) {      // staged (the retry queue is free by now): written below by all lanes
                             s_q[2 * pos] = ks[e];
                             s_q[2 * pos + 1] = cs[e];
                         } else {
@@ -1582,7 +1655,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
         if constexpr (!VER) __syncthreads();
         if constexpr (!VER)
         {   // kept entries: f^-1 and the global stores with every lane busy (a lane-at-a-time version cost a third of the kernel)
-            const uint32_t nst = min(s_wr, (uint32_t)(PC_RETRY / 2));
+            const uint32_t nst = min(s_wr, (uint32_t)(QN / 2));
             for (uint32_t i = tid; i < nst; i += PC_THREADS) {
                 const uint32_t r = s_q[2 * i], cnt = s_q[2 * i + 1];
                 nge++;
@@ -1599,6 +1672,7 @@ k_part_count32(const uint32_t* __restrict__ buf, const uint32_t* __restrict__ ps
             s_nkeep = 0;
             s_ndist = 0;
             s_wr = 0;
+            if constexpr (LIST) s_nlist = 0;
         }
         __syncthreads();
 #pragma unroll
@@ -1672,7 +1746,8 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
         // chromosome: its 64-bit shared-memory loads + CAS cost more than the sweep they save), kept for comparison.
         const char* ev = getenv("SPK_PCOUNT_TABLE");
         const bool ver = (ev && ev[0] == 'v');
-        uint32_t retry_cap = ver ? PC_RETRY_V : PC_RETRY;
+        const bool list = !ver && !(ev && ev[0] == 's') && !d_histo;       // "sweep": the sweep kernel for every call
+        uint32_t retry_cap = ver ? PC_RETRY_V : (list ? PC_RETRY_L : PC_RETRY);
         if (const char* e = getenv("SPK_PCOUNT_RETRY_CAP")) {       // test hook: exercise the queue-overflow paths
             const long v = atol(e);
             if (v >= 0 && v < (long)retry_cap) retry_cap = (uint32_t)v;
@@ -1685,6 +1760,11 @@ int run_plan(const PcPlan& pl, const uint8_t* pk, const uint8_t* vl, uint32_t lo
             SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smv));
             k_part_count32<true, true><<<cgrid3, PC_THREADS, smv, st>>>((const uint32_t*)buf, nullptr, pl.P, pl.mx, o,
                                                                        retry_cap, gi);
+        } else if (list) {
+            const size_t sml = (size_t)PC_SLOTS * 8 + PC_RETRY_L * 4 + PC_KEEP_L * 2;
+            SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sml));
+            k_part_count32<true, false, true><<<cgrid3, PC_THREADS, sml, st>>>((const uint32_t*)buf, nullptr, pl.P, pl.mx, o,
+                                                                              retry_cap, gi);
         } else {
             SPK_CUDA(cudaFuncSetAttribute(k_part_count32<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           PC_SLOTS * 8 + PC_RETRY * 4));

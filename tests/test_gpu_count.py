@@ -185,9 +185,10 @@ def test_v3_descriptor_pipeline(k, gmax, pbits, monkeypatch):
     fa = util.fasta([("big", "".join(parts))])
     for lower in (1, 3):
         d3 = _check_forced(fa, k, lower, gmax, pbits)
-        monkeypatch.setenv("SPK_PCOUNT_TABLE", "versioned")      # the no-clear / no-sweep variant of the counter's table
-        _check_forced(fa, k, lower, gmax, pbits)
-        monkeypatch.delenv("SPK_PCOUNT_TABLE")
+        for variant in ("versioned", "sweep"):      # (default: the kept-slot-list kernel) no-clear table; full sweep
+            monkeypatch.setenv("SPK_PCOUNT_TABLE", variant)
+            _check_forced(fa, k, lower, gmax, pbits)
+            monkeypatch.delenv("SPK_PCOUNT_TABLE")
         monkeypatch.setenv("SPK_PCOUNT_PIPE", "v2")
         d2 = _check_forced(fa, k, lower, gmax, pbits)
         monkeypatch.delenv("SPK_PCOUNT_PIPE")
@@ -291,7 +292,7 @@ def test_pack_matches_oracle_codes(mode, monkeypatch):
         assert seq.n_valid == int(np.sum(want < 4))
 
 
-@pytest.mark.parametrize("table", ["sweep", "versioned"])
+@pytest.mark.parametrize("table", ["list", "sweep", "versioned"])
 def test_v3_dense_partitions_and_histogram(table, monkeypatch):
     """70 Mb of random sequence, lower_count 1: ~3000 distinct k-mers per partition, all dumped (more than the
     kept-slot list of the versioned table holds: scan fallback), and the count histogram path (`histo_len`)."""
@@ -319,3 +320,10 @@ def test_v3_dense_partitions_and_histogram(table, monkeypatch):
     h = dump.histo.cpu().numpy()
     want = np.bincount(np.minimum(ocounts, 299).astype(np.int64), minlength=300)
     np.testing.assert_array_equal(h[1:], want[1:])
+    # without a histogram ("list": every partition keeps more slots than its list holds -> swept one by one)
+    dump2 = engine.count_packed(ps, 17, 1, table=table)
+    keys2, counts2 = dump2.to_host()
+    o2 = np.argsort(keys2, kind="stable")
+    np.testing.assert_array_equal(keys2[o2], okeys)
+    np.testing.assert_array_equal(counts2[o2], ocounts)
+    np.testing.assert_array_equal(dump2.pindex.cpu().numpy()[1::2], dump.pindex.cpu().numpy()[1::2])
