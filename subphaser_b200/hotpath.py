@@ -689,28 +689,38 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         M = len(dm)
     if M == 0:
         raise ValueError("0 kmer remained after filtering. Please reset the filter options.")
-    if world > 1:
-        # Only the report (bootstrap, PCA input, the matrix handed back to the host) needs every row on every rank:
-        # the 0.6-GB all-gather + sort runs on the side stream over its own communicator, underneath the Gram pass,
-        # the t-test and the map stage, which work on the row shards.
-        side_pg = _SCRATCH.get("side_pg")
-        if side_pg is None or side_pg[0] != world:
-            side_pg = (world, dist.new_group(ranks=list(range(world))))
-            _SCRATCH["side_pg"] = side_pg
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            e_g = t.start("gather_rows_side")
-            dm = gather_rows(shard, m_rows, n_fold_all, dist, dev, group=side_pg[1])
-            t.stop(e_g)
-    # the differential matrix is final here: its device->host copy (0.6 GB for wheat, ~25 ms of PCIe) runs on a
-    # side stream underneath the clustering and mapping stages
+    # Side work is ENQUEUED where the host would otherwise wait for the main stream (just before a stage's result is
+    # read back): enqueuing it first kept the main stream idle for the ~1 ms of host time its launches take.
+    ev_rows = torch.cuda.Event()
+    ev_rows.record()                                   # the row shard (world 1: the matrix) is final here
     host_copy = None
     return_host = bool(return_host) and rank == 0     # one copy of the results leaves the node, not one per rank
-    if return_host:
-        d2h_stream = _SCRATCH.setdefault("d2h_stream", torch.cuda.Stream())
-        d2h_stream.wait_stream(side if world > 1 else torch.cuda.current_stream())
-        with torch.cuda.stream(d2h_stream):
-            host_copy = (_to_host_pinned("dm_keys", dm.keys), _to_host_pinned("dm_norm", dm.norm))
+
+    def enqueue_gather_and_copy():
+        nonlocal dm, host_copy
+        if world > 1:
+            # Only the report (bootstrap, PCA input, the matrix handed back to the host) needs every row on every
+            # rank: the 0.6-GB all-gather + sort runs on the side stream over its own communicator, underneath the
+            # Gram pass, the t-test and the map stage, which work on the row shards.
+            side_pg = _SCRATCH.get("side_pg")
+            if side_pg is None or side_pg[0] != world:
+                side_pg = (world, dist.new_group(ranks=list(range(world))))
+                _SCRATCH["side_pg"] = side_pg
+            side.wait_event(ev_rows)
+            with torch.cuda.stream(side):
+                e_g = t.start("gather_rows_side")
+                dm = gather_rows(shard, m_rows, n_fold_all, dist, dev, group=side_pg[1])
+                t.stop(e_g)
+        # the differential matrix is final: its device->host copy (0.6 GB for wheat) runs on its own stream
+        # underneath the clustering and mapping stages
+        if return_host:
+            d2h_stream = _SCRATCH.setdefault("d2h_stream", torch.cuda.Stream())
+            if world > 1:
+                d2h_stream.wait_stream(side)
+            else:
+                d2h_stream.wait_event(ev_rows)
+            with torch.cuda.stream(d2h_stream):
+                host_copy = (_to_host_pinned("dm_keys", dm.keys), _to_host_pinned("dm_norm", dm.norm))
 
     # ---- K5-K8 cluster ---------------------------------------------------------------------------------
     if nsg is None:
@@ -729,45 +739,55 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     # the side stream would block the host until the side stream reaches it, and the main stream would idle)
     order = torch.tensor([i for _, i in sorted(zip(labels, range(n)))], dtype=torch.int32, device=dev)
     lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
+    ev_lab = torch.cuda.Event()
+    ev_lab.record()
+    enqueue_gather_and_copy()
     lab_full_h = lab_full[0].cpu().numpy()
     t.stop(e)
     # The bootstrap (replicates x tiny K-Means problems: a few dozen thread blocks for milliseconds) and the PCA (one
     # thread block) only feed the report; nothing downstream waits for them.  They run on a side stream underneath the
     # t-test, the table build and the map kernels and are joined at the end.
     R = int(replicates)
-    side.wait_stream(torch.cuda.current_stream())
     lab_b = ari = vm = None
-    with torch.cuda.stream(side):
-        e_side = t.start("bootstrap_pca_side")
-        if Z is None and R > 0:
-            Z = engine.zscore_rows(dm.norm)
-        if R > 0:
-            d_idx = engine.resample_indices(M, R, seed)        # same generator state on every rank: same plan
-            if world > 1:
-                # the replicates are independent: rank r clusters replicates [lo, hi) and the labels are all-gathered
-                per = (R + world - 1) // world
-                lo, hi = min(rank * per, R), min((rank + 1) * per, R)
-                lab_pad = torch.zeros(per, n, dtype=torch.int32, device=dev)
-                if hi > lo:
-                    Gb = engine.gram_batched(Z, d_idx[lo:hi].contiguous())
-                    lab_loc, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1, r0=lo)
-                    lab_pad[:hi - lo] = lab_loc
-                lab_all = torch.empty(world * per, n, dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(lab_all.view(-1), lab_pad.view(-1), group=_SCRATCH["side_pg"][1])
-                lab_b = lab_all[:R].contiguous()
-            else:
-                Gb = engine.gram_batched(Z, d_idx)
-                lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
-            ari, vm = engine.cluster_scores(lab_full[0], lab_b)
-        eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
-        t.stop(e_side)
+    eig = scores = pratio = None
+
+    def enqueue_bootstrap():
+        nonlocal Z, lab_b, ari, vm, eig, scores, pratio
+        side.wait_event(ev_lab)
+        with torch.cuda.stream(side):
+            e_side = t.start("bootstrap_pca_side")
+            if Z is None and R > 0:
+                Z = engine.zscore_rows(dm.norm)
+            if R > 0:
+                d_idx = engine.resample_indices(M, R, seed)        # same generator state on every rank: same plan
+                if world > 1:
+                    # the replicates are independent: rank r clusters replicates [lo, hi), the labels are all-gathered
+                    per = (R + world - 1) // world
+                    lo, hi = min(rank * per, R), min((rank + 1) * per, R)
+                    lab_pad = torch.zeros(per, n, dtype=torch.int32, device=dev)
+                    if hi > lo:
+                        Gb = engine.gram_batched(Z, d_idx[lo:hi].contiguous())
+                        lab_loc, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1, r0=lo)
+                        lab_pad[:hi - lo] = lab_loc
+                    lab_all = torch.empty(world * per, n, dtype=torch.int32, device=dev)
+                    dist.all_gather_into_tensor(lab_all.view(-1), lab_pad.view(-1), group=_SCRATCH["side_pg"][1])
+                    lab_b = lab_all[:R].contiguous()
+                else:
+                    Gb = engine.gram_batched(Z, d_idx)
+                    lab_b, _ = engine.kmeans_gram(Gb, nsg, order=order, seed=seed + 1)
+                ari, vm = engine.cluster_scores(lab_full[0], lab_b)
+            eig, scores, pratio = engine.pca_gram(G, min(nsg, n))
+            t.stop(e_side)
+
     e = t.start("ttest")
     if len(shard):
         best, pval, means = engine.ttest_groups(shard.norm, lab_full_h.tolist(), nsg)
+        enqueue_bootstrap()
         keep = ~(pval > max_pval)
         sig_keys = shard.keys[keep].contiguous()
         sig_vals = best[keep].to(torch.uint8).contiguous()
     else:
+        enqueue_bootstrap()
         sig_keys = torch.empty(0, dtype=torch.int64, device=dev)
         sig_vals = torch.empty(0, dtype=torch.uint8, device=dev)
     if world > 1:
