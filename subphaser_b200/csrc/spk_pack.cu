@@ -764,17 +764,21 @@ __global__ void __launch_bounds__(256) k_pack_probe(const uint8_t* __restrict__ 
     }
 }
 
-// 4 bytes -> per-byte flags (bit b of each result = byte b): 2-bit codes, valid, line break, forbidden ('\r' or '>')
-__device__ __forceinline__ void pkr_word(uint32_t w, uint32_t& code8, uint32_t& v4, uint32_t& nl4, uint32_t& bad4) {
-    const uint32_t u = w & 0xdfdfdfdfu;
-    const uint32_t va = eq_bytes(u, 'A') | eq_bytes(u, 'C') | eq_bytes(u, 'G') | eq_bytes(u, 'T');
-    const uint32_t vb = va >> 7;
-    const uint32_t x = (w >> 1) & 0x03030303u;                                // A0 C1 G3 T2
-    const uint32_t code = (x ^ ((x >> 1) & 0x01010101u)) & (vb | (vb << 1));  // A0 C1 G2 T3, 0 if invalid
+// 4 bytes -> 2-bit codes (8 bits), valid flags (4 bits), "special" flags (4 bits: byte < 0x40 — every line break,
+// '\r' and '>' is one; the caller looks at those bytes individually, there is about one per thread).
+// x = bits 2..1 of a letter tell A, C, T, G apart (0, 1, 2, 3); a byte is a valid base iff its upper-case form equals
+// the letter x stands for — one byte-permute looks the four expected letters up, another the four codes.
+__device__ __forceinline__ void pkr_word(uint32_t w, uint32_t& code8, uint32_t& v4, uint32_t& sp4) {
+    const uint32_t x = (w >> 1) & 0x03030303u;
+    const uint32_t t = x | (x >> 4);
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);                     // nibble i = x of byte i
+    const uint32_t expect = __byte_perm(0x47544341u, 0u, sel);            // 'A' 'C' 'T' 'G' by x
+    const uint32_t vb = zero_bytes(expect ^ (w & 0xdfdfdfdfu)) >> 7;      // 1 per valid byte
+    const uint32_t code = __byte_perm(0x02030100u, 0u, sel) & (vb | (vb << 1));   // A0 C1 G2 T3, 0 if invalid
     code8 = (code * 0x01041040u) >> 24;
     v4 = ((vb * 0x01020408u) >> 24) & 0xfu;
-    nl4 = (((eq_bytes(w, '\n') >> 7) * 0x01020408u) >> 24) & 0xfu;
-    bad4 = ((((eq_bytes(w, '\r') | eq_bytes(w, '>')) >> 7) * 0x01020408u) >> 24) & 0xfu;
+    const uint32_t sp = (~(w | (w << 1)) & 0x80808080u) >> 7;
+    sp4 = ((sp * 0x01020408u) >> 24) & 0xfu;
 }
 
 __global__ void __launch_bounds__(PKR_THREADS)
@@ -782,28 +786,54 @@ k_pack_regular(const uint8_t* __restrict__ in, size_t nbytes, const PackReg* __r
                uint32_t* __restrict__ packed, uint32_t* __restrict__ valid_out, uint64_t* __restrict__ totals,
                uint32_t* __restrict__ irregular) {
     __shared__ __align__(16) uint8_t s_in[PKR_STAGE];
-    if (*irregular) return;                                       // (set by the probe: uniform)
+    // Persistent CTAs: the parameters are read once, and the bytes of the CTA's NEXT tile are loaded into registers
+    // before the current tile is classified (a tile per CTA spent its life waiting: parameters, then bytes, then a
+    // barrier — 19 stalled warps per issued instruction on the load scoreboard).
+    const uint32_t irr0 = *irregular;
     const unsigned long long h = reg->h, W = reg->W, n = reg->n;
-    const unsigned long long j0 = (unsigned long long)blockIdx.x * PKR_BASES;
-    const size_t t = (size_t)blockIdx.x * PKR_THREADS + threadIdx.x;
-    if (j0 >= n) {                                                // padding words past the sequence
+    if (irr0) return;                                             // (set by the probe: uniform)
+    constexpr int NV = (PKR_STAGE / 16 + PKR_THREADS - 1) / PKR_THREADS;   // 16-byte loads per thread and tile (3)
+    const size_t n_tiles = (nwords + PKR_THREADS - 1) / PKR_THREADS;
+    uint32_t nv_total = 0, anybad = 0;
+    uint4 pre[NV];
+    auto tile_origin = [&](size_t tile, unsigned long long& j0, unsigned long long& q0, size_t& a0) {
+        j0 = (unsigned long long)tile * PKR_BASES;
+        q0 = j0 / W;
+        a0 = (size_t)(h + j0 + q0) & ~(size_t)15;
+    };
+    auto prefetch = [&](size_t tile) {
+        unsigned long long pj0, pq0;
+        size_t pa0;
+        tile_origin(tile, pj0, pq0, pa0);
+#pragma unroll
+        for (int q = 0; q < NV; q++) {
+            const int i = threadIdx.x + q * PKR_THREADS;
+            const size_t pos = pa0 + (size_t)i * 16;
+            pre[q] = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+            if (tile < n_tiles && pj0 < n && i < PKR_STAGE / 16 && pos < nbytes) pre[q] = load_tile_bytes(in, nbytes, pos);
+        }
+    };
+    prefetch(blockIdx.x);
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    unsigned long long j0, q0;
+    size_t a0;
+    tile_origin(tile, j0, q0, a0);
+    const size_t t = tile * PKR_THREADS + threadIdx.x;
+    if (j0 >= n) {                                                // padding words past the sequence (block-uniform)
         if (t < nwords) {
             valid_out[t] = 0;
             *reinterpret_cast<uint2*>(packed + 2 * t) = make_uint2(0u, 0u);
         }
-        return;
+        continue;
     }
-    // ---- stage the CTA's bytes (aligned 16-byte loads; past the end of the input: '\n') ----
-    const unsigned long long q0 = j0 / W;
-    const size_t sb = (size_t)(h + j0 + q0);                      // first byte of the CTA
-    const size_t a0 = sb & ~(size_t)15;
-    for (int i = threadIdx.x; i < PKR_STAGE / 16; i += PKR_THREADS) {
-        const size_t pos = a0 + (size_t)i * 16;
-        uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-        if (pos < nbytes) v = load_tile_bytes(in, nbytes, pos);
-        *reinterpret_cast<uint4*>(s_in + i * 16) = v;
+    // ---- stage the tile's bytes (aligned 16-byte loads, already in registers; past the end of the input: '\n') ----
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+        const int i = threadIdx.x + q * PKR_THREADS;
+        if (i < PKR_STAGE / 16) *reinterpret_cast<uint4*>(s_in + i * 16) = pre[q];
     }
     __syncthreads();
+    prefetch(tile + gridDim.x);
     const unsigned long long j = j0 + 32ull * threadIdx.x;
     uint32_t vword = 0, bad = 0;
     uint64_t bits = 0;
@@ -833,20 +863,28 @@ k_pack_regular(const uint8_t* __restrict__ in, size_t nbytes, const PackReg* __r
 #pragma unroll
         for (int i = 0; i < 10; i++) raw[i] = wsrc[i];
         uint64_t code = 0, code_hi = 0;                            // 2 bits per byte: bytes 0..31, bytes 32..35
-        uint64_t vm = 0, nl = 0, bd = 0;                           // 1 bit per byte (36 bytes)
+        uint64_t vm = 0, spm = 0;                                  // 1 bit per byte (36 bytes)
 #pragma unroll
         for (int i = 0; i < 9; i++) {
             const uint32_t w = __funnelshift_r(raw[i], raw[i + 1], sh);
-            uint32_t c8, v4, n4, b4;
-            pkr_word(w, c8, v4, n4, b4);
+            uint32_t c8, v4, s4;
+            pkr_word(w, c8, v4, s4);
             if (i < 8) code |= (uint64_t)c8 << (8 * i);
             else code_hi = c8;
             vm |= (uint64_t)v4 << (4 * i);
-            nl |= (uint64_t)n4 << (4 * i);
-            bd |= (uint64_t)b4 << (4 * i);
+            spm |= (uint64_t)s4 << (4 * i);
         }
         const uint64_t smask = (1ull << span) - 1;                // span <= 35
-        if (((nl ^ expect) | bd) & smask) bad = 1;
+        uint64_t nl = 0;
+        spm &= smask;
+        while (spm) {                                             // the bytes below 0x40 of the span, one by one
+            const int q = __ffsll((long long)spm) - 1;
+            spm &= spm - 1;
+            const uint8_t c = s_in[lo + q];
+            if (c == '\n') nl |= 1ull << q;
+            else if (c == '\r' || c == '>') bad = 1;
+        }
+        if (nl != expect) bad = 1;                                // (expect has no bit at or above span)
         // drop the line-break bytes (<= 3 inside the span), highest first, then keep the first nb bases
         uint64_t drop = nl & smask;
         uint64_t vbits = vm & smask;
@@ -872,9 +910,13 @@ k_pack_regular(const uint8_t* __restrict__ in, size_t nbytes, const PackReg* __r
         valid_out[t] = vword;
         *reinterpret_cast<uint2*>(packed + 2 * t) = make_uint2((uint32_t)bits, (uint32_t)(bits >> 32));
     }
+    nv_total += (uint32_t)__popc(vword);
+    anybad |= bad;
+    __syncthreads();                                              // s_in is rewritten by the next tile
+    }
     // ---- totals ----
-    uint32_t nv = spk_warp_sum_u32((uint32_t)__popc(vword));
-    const uint32_t anybad = __ballot_sync(0xffffffffu, bad != 0);
+    uint64_t nv = spk_warp_sum_u64((uint64_t)nv_total);
+    anybad = __ballot_sync(0xffffffffu, anybad != 0);
     if ((threadIdx.x & 31) == 0) {
         if (nv) atomicAdd((unsigned long long*)&totals[0], (unsigned long long)nv);
         if (anybad) atomicOr(irregular, 1u);
@@ -948,7 +990,7 @@ extern "C" int spk_pack_fasta(const uint8_t* d_ascii, size_t nbytes, uint32_t* d
         const size_t nwords = spk_valid_words(cap_bases);           // (packed words = 2 x validity words)
         k_pack_probe<<<1, 256, 0, st>>>(d_ascii, nbytes, reg, irregular, w.totals);
         SPK_LAUNCH_CHECK();
-        k_pack_regular<<<(unsigned)((nwords + PKR_THREADS - 1) / PKR_THREADS), PKR_THREADS, 0, st>>>(
+        k_pack_regular<<<(unsigned)min((size_t)sms * 5, (nwords + PKR_THREADS - 1) / PKR_THREADS), PKR_THREADS, 0, st>>>(
             d_ascii, nbytes, reg, nwords, d_packed, d_valid, w.totals, irregular);
         SPK_LAUNCH_CHECK();
         run_single = irregular;
