@@ -247,13 +247,6 @@ int spk_fasta_record_starts(const uint8_t* d_ascii, uint64_t nbytes, uint64_t* d
 int spk_fasta_wrap_check(const uint8_t* d_ascii, uint64_t beg, uint64_t end, uint32_t width, uint64_t* d_out,
                          void* stream);
 
-/*
- * spk_store_to_host: device buffer -> PINNED host buffer (cudaHostAlloc / cudaHostRegister memory) written by a small
- * kernel over PCIe instead of the copy engine, asynchronous on `stream`.  Used for the bulk results of a run (the
- * differential matrix the reference writes as `.kmer.mat`, Jellyfish.py:515-520) so that the small result reads of
- * the following stages do not queue behind a 0.6-GB cudaMemcpyAsync.  Both pointers 16-byte aligned.
- */
-int spk_store_to_host(const void* d_src, void* h_dst, uint64_t nbytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Text wire formats on the device.  spk_format_rows writes the rows of `.kmer.mat` (kind 0:

@@ -52,7 +52,6 @@ SIGNATURES = {
     "spk_tot_select_pass": (c_i, [c_p, c_p, c_u64, c_i, c_u64, c_p, c_p]),
     "spk_fasta_record_starts": (c_i, [c_p, c_u64, c_p, c_u64, c_p, c_p]),
     "spk_fasta_wrap_check": (c_i, [c_p, c_u64, c_u64, c_u32, c_p, c_p]),
-    "spk_store_to_host": (c_i, [c_p, c_p, c_u64, c_p]),
     "spk_format_rows": (c_i, [c_p, c_p, c_u64, c_i, c_i, c_i, c_p, c_u64, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "spk_sort_workspace_bytes": (c_sz, [c_u64]),
     "spk_sort_pairs_u64": (c_i, [c_p, c_p, c_p, c_p, c_u64, c_i, c_p, c_sz, c_p]),

@@ -44,28 +44,6 @@ k_fasta_wrap_check(const uint8_t* __restrict__ in, uint64_t beg, uint64_t end, u
     }
 }
 
-
-// Results -> pinned host memory by stores from a few CTAs instead of the copy engine.  The differential matrix of a
-// wheat run is 0.6 GB; as one (or many chunked) cudaMemcpyAsync it occupies the device-to-host copy engine for
-// ~13 ms, and the path's small result reads (labels, sizes, masks: each a host synchronisation the next stage waits
-// for) queue behind it in FIFO order.  Posted PCIe writes issued by SMs do not touch that queue.
-__global__ void __launch_bounds__(256)
-k_store_to_host(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n16, const uint8_t* __restrict__ srcb,
-                uint8_t* __restrict__ dstb, uint64_t nbytes) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n16; i += 4 * stride) {          // four loads in flight per thread, then four stores
-        const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride),
-                    d = __ldcs(src + i + 3 * stride);
-        dst[i] = a;
-        dst[i + stride] = b;
-        dst[i + 2 * stride] = c;
-        dst[i + 3 * stride] = d;
-    }
-    for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
-    for (uint64_t j = n16 * 16 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nbytes; j += stride) dstb[j] = srcb[j];
-}
-
 }  // namespace
 
 extern "C" int spk_fasta_record_starts(const uint8_t* d_ascii, uint64_t nbytes, uint64_t* d_pos, uint64_t cap,
@@ -90,19 +68,6 @@ extern "C" int spk_fasta_wrap_check(const uint8_t* d_ascii, uint64_t beg, uint64
     SPK_CHECK_ARG(d_ascii, "null input");
     const unsigned grid = (unsigned)min((end - beg + 255) / 256, (uint64_t)spk_num_sms() * 32);
     k_fasta_wrap_check<<<grid, 256, 0, st>>>(d_ascii, beg, end, width, (unsigned long long*)d_out);
-    SPK_LAUNCH_CHECK();
-    return SPK_OK;
-}
-
-// d_src (device) -> h_dst (pinned host memory, device-accessible under unified addressing), asynchronous on `stream`.
-extern "C" int spk_store_to_host(const void* d_src, void* h_dst, uint64_t nbytes, void* stream) {
-    SPK_CHECK_ARG(d_src && h_dst, "null pointer");
-    SPK_CHECK_ARG(((uintptr_t)d_src & 15) == 0 && ((uintptr_t)h_dst & 15) == 0, "buffers must be 16-byte aligned");
-    if (nbytes == 0) return SPK_OK;
-    void* dev_view = nullptr;
-    SPK_CUDA(cudaHostGetDevicePointer(&dev_view, h_dst, 0));
-    k_store_to_host<<<64, 256, 0, (cudaStream_t)stream>>>((const uint4*)d_src, (uint4*)dev_view, nbytes / 16,
-                                                          (const uint8_t*)d_src, (uint8_t*)dev_view, nbytes);
     SPK_LAUNCH_CHECK();
     return SPK_OK;
 }

@@ -753,8 +753,8 @@ class SigTable:
         return int(((f & 1) != 0).sum().item() + ((f & 2) != 0).sum().item())
 
 
-def map_bins(seq, sig, S, bin_size, chunk_size, record_lengths=None):
-    """-> (line_counts int32 [n_lines, S] device, n_hits).
+def map_bins(seq, sig, S, bin_size, chunk_size, record_lengths=None, sync=True):
+    """-> (line_counts int32 [n_lines, S] device, n_hits) — n_hits as a device tensor when sync=False.
     record_lengths (multi-record FASTA): bases of every record in file order; the rows of record r then start at
     sum(spk_map_num_lines(L_q) for q < r) and use the record's own coordinates (Seqs.py:121-153)."""
     require_cuda()
@@ -790,7 +790,7 @@ def map_bins(seq, sig, S, bin_size, chunk_size, record_lengths=None):
         call("spk_map_bins", _p(seq.packed), _p(seq.valid), seq.n_bases, sig.k, _p(sig.skeys), _p(sig.svals),
              sig.slots, S, _p(sig.filter), sig.filter_bits, sig.pack_vals, int(bin_size), int(chunk_size), _p(counts),
              max(n_lines, 1), _p(sig.hit_flags), _p(nhits), _stream())
-    return counts[:n_lines], int(nhits.item())
+    return counts[:n_lines], (int(nhits.item()) if sync else nhits)
 
 
 def stack_windows(line_counts, line_window, n_windows):

@@ -466,12 +466,20 @@ def _to_host_pinned(name, t):
     if buf is None or buf.numel() < n or buf.dtype != t.dtype:
         buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
         _PINNED[name] = buf
-    src = t.contiguous().view(-1)
-    if src.is_cuda and n * src.element_size() >= (1 << 20):
-        _lib.call("spk_store_to_host", engine._p(src), buf.data_ptr(), n * src.element_size(), engine._stream())
-    else:
-        buf[:n].copy_(src, non_blocking=True)
+    _copy_chunked(buf[:n], t.contiguous().view(-1))
     return buf[:n].view(t.shape)
+
+
+def _host_copy_plan(name, t):
+    """Like _to_host_pinned, but nothing is copied yet: -> (host view, [(dst piece, src piece), ...])."""
+    n = t.numel()
+    buf = _PINNED.get(name)
+    if buf is None or buf.numel() < n or buf.dtype != t.dtype:
+        buf = torch.empty(max(n, 1), dtype=t.dtype, pin_memory=True)
+        _PINNED[name] = buf
+    src = t.contiguous().view(-1)
+    step = max(_COPY_CHUNK // max(src.element_size(), 1), 1)
+    return buf[:n].view(t.shape), [(buf[off:min(off + step, n)], src[off:min(off + step, n)]) for off in range(0, n, step)]
 
 
 class StageTimer:
@@ -694,10 +702,11 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     ev_rows = torch.cuda.Event()
     ev_rows.record()                                   # the row shard (world 1: the matrix) is final here
     host_copy = None
+    copy_pieces = []
     return_host = bool(return_host) and rank == 0     # one copy of the results leaves the node, not one per rank
 
-    def enqueue_gather_and_copy():
-        nonlocal dm, host_copy
+    def enqueue_gather():
+        nonlocal dm
         if world > 1:
             # Only the report (bootstrap, PCA input, the matrix handed back to the host) needs every row on every
             # rank: the 0.6-GB all-gather + sort runs on the side stream over its own communicator, underneath the
@@ -711,16 +720,31 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
                 e_g = t.start("gather_rows_side")
                 dm = gather_rows(shard, m_rows, n_fold_all, dist, dev, group=side_pg[1])
                 t.stop(e_g)
-        # the differential matrix is final: its device->host copy (0.6 GB for wheat) runs on its own stream
-        # underneath the clustering and mapping stages
+                ev_rows.record()                       # (now: the FULL matrix is final)
+
+    def enqueue_host_copy():
+        # The device->host copy of the differential matrix (0.6 GB for wheat, ~13 ms of PCIe) runs on its own stream
+        # underneath the map stage — and only there: while it is in flight every small result read of the main
+        # stream (labels, sizes, masks: each a host synchronisation) arrives ~10 ms late, whichever engine moves the
+        # bulk, so it is started after the last of those reads.
+        # The pieces are handed to the copy engine a few at a time from inside the map loop (pump_host_copy): issuing
+        # all of them at once kept the host in the driver for the duration of the transfer, with nothing queued on the
+        # main stream.
+        nonlocal host_copy, copy_pieces
         if return_host:
             d2h_stream = _SCRATCH.setdefault("d2h_stream", torch.cuda.Stream())
-            if world > 1:
-                d2h_stream.wait_stream(side)
-            else:
-                d2h_stream.wait_event(ev_rows)
-            with torch.cuda.stream(d2h_stream):
-                host_copy = (_to_host_pinned("dm_keys", dm.keys), _to_host_pinned("dm_norm", dm.norm))
+            d2h_stream.wait_event(ev_rows)
+            hk, pk = _host_copy_plan("dm_keys", dm.keys)
+            hn, pn = _host_copy_plan("dm_norm", dm.norm)
+            host_copy = (hk, hn)
+            copy_pieces = pk + pn
+
+    def pump_host_copy(k):
+        if copy_pieces:
+            with torch.cuda.stream(_SCRATCH["d2h_stream"]):
+                for _ in range(min(k, len(copy_pieces))):
+                    dst, src = copy_pieces.pop(0)
+                    dst.copy_(src, non_blocking=True)
 
     # ---- K5-K8 cluster ---------------------------------------------------------------------------------
     if nsg is None:
@@ -741,7 +765,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     lab_full, inertia = engine.kmeans_gram(G, nsg, order=order, seed=seed)
     ev_lab = torch.cuda.Event()
     ev_lab.record()
-    enqueue_gather_and_copy()
+    enqueue_gather()
     lab_full_h = lab_full[0].cpu().numpy()
     t.stop(e)
     # The bootstrap (replicates x tiny K-Means problems: a few dozen thread blocks for milliseconds) and the PCA (one
@@ -799,11 +823,14 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     sig = engine.SigTable(sig_keys, sig_vals, k, track_hits=False, S=nsg)
     t.stop(e)
     win_counts = {}
+    enqueue_host_copy()
+    per_iter = (len(copy_pieces) + max(len(mine), 1) - 1) // max(len(mine), 1)
     e_loop = t.start("_loop_map_stack")
     for i in mine:
         e = t.start("map")
-        lines, nh = engine.map_bins(seqs[i], sig, nsg, bin_size, chunk_size)
+        lines, _ = engine.map_bins(seqs[i], sig, nsg, bin_size, chunk_size, sync=False)   # (no host read in this loop)
         t.stop(e)
+        pump_host_copy(per_iter)
         # ---- stack lines into windows (Circos.stack_matrix) on the device ----
         e = t.start("stack")
         L = seqs[i].n_bases
@@ -816,6 +843,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         win_counts[i] = out[:nwin]
         t.stop(e)
     t.stop(e_loop)
+    pump_host_copy(len(copy_pieces))
     if keep_seqs is not None:
         keep_seqs.update(seqs)
 

@@ -671,18 +671,3 @@ def test_fold_histogram_matches_numpy():
         np.testing.assert_array_equal(fh.edges, edges)
         assert fh.xlim == float(np.percentile(data, 99))
         assert fh.percentile(50) == float(np.percentile(data, 50)) and fh.percentile(0) == data.min()
-
-
-@pytest.mark.parametrize("nbytes", [16, 4096 + 7, (1 << 22) + 13, 50_000_001])
-def test_store_to_host_equals_memcpy(nbytes):
-    """spk_store_to_host (SM stores into pinned host memory) moves the same bytes as cudaMemcpyAsync."""
-    import torch
-    from subphaser_b200 import engine, _lib
-    g = torch.Generator(device="cuda")
-    g.manual_seed(nbytes)
-    src = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device="cuda", generator=g)
-    dst = torch.zeros(nbytes + 32, dtype=torch.uint8, pin_memory=True)
-    _lib.call("spk_store_to_host", engine._p(src), dst.data_ptr(), nbytes, engine._stream())
-    torch.cuda.synchronize()
-    assert torch.equal(dst[:nbytes], src.cpu())
-    assert int(dst[nbytes:].sum()) == 0
