@@ -257,7 +257,7 @@ def parity_at_scale(plan, threads, sample_bases):
     return out
 
 
-def e2e_dropin(repeats=2):
+def e2e_dropin(repeats=3):
     """The path through the reference-facing MODULE surface, from a genome file on disk to the result files on disk:
     Seqs.split_genomes -> Jellyfish.run_jellyfish_dumps -> JellyfishDumps.to_matrix / filter / write_matrix -> Cluster
     (+ bootstrap) -> output_kmers -> Seqs.map_kmer3 -> Circos.stack_matrix -> Stats.enrich_bin (pipeline.run_hot_path
