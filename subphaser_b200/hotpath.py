@@ -281,8 +281,8 @@ def exchange_rows(dm, n_union_local, dist, dev):
 
 
 def gather_sig(keys, vals, key_bits, dist, dev):
-    """Significant k-mers of every rank's row shard -> all of them on every rank, ascending (the table the map stage
-    probes is built from the same list on every rank): one all_reduce of the sizes, two all_gathers, one sort."""
+    """Significant k-mers of every rank's row shard -> all of them on every rank (the table the map stage probes is
+    built from the same list on every rank): one all_reduce of the sizes, two all_gathers."""
     rank, world = dist.get_rank(), dist.get_world_size()
     sz = torch.zeros(world, dtype=torch.int64, device=dev)
     sz[rank] = int(keys.numel())
@@ -291,10 +291,8 @@ def gather_sig(keys, vals, key_bits, dist, dev):
     ident = list(range(world))
     kk = _gather_concat({rank: keys.contiguous()}, m, ident, world, dist, dev, torch.int64)
     vv = _gather_concat({rank: vals.contiguous()}, m, ident, world, dist, dev, torch.uint8)
-    allk = torch.cat([kk[r] for r in range(world)])
-    allv = torch.cat([vv[r] for r in range(world)])
-    order = engine.argsort_keys(allk, key_bits)
-    return allk[order].contiguous(), allv[order].contiguous()
+    # (rank order, not k-mer order: the probe table built from the list does not depend on the order of its keys)
+    return torch.cat([kk[r] for r in range(world)]), torch.cat([vv[r] for r in range(world)])
 
 
 def exchange_windows(win_counts, n, nsg, owner, dist, dev, nw_known=None):
