@@ -280,10 +280,26 @@ def exchange_rows(dm, n_union_local, dist, dev):
     return gather_rows(dm, m, n_fold, dist, dev), n_union
 
 
-def gather_sig(keys, vals, key_bits, dist, dev):
-    """Significant k-mers of every rank's row shard -> all of them on every rank (the table the map stage probes is
-    built from the same list on every rank): one all_reduce of the sizes, two all_gathers."""
+def gather_sig(keys, vals, key_bits, dist, dev, max_rows=None):
+    """Significant k-mers of every rank's row shard -> all of them on every rank, in rank order (the probe table the
+    map stage builds from the list does not depend on the order of its keys).
+    With `max_rows` (an upper bound on any rank's list, known from the row counts already exchanged) and keys of at
+    most 56 bits: ONE all_gather of fixed-width rows — the subgenome id rides in the top byte of the key, unused slots
+    hold -1 — and no size exchange.  Otherwise: one all_reduce of the sizes and two all_gathers."""
     rank, world = dist.get_rank(), dist.get_world_size()
+    if max_rows is not None and key_bits <= 56:
+        width = max(int(max_rows), 1)
+        send = torch.full((width,), -1, dtype=torch.int64, device=dev)
+        n_mine = int(keys.numel())
+        if n_mine:
+            send[:n_mine] = keys | (vals.to(torch.int64) << 56)
+        recv = torch.empty(world * width, dtype=torch.int64, device=dev)
+        try:
+            dist.all_gather_into_tensor(recv, send)
+        except (RuntimeError, NotImplementedError, AttributeError):
+            dist.all_gather(list(recv.view(world, width).unbind(0)), send)
+        got = recv[recv != -1]
+        return (got & ((1 << 56) - 1)).contiguous(), (got >> 56).to(torch.uint8).contiguous()
     sz = torch.zeros(world, dtype=torch.int64, device=dev)
     sz[rank] = int(keys.numel())
     dist.all_reduce(sz)
@@ -291,7 +307,6 @@ def gather_sig(keys, vals, key_bits, dist, dev):
     ident = list(range(world))
     kk = _gather_concat({rank: keys.contiguous()}, m, ident, world, dist, dev, torch.int64)
     vv = _gather_concat({rank: vals.contiguous()}, m, ident, world, dist, dev, torch.uint8)
-    # (rank order, not k-mer order: the probe table built from the list does not depend on the order of its keys)
     return torch.cat([kk[r] for r in range(world)]), torch.cat([vv[r] for r in range(world)])
 
 
@@ -813,7 +828,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         sig_keys = torch.empty(0, dtype=torch.int64, device=dev)
         sig_vals = torch.empty(0, dtype=torch.uint8, device=dev)
     if world > 1:
-        sig_keys, sig_vals = gather_sig(sig_keys, sig_vals, 2 * k, dist, dev)
+        sig_keys, sig_vals = gather_sig(sig_keys, sig_vals, 2 * k, dist, dev, max_rows=max(m_rows))
     t.stop(e)
 
     # ---- K9 map ----------------------------------------------------------------------------------------

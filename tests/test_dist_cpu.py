@@ -168,3 +168,56 @@ def test_class_exchange_more_ranks_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+def _worker_sig(rank, world, port, q):
+    """gather_sig (both forms) and exchange_rows_meta: every rank ends with every rank's significant k-mers"""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from subphaser_b200 import hotpath
+    dev = torch.device("cpu")
+
+    def part(r):
+        g = torch.Generator().manual_seed(100 + r)
+        n = [0, 5, 1000, 37][r % 4]                     # (rank 0 has no significant k-mer at all)
+        return (torch.randint(0, 1 << 34, (n,), generator=g, dtype=torch.int64),
+                torch.randint(0, 3, (n,), generator=g, dtype=torch.int64).to(torch.uint8))
+
+    keys, vals = part(rank)
+    want_k = torch.cat([part(r)[0] for r in range(world)])
+    want_v = torch.cat([part(r)[1] for r in range(world)])
+    ok = True
+    for kw in (dict(max_rows=1000), dict(), dict(max_rows=1000, key_bits=60)):
+        kb = kw.pop("key_bits", 34)
+        gk, gv = hotpath.gather_sig(keys, vals, kb, dist, dev, **kw)
+        ok &= bool(torch.equal(gk, want_k) and torch.equal(gv, want_v))
+
+    class Shard:
+        n_fold_pass = 10 * (rank + 1)
+
+        def __len__(self):
+            return 3 + rank
+
+    m, n_union, n_fold = hotpath.exchange_rows_meta(Shard(), 100 + rank, dist, dev)
+    ok &= m == [3 + r for r in range(world)] and n_union == sum(100 + r for r in range(world))
+    ok &= n_fold == sum(10 * (r + 1) for r in range(world))
+    q.put((rank, ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_sig_and_row_meta_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker_sig, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(r, True) for r in range(world)]
