@@ -1,5 +1,5 @@
 import sys, os, json
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 for env in ({}, {"SPK_PACK_MODE": "single"}, {"SPK_PCOUNT_TABLE": "sweep"}, {"SPK_PMATRIX_KERNEL": "general"}, {"SPK_MAP_KERNEL": "tile"}):
     os.environ.update(env)
