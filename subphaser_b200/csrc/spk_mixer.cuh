@@ -5,7 +5,6 @@
 #include <stdint.h>
 
 constexpr uint64_t SPK_MIX_C1 = 0xff51afd7ed558ccdULL;
-constexpr uint64_t SPK_MIX_C2 = 0xc4ceb9fe1a85ec53ULL;
 
 constexpr uint64_t spk_inv64(uint64_t a) {  // multiplicative inverse of odd a modulo 2^64 (Newton)
     uint64_t x = a;
@@ -13,19 +12,21 @@ constexpr uint64_t spk_inv64(uint64_t a) {  // multiplicative inverse of odd a m
     return x;
 }
 constexpr uint64_t SPK_MIX_C1_INV = spk_inv64(SPK_MIX_C1);
-constexpr uint64_t SPK_MIX_C2_INV = spk_inv64(SPK_MIX_C2);
-static_assert(SPK_MIX_C1 * SPK_MIX_C1_INV == 1ull && SPK_MIX_C2 * SPK_MIX_C2_INV == 1ull, "inverse constants");
+static_assert(SPK_MIX_C1 * SPK_MIX_C1_INV == 1ull, "inverse constant");
 
 struct Mixer {
     uint64_t mask;  // 2k low bits
     int s;          // xorshift distance k = (2k)/2: x ^= x >> s is an involution on 2k-bit words
     int rbits;      // remainder bits = 2k - (partition / bucket bits)
+    // fold, one odd multiply, fold: the top bits of the product depend on every bit of the folded word, and the second
+    // fold carries them into the low bits the shared-memory tables are indexed with.  (Round 1 used two multiply
+    // rounds; on wheat-like and on low-complexity sequence — microsatellites, homopolymers with 2 % substitutions —
+    // partition sizes, distinct keys per partition and home-slot collisions are the same with one, and the mixer is a
+    // quarter of level 1's instructions.)
     __host__ __device__ uint64_t fwd(uint64_t u) const {
         uint64_t x = u;
         x ^= x >> s;
         x = (x * SPK_MIX_C1) & mask;
-        x ^= x >> s;
-        x = (x * SPK_MIX_C2) & mask;
         x ^= x >> s;
         return x;
     }
@@ -33,8 +34,6 @@ struct Mixer {
     // enough to spread keys over buckets when an occasional crowded bucket is handled gracefully (K9 table)
     __host__ __device__ uint64_t fwd_light(uint64_t u) const { return (u * SPK_MIX_C1) & mask; }
     __host__ __device__ uint64_t inv(uint64_t x) const {
-        x ^= x >> s;
-        x = (x * SPK_MIX_C2_INV) & mask;
         x ^= x >> s;
         x = (x * SPK_MIX_C1_INV) & mask;
         x ^= x >> s;
