@@ -697,7 +697,6 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
         n_union = len(cm)
         del cm
     shard = dm          # world > 1: this rank's rows (its partition class), ascending k-mer
-    full_side = None
     side = _SCRATCH.setdefault("side_stream", torch.cuda.Stream())
     if world > 1:
         e = t.start("exchange")
@@ -889,7 +888,7 @@ def run(chrom_inputs, labels, sgs, k, lower_count=3, min_fold=2, baseline=1, rat
     return dict(n_kmers=n_kmers_total, n_kmers_local=n_kmers, n_union=n_union, n_diff=M, n_sig=int(sig_keys.numel()),
                 n_windows=int(allw.shape[0]), labels_full=lab_full_h.tolist(), d_bs=d_bs,
                 lengths=[d.length for d in dump_list], enrich=enr, dm=dm, window_counts=allw,
-                pca=pca_host,
+                pca=pca_host, bootstrap_scores=(ari, vm),      # per-replicate ARI / V-measure against the full run (device)
                 h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes if return_host else int(allw.numel() * 8 * 4),
                 matrix_host=_matrix_host(host_copy) if return_host else None)
 
