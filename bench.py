@@ -534,6 +534,13 @@ def main():
             "stage_ms_per_rank": rank_stages,
             "results": {"n_union": res["n_union"], "n_diff": res["n_diff"], "n_sig": res["n_sig"],
                         "n_windows": n_windows, "labels": res["labels_full"]},
+            # K9 extras: positions looked up per second on this rank's GPU (live), and the L2-side
+            # utilisation of the kernel from its ncu capture (profiles/r02_map_w_key_metrics.txt; not a live number)
+            "map_extras": {"positions_per_s_per_gpu": (sum(lengths[i] for i in mine) * args.steps / (stage_ms["map"] / 1e3)
+                                                       if stage_ms.get("map") else None),
+                           "lts_throughput_pct_ncu": 51.3, "l1_to_l2_request_busy_pct_ncu": 63.2,
+                           "floor_note": "one 32-B L2 sector request per position and one request per SM cycle: "
+                                         "14.2e9 positions / (148 SMs x 1.965 GHz) = 49 ms per step"},
             "roofline": roofline, "cpu_baseline": cpu, "parity_at_scale": parity, "e2e": e2e, "e2e_dropin": dropin,
             "gpu_launches": int(launches), "clocks": clocks,
         }
