@@ -62,3 +62,24 @@ def test_group_exchanges_matches_reference_groups():
     got2 = list(Stats.group_exchanges(lines2, {"c1": "SG1"}))
     assert got2 == [["c1", 0, 10, "SG1", "SG1", 1, "no"], ["c1", 10, 20, "SG2", "SG1", 1, "yes"],
                     ["c1", 20, 30, "SG1", "SG1", 1, "no"], ["c1", 40, 50, "SG1", "SG1", 1, "no"]]
+
+
+def test_clock_sampler_summary_counts_only_samples_after_mark():
+    """bench.ClockSampler: the `clocks` object of the bench line is built from the samples of the timed region only
+    (the sampler is started before the warm-up), medians the SM clock and reports every active throttle reason."""
+    import time
+    import bench
+    s = bench.ClockSampler(0)
+    s.nvml = (None, None, 1965)            # (pretend the NVML poller is the source; nothing is started)
+    t0 = time.perf_counter()
+    s.lines = [(t0 - 5.0, "0,1200,1965,0,0x4,Not Active,Not Active,Not Active,Active"),        # warm-up: ignored
+               (t0 + 0.1, "0,1965,1965,0,0x0,Not Active,Not Active,Not Active,Not Active"),
+               (t0 + 0.3, "0,1950,1965,0,0x4,Not Active,Not Active,Not Active,Active"),
+               (t0 + 0.5, "0,1965,1965,0,0x0,Not Active,Not Active,Not Active,Not Active"),
+               (t0 + 0.7, "garbage")]
+    s.t0 = t0
+    out = s.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["source"] == "nvml"
+    s2 = bench.ClockSampler(0)
+    assert s2.stop()["reasons"] == ["unavailable"]
